@@ -1,0 +1,156 @@
+/* psmc_host.h -- host side of the B200-native `psmc` driver (plain C, like the reference).
+ *
+ * Mirrors the reference's host interface for the path around the E-step (same option letters, same
+ * .psmcfa grammar, same .psmc text), re-implemented from its behaviour:
+ *   options / header text        cli.c:142-227        -> cli.c (this directory)
+ *   pattern parser               cli.c:66-99          -> pattern.c
+ *   .psmcfa reader               cli.c:103-138, kseq.h -> psmcfa.c
+ *   params -> HMM                core.c:6-133         -> model.c   (O(N) factored form, not a dense matrix)
+ *   Hooke-Jeeves                 kmin.c:48-107        -> hj.c
+ *   EM iteration                 em.c:15-78           -> em.c      (E-step = psmc_b200_estep on the GPU)
+ *   round printer, -i reader     aux.c:49-113         -> output.c
+ *   bootstrap resampling         aux.c:8-47           -> resamp.c  (seedable)
+ *   decode printer               aux.c:129-232        -> decode.c  (posteriors from psmc_b200_decode)
+ */
+#ifndef PSMC_HOST_H
+#define PSMC_HOST_H
+
+#include <stdint.h>
+#include <stdio.h>
+#include "psmc_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSMCH_VERSION "0.6.5-r74-dirty" /* the version string consumers see (cli.c:13); ours is in MM B200 line */
+#define PSMCH_N_PARAMS 3                /* theta, rho, max_t (psmc.h:12) */
+#define PSMCH_T_INF 1000.0              /* psmc.h:14 */
+#define PSMCH_TINY 1e-25                /* khmm.h:28 */
+#define PSMCH_INF 1e300                 /* khmm.h:29 */
+
+#define PSMCH_F_DECODE 0x1
+#define PSMCH_F_FULLDEC 0x2
+#define PSMCH_F_SIMU 0x4
+#define PSMCH_F_DIVERG 0x8
+#define PSMCH_F_PROB 0x10
+
+/* ---- sequences ------------------------------------------------------------------------------ */
+typedef struct {
+	int32_t L, L_e, n_e; /* bins, non-missing bins, het bins (cli.c:118-128) */
+	signed char *seq;    /* values 0/1/2 */
+	char *name;
+} psmch_seq_t;
+
+typedef struct {
+	int n_seqs;
+	psmch_seq_t *seqs;
+	int64_t sum_L; /* sum of L_e (cli.c:133-137) */
+	int64_t sum_n; /* sum of n_e */
+} psmch_seqs_t;
+
+int  psmch_read_psmcfa(const char *fn, psmch_seqs_t *out); /* "-" = stdin; gz or plain */
+void psmch_free_seqs(psmch_seqs_t *s);
+void psmch_resample(psmch_seqs_t *s, double (*rnd)(void)); /* aux.c:8-47; rnd() in [0,1) */
+
+/* ---- parameter space and model ----------------------------------------------------------------- */
+typedef struct {
+	int n;        /* psmc's n; number of states N = n + 1 */
+	int n_free;   /* free lambdas */
+	int *par_map; /* n+1 entries */
+	char *pattern;
+	int n_params; /* n_free + 3 (+1 with the divergence parameter) */
+	int diverg;
+	double alpha0;  /* -l, default 0.1 (cli.c:151) */
+	double *inp_ti; /* time intervals from -i (n+1 values) or NULL */
+} psmch_space_t;
+
+int  psmch_parse_pattern(const char *pattern, int *n_free, int **par_map); /* returns n or -1 */
+int  psmch_space_init(psmch_space_t *sp, const char *pattern, int diverg, double alpha0);
+void psmch_space_free(psmch_space_t *sp);
+
+typedef struct {
+	int N;
+	double *params;                    /* n_params: the point the model currently describes */
+	double *t;                         /* n+2 interval boundaries */
+	double *sigma;                     /* N (also a0) */
+	double *e;                         /* 2N */
+	double *U, *V, *W, *Z, *D;         /* N each */
+	double C_pi, C_sigma;
+	double *lam, *alp, *bet, *qax, *tau; /* scratch */
+} psmch_model_t;
+
+int  psmch_model_alloc(psmch_model_t *m, const psmch_space_t *sp);
+void psmch_model_free(psmch_model_t *m);
+void psmch_model_update(const psmch_space_t *sp, const double *params, psmch_model_t *m); /* core.c:61-133 */
+void psmch_model_dense(const psmch_model_t *m, double *a /* N*N */);
+void psmch_avg_t(const psmch_space_t *sp, const psmch_model_t *m, double *avg_t);           /* core.c:135-162 */
+void psmch_model_view(const psmch_model_t *m, psmc_b200_model *v);
+
+/* ---- expected counts and the EM objective ---------------------------------------------------- */
+typedef struct {
+	int N;
+	double LL;
+	double *E;                      /* 2N */
+	double *RL, *CL, *RU, *CU, *AD; /* N each */
+	double *A;                      /* N*N dense counts or NULL */
+	double Q0;
+} psmch_counts_t;
+
+int    psmch_counts_alloc(psmch_counts_t *c, int N, int dense);
+void   psmch_counts_free(psmch_counts_t *c);
+void   psmch_counts_view(psmch_counts_t *c, psmc_b200_stats *v);
+void   psmch_counts_from_dense(psmch_counts_t *c); /* marginals of c->A */
+double psmch_Q0(psmch_counts_t *c);                 /* khmm.c:326-342; transition part needs c->A, else a marginal surrogate */
+double psmch_Q(const psmch_model_t *m, const psmch_counts_t *c); /* khmm.c:363-382 in O(N) on the factored model */
+
+/* ---- Hooke-Jeeves ---------------------------------------------------------------------------- */
+typedef double (*psmch_func_t)(int n, double *x, void *data);
+double psmch_hooke_jeeves(psmch_func_t f, int n, double *x, void *data, double r, double eps, int max_calls);
+#define PSMCH_HJ_RADIUS 0.5
+#define PSMCH_HJ_EPS 1e-7
+#define PSMCH_HJ_MAXCALL 50000
+
+/* ---- options, EM state, output ---------------------------------------------------------------- */
+typedef struct {
+	int flag, n_iters, cap_k, is_bootstrap;
+	char *pattern, *pre_fn, *in_fn, *cnt_fn;
+	FILE *fpout;
+	double max_t, tr_ratio, alpha0, ran_init, dt0;
+	double *inp_pa; /* parameters read by -i */
+	double *inp_ti;
+	/* B200 additions (long options / environment only; never change the .psmc text) */
+	int n_gpus;          /* --gpus N   [1] */
+	int devices[16];
+	long seed;           /* --seed S   [-1 = time^pid as the reference, main.c:11] */
+	int chunk_len;       /* --chunk L  [0 = auto] */
+	int verbose;         /* --verbose  timing lines on stderr */
+} psmch_opts_t;
+
+typedef struct {
+	psmch_space_t sp;
+	psmch_model_t model;
+	psmch_counts_t counts;
+	double *post_sigma;
+	double lk, Q0, Q1;
+	int n_gpus;
+	psmc_b200_ctx *ctx[16];
+	int *seq_owner; /* per sequence: which context holds it */
+	int64_t n_seqs;
+	int hj_calls;
+	double t_estep_ms, t_mstep_ms; /* wall time of the last iteration */
+} psmch_em_t;
+
+int  psmch_parse_cli(int argc, char *argv[], psmch_opts_t *o);
+void psmch_print_header(const psmch_opts_t *o, const psmch_space_t *sp, const psmch_seqs_t *sq, int stage);
+int  psmch_read_param(psmch_opts_t *o, psmch_space_t *sp); /* aux.c:84-113 */
+int  psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void));
+int  psmch_em_iterate(psmch_em_t *em, FILE *fpout); /* one psmc_em (em.c:27-78); prints the IT line */
+void psmch_em_free(psmch_em_t *em);
+void psmch_print_round(const psmch_opts_t *o, const psmch_em_t *em, const psmch_seqs_t *sq, FILE *fp); /* aux.c:49-82 */
+int  psmch_decode(const psmch_opts_t *o, psmch_em_t *em, const psmch_seqs_t *sq, FILE *fp);          /* aux.c:129-232 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+/* psmc_b200.h -- C ABI of the B200-native PSMC E-step (libpsmc_b200.so).
+ *
+ * The reference (lh3/psmc) has no plugin/FFI layer; its seam for this path is the khmm.h C API as
+ * used by exactly two call sites: psmc_em (em.c:33-55) and psmc_decode (aux.c:150-221).  The entry
+ * points below are what a maintainer binds in place of those loops.
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures.
+ *
+ * Conventions
+ *   - N = number of HMM states (= psmc_par_t::n + 1, core.c:27).  Supported on the GPU: 1 <= N <= 128.
+ *   - observation symbols: 0 = hom, 1 = het, 2 (or anything else) = missing (cli.c:15-32, khmm.c:21).
+ *   - all floating point is FP64 (khmm.h:25-27 FLOAT == double).
+ *   - every function returns 0 on success or a negative PSMC_B200_E* code; psmc_b200_last_error()
+ *     gives the message (the reference asserts/aborts instead: khmm.c:216,250,301).
+ *   - there is NO CPU fallback: if no CUDA device is usable, create() fails with PSMC_B200_ENODEV.
+ */
+#ifndef PSMC_B200_H
+#define PSMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSMC_B200_VERSION 100  /* 0.1.0 */
+
+#define PSMC_B200_EINVAL   (-1) /* bad argument */
+#define PSMC_B200_ENODEV   (-2) /* no usable CUDA device / CUDA runtime error at init */
+#define PSMC_B200_ECUDA    (-3) /* CUDA error while running */
+#define PSMC_B200_ESTRUCT  (-4) /* dense transition matrix is not diagonal + rank-1 lower + rank-1 upper (e.g. after -C, aux.c:115-127) */
+#define PSMC_B200_ENUMERIC (-5) /* non-finite value in the model or in the results */
+
+/* create() flags */
+#define PSMC_B200_F_DEFAULT 0
+
+typedef struct psmc_b200_ctx psmc_b200_ctx;
+
+/* Factored PSMC model (derived from core.c:100-125):
+ *   a[k][l] = U[k]*V[l] (l<k),  W[k]*Z[l] (l>k),  D[k] (l==k);   e[0][k], e[1][k];  a0[k].
+ * It replaces hmm_par_t (khmm.h:31-37) on this path. */
+typedef struct {
+	int32_t n_states;
+	const double *a0;  /* N      hmm_par_t::a0 (khmm.h:36) = sigma_k (core.c:123) */
+	const double *e;   /* 2*N    hmm_par_t::e rows 0 and 1 (khmm.h:34); the missing row is implicit 1.0 (khmm.c:21) */
+	const double *U, *V, *W, *Z, *D; /* N each */
+} psmc_b200_model;
+
+/* Expected counts of one E-step, summed over all sequences.  Replaces hmm_exp_t (khmm.h:49-53) as
+ * filled by hmm_expect + hmm_add_expect (khmm.c:297-359) including the per-sequence HMM_TINY
+ * initialisation (khmm.c:305-308):
+ *   E[b*N+k]      = he_sum->E[b][k], b = 0,1
+ *   RL[k] = sum_{l<k} A[k][l]   CL[l] = sum_{k>l} A[k][l]
+ *   RU[k] = sum_{l>k} A[k][l]   CU[l] = sum_{k<l} A[k][l]   AD[k] = A[k][k]
+ * which are sufficient for hmm_Q (khmm.c:363-382) under the factored model. */
+typedef struct {
+	double LL;         /* sum over sequences of hmm_lk (khmm.c:245-260, em.c:48) */
+	double *E;         /* 2*N, caller-owned */
+	double *RL, *CL, *RU, *CU, *AD; /* N each, caller-owned */
+} psmc_b200_stats;
+
+/* Layout/timing report of a context (for benchmarks and tests). */
+typedef struct {
+	int32_t device, n_states, n_states_padded, n_seqs, n_chunks, chunk_len;
+	int64_t total_bins;
+	int64_t bytes_obs, bytes_forward, bytes_transfer, bytes_total;
+	/* device time of the kernels of the LAST run, milliseconds (CUDA events on the context's stream):
+	 * [0] transfer-matrix kernel  [1] boundary-chain kernel  [2] forward kernel
+	 * [3] backward+counts kernel  [4] reduction kernel        [5] whole E-step (first launch .. last) */
+	float ms[8];
+	int32_t launches; /* kernels launched by the last run */
+} psmc_b200_info;
+
+int  psmc_b200_version(void);
+const char *psmc_b200_last_error(void);
+int  psmc_b200_device_count(void);
+
+/* Upload the sequences once (2-bit packed) and plan the chunked execution.
+ * Replaces, for the whole run, the per-iteration per-sequence hmm_new_data copies
+ * (em.c:42-44, khmm.c:37-45) and the (L+1)-row calloc of f and b (khmm.c:158-159,224).
+ *   seqs[i] points to L[i] symbols (values 0/1/2, psmc_seq_t::seq, psmc.h:22-26).
+ *   device: CUDA ordinal.  chunk_len: bins per chunk, 0 = choose automatically.
+ * Sequences are immutable afterwards (as in the reference after psmc_parse_cli/psmc_resamp). */
+int  psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *const *seqs,
+                      int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags);
+/* Same, with all sequences concatenated in one buffer (sum of L bytes). */
+int  psmc_b200_create_cat(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat,
+                          int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags);
+void psmc_b200_destroy(psmc_b200_ctx *ctx);
+
+/* One E-step: forward, backward, log-likelihood and expected counts over every sequence.
+ * Replaces em.c:33-55 (hmm_pre_backward + the loop over hmm_forward / hmm_backward / hmm_lk /
+ * hmm_expect / hmm_add_expect).  Host buffers in, host buffers out, synchronous. */
+int  psmc_b200_estep(psmc_b200_ctx *ctx, const psmc_b200_model *model, psmc_b200_stats *out);
+
+/* Same with the reference's dense hmm_par_t contents: a is N*N row-major (hmm_par_t::a), e is 2*N.
+ * The factors are extracted and verified (relative tolerance tol, e.g. 1e-9); a matrix without the
+ * PSMC structure (e.g. capped by psmc_cap_matrix, aux.c:115-127) is refused with PSMC_B200_ESTRUCT. */
+int  psmc_b200_estep_dense(psmc_b200_ctx *ctx, int32_t n_states, const double *a0, const double *a,
+                           const double *e, double tol, psmc_b200_stats *out);
+int  psmc_b200_factorize(int32_t n_states, const double *a, double tol,
+                         double *U, double *V, double *W, double *Z, double *D);
+
+/* Asynchronous halves for multi-GPU drivers (one context per GPU, sequences sharded by the caller):
+ * launch() enqueues the whole E-step on the context's stream and leaves the raw statistics vector
+ *   [ LL | E0(N) E1(N) | RL(N) CL(N) RU(N) CU(N) AD(N) ]   (7*N+1 doubles, WITHOUT the TINY terms)
+ * in device memory; device_stats() returns that device pointer (for an NCCL all-reduce);
+ * finish() copies it back, adds n_seqs_total*HMM_TINY terms and unpacks it.
+ * wait() blocks until the stream is idle. */
+int  psmc_b200_estep_launch(psmc_b200_ctx *ctx, const psmc_b200_model *model);
+void *psmc_b200_device_stats(psmc_b200_ctx *ctx);
+int  psmc_b200_stats_len(const psmc_b200_ctx *ctx);
+void *psmc_b200_stream(psmc_b200_ctx *ctx);
+int  psmc_b200_wait(psmc_b200_ctx *ctx);
+int  psmc_b200_estep_finish(psmc_b200_ctx *ctx, int64_t n_seqs_total, psmc_b200_stats *out);
+/* unpack a raw statistics vector that already lives on the host (e.g. after an all-reduce) */
+int  psmc_b200_unpack_stats(int32_t n_states, const double *raw, int64_t n_seqs_total, psmc_b200_stats *out);
+
+/* Posterior decoding of one sequence.  Replaces aux.c:157-158 (hmm_forward/hmm_backward) plus
+ * hmm_post_decode (khmm.c:264-282; aux.c:167-182) and, when post/p_recomb are non-NULL,
+ * hmm_post_state (khmm.c:286-293) and the recombination probability of aux.c:188-193.
+ *   best_k[L]: argmax_k f*b*s (first maximum wins), best_p[L]: its posterior,
+ *   model may be NULL to reuse the forward pass of the previous estep/decode call on this context.
+ *   post[L*N] (optional), p_recomb[L] (optional, 0 at the last bin), s_out[L] (optional; hmm_data_t::s, aux.c:159-164). */
+int  psmc_b200_decode(psmc_b200_ctx *ctx, const psmc_b200_model *model, int32_t seq_id,
+                      int32_t *best_k, double *best_p, double *post, double *p_recomb, double *s_out);
+
+int  psmc_b200_get_info(const psmc_b200_ctx *ctx, psmc_b200_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

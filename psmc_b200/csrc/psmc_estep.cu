@@ -1,0 +1,1228 @@
+// psmc_estep.cu -- B200 (sm_100a) E-step of the PSMC HMM behind the C ABI of include/psmc_b200.h.
+//
+// What this replaces (reference lh3/psmc): the per-iteration loop em.c:33-55 over
+// hmm_forward (khmm.c:145-190), hmm_backward (khmm.c:210-241), hmm_lk (khmm.c:245-260),
+// hmm_expect (khmm.c:297-324) and hmm_add_expect (khmm.c:346-359), and the forward/backward/posterior
+// part of psmc_decode (aux.c:150-201).  Nothing here is translated from khmm.c: the reference is a
+// dense O(N^2)-per-bin single-thread loop that materialises f and b; this is an O(N)-per-bin,
+// chunk-parallel, exact formulation for the GPU.
+//
+// Algorithm (DESIGN.md has the derivation)
+//   The PSMC transition matrix is diagonal + rank-1 strictly-lower + rank-1 strictly-upper
+//   (core.c:100-123):  a[k][l] = U_k V_l (l<k), W_k Z_l (l>k), D_k (l=k).  One forward step is
+//       f'[l] = e_x[l] * ( D_l f[l] + Z_l * sum_{k<l} W_k f[k] + V_l * sum_{k>l} U_k f[k] )
+//   i.e. two exclusive scans; one backward step is the transposed pattern.  The states of one
+//   sequence position live in the registers of a lane group (G lanes x SPL states per lane) and the
+//   scans are warp shuffles.
+//   The chain over bins is serial, so every sequence is cut into chunks and made exact again:
+//     K1 transfer : per chunk, the N x N transfer operator T_c = prod_u diag(e_{x_u}) A^T, one column
+//                   per lane group, per-column power-of-two scaling (exact).
+//     K2 chain    : per sequence, v_{c+1} = normalise(T_c v_c) left to right (exact forward vector at
+//                   every chunk start) and beta_c = T_{c+1}^T beta_{c+1} right to left (direction of
+//                   the backward vector at every chunk end).
+//     K3 forward  : one warp per chunk; scaled forward from the exact start; writes f_u (N doubles)
+//                   and the scale s_u per bin to HBM; accumulates log-likelihood.
+//     K4 backward : one warp per chunk; scaled backward from the exact end, re-reading f_u; accumulates
+//                   the emission counts E[x][k] and the five O(N) marginals of the transition counts
+//                   (RL, CL, RU, CU, AD) in registers; per-warp partials.
+//     K5 reduce   : fixed-order tree over the partials -> one statistics vector in device memory
+//                   (deterministic; this is the buffer an NCCL all-reduce would sum across GPUs).
+//   Scaling follows the reference exactly (f normalised per bin, b_u divided by s_u, khmm.c:183-184,
+//   226, 233), so gamma_u = f_u b_u s_u and xi_u = f_u a e b_{u+1} carry no extra factors.
+//
+// All arithmetic is FP64.  No tensor cores: there is no dense contraction on this path.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <math.h>
+#include <limits.h>
+#include <vector>
+#include <algorithm>
+
+#include "psmc_b200.h"
+
+#define FULLMASK 0xffffffffu
+#define HMM_TINY_ 1e-25 /* khmm.h:28 */
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+#define CUDA_TRY(call, code)                                                                     \
+	do {                                                                                         \
+		cudaError_t e_ = (call);                                                                 \
+		if (e_ != cudaSuccess)                                                                   \
+			return set_err(code, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-side layout
+// ------------------------------------------------------------------------------------------------
+struct Chunk {
+	int32_t seq;     // sequence id
+	int32_t flags;   // bit0: first chunk of its sequence, bit1: last chunk of its sequence
+	int32_t u0;      // first bin of the chunk, sequence-local
+	int32_t len;     // bins in the chunk (>= 1)
+	int64_t gb0;     // global bin index of u0 (rows of fhat / entries of sc)
+	int64_t ow0;     // first packed-observation word of the SEQUENCE (16 bins per 32-bit word)
+	int32_t Lseq;    // length of the sequence
+	int32_t pad_;
+};
+#define CH_FIRST 1
+#define CH_LAST 2
+
+// model arrays on the device, each NP doubles, contiguous: a0 e0 e1 U V W Z D
+enum { M_A0 = 0, M_E0, M_E1, M_U, M_V, M_W, M_Z, M_D, M_COUNT };
+// statistics rows: E0 E1 RL CL RU CU AD
+enum { S_E0 = 0, S_E1, S_RL, S_CL, S_RU, S_CU, S_AD, S_COUNT };
+
+// ------------------------------------------------------------------------------------------------
+// lane-group primitives: a vector of NP = G*SPL states is held by G consecutive lanes, SPL states
+// per lane (state = gl*SPL + i).  G is a power of two <= 32.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ double gscan_up(double t, int gl) // exclusive prefix over the lanes of a group
+{
+	double x = __shfl_up_sync(FULLMASK, t, 1, G);
+	if (gl == 0) x = 0.0;
+#pragma unroll
+	for (int d = 1; d < G; d <<= 1) {
+		double y = __shfl_up_sync(FULLMASK, x, d, G);
+		if (gl >= d) x += y;
+	}
+	return x;
+}
+template <int G>
+__device__ __forceinline__ double gscan_down(double t, int gl) // exclusive suffix over the lanes of a group
+{
+	double x = __shfl_down_sync(FULLMASK, t, 1, G);
+	if (gl == G - 1) x = 0.0;
+#pragma unroll
+	for (int d = 1; d < G; d <<= 1) {
+		double y = __shfl_down_sync(FULLMASK, x, d, G);
+		if (gl + d < G) x += y;
+	}
+	return x;
+}
+template <int G>
+__device__ __forceinline__ double gsum(double t) // all-reduce over the lanes of a group (same bits in every lane)
+{
+#pragma unroll
+	for (int d = G >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULLMASK, t, d, G);
+	return t;
+}
+template <int G>
+__device__ __forceinline__ int gmax_i(int t)
+{
+#pragma unroll
+	for (int d = G >> 1; d > 0; d >>= 1) t = max(t, __shfl_xor_sync(FULLMASK, t, d, G));
+	return t;
+}
+
+// out[i] = D[i] x[i] + pc[i] * sum_{j<i} pm[j] x[j] + sc[i] * sum_{j>i} sm[j] x[j]   (indices over the whole group)
+//   forward  (A^T f): pm = W, pc = Z, sm = U, sc = V
+//   backward (A g)  : pm = V, pc = U, sm = Z, sc = W
+template <int SPL, int G>
+__device__ __forceinline__ void semisep(const double (&x)[SPL], const double (&pm)[SPL], const double (&pc)[SPL],
+                                        const double (&sm)[SPL], const double (&sc)[SPL], const double (&D)[SPL],
+                                        int gl, double (&out)[SPL])
+{
+	double tp = 0.0, ts = 0.0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		tp = fma(x[i], pm[i], tp);
+		ts = fma(x[i], sm[i], ts);
+	}
+	double p = gscan_up<G>(tp, gl), s = gscan_down<G>(ts, gl);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		out[i] = fma(pc[i], p, D[i] * x[i]);
+		p = fma(x[i], pm[i], p);
+	}
+#pragma unroll
+	for (int i = SPL - 1; i >= 0; --i) {
+		out[i] = fma(sc[i], s, out[i]);
+		s = fma(x[i], sm[i], s);
+	}
+}
+
+// exclusive prefix P[i] = sum_{j<i} pm[j] x[j] and exclusive suffix S[i] = sum_{j>i} sm[j] x[j]
+template <int SPL, int G>
+__device__ __forceinline__ void prefsuf(const double (&x)[SPL], const double (&pm)[SPL], const double (&sm)[SPL],
+                                        int gl, double (&P)[SPL], double (&S)[SPL])
+{
+	double tp = 0.0, ts = 0.0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		tp = fma(x[i], pm[i], tp);
+		ts = fma(x[i], sm[i], ts);
+	}
+	double p = gscan_up<G>(tp, gl), s = gscan_down<G>(ts, gl);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		P[i] = p;
+		p = fma(x[i], pm[i], p);
+	}
+#pragma unroll
+	for (int i = SPL - 1; i >= 0; --i) {
+		S[i] = s;
+		s = fma(x[i], sm[i], s);
+	}
+}
+
+template <int SPL>
+__device__ __forceinline__ void load_vec(const double *__restrict__ p, double (&v)[SPL])
+{
+	if (SPL == 1) {
+		v[0] = __ldg(p);
+	} else {
+#pragma unroll
+		for (int i = 0; i < SPL; i += 2) {
+			double2 t = __ldg(reinterpret_cast<const double2 *>(p + i));
+			v[i] = t.x;
+			v[i + 1] = t.y;
+		}
+	}
+}
+template <int SPL>
+__device__ __forceinline__ void store_vec(double *__restrict__ p, const double (&v)[SPL])
+{
+	if (SPL == 1) {
+		p[0] = v[0];
+	} else {
+#pragma unroll
+		for (int i = 0; i < SPL; i += 2) *reinterpret_cast<double2 *>(p + i) = make_double2(v[i], v[i + 1]);
+	}
+}
+
+__device__ __forceinline__ int obs_at(const uint32_t *__restrict__ obs, int64_t ow0, int u)
+{
+	return (__ldg(obs + ow0 + (u >> 4)) >> ((u & 15) * 2)) & 3;
+}
+
+// exact power-of-two rescale helpers: k = floor(log2(x)) for a normal positive x
+__device__ __forceinline__ int exponent_of(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
+__device__ __forceinline__ double pow2i(int k) { return __hiloint2double((1023 + k) << 20, 0); } // |k| < 1022
+
+// ------------------------------------------------------------------------------------------------
+// K1: transfer operators.  grid = (n_k1_chunks, NP / COLS), block = COLS * G threads; the lane group
+// of column j pushes the unit vector e_j through every bin of the chunk.
+// T[c] is stored column-major (column j = 64 consecutive doubles), mantissas only; Tex[c][j] holds
+// the power-of-two exponent of column j.
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G, int COLS>
+__global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ chunks, const int32_t *__restrict__ k1_list,
+                                                      const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                      double *__restrict__ T, int32_t *__restrict__ Tex, int N)
+{
+	constexpr int NP = SPL * G;
+	const int c = k1_list[blockIdx.x];
+	const Chunk ch = chunks[c];
+	const int gl = threadIdx.x % G;
+	const int col = blockIdx.y * COLS + threadIdx.x / G;
+	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], f[SPL];
+	const int s0 = gl * SPL;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = model[M_U * NP + s0 + i];
+		cV[i] = model[M_V * NP + s0 + i];
+		cW[i] = model[M_W * NP + s0 + i];
+		cZ[i] = model[M_Z * NP + s0 + i];
+		cD[i] = model[M_D * NP + s0 + i];
+		e0[i] = model[M_E0 * NP + s0 + i];
+		f[i] = (s0 + i == col && col < N) ? 1.0 : 0.0;
+	}
+	int ex = 0;
+	const int uend = ch.u0 + ch.len;
+	uint32_t word = 0;
+	for (int u = ch.u0; u < uend; ++u) {
+		if (u == ch.u0 || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
+		const int x = (word >> ((u & 15) * 2)) & 3;
+		double out[SPL];
+		if (u == 0) { // first bin of the sequence: emission only (khmm.c:171-174 has no transition there)
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) out[i] = f[i];
+		} else {
+			semisep<SPL, G>(f, cW, cZ, cU, cV, cD, gl, out);
+		}
+		if (x == 0) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = out[i] * e0[i];
+		} else if (x == 1) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = out[i] * (1.0 - e0[i]);
+		} else {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = out[i];
+		}
+		if (((u - ch.u0) & 15) == 15 || u == uend - 1) { // exact power-of-two rescale of the column
+			double t = 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) t += f[i];
+			t = gsum<G>(t);
+			if (t > 1e-290 && t < 1e290) {
+				const int k = exponent_of(t);
+				const double sc = pow2i(-k);
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) f[i] *= sc;
+				ex += k;
+			}
+		}
+	}
+	double *Tc = T + (size_t)c * NP * NP + (size_t)col * NP + s0;
+	store_vec<SPL>(Tc, f);
+	if (gl == 0) Tex[(size_t)c * NP + col] = ex;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: boundary chains.  One block per (sequence, direction); blockDim = NP.
+//   dir 0: vstart[c+1] = normalise( T_c * vstart[c] ), starting from a0 at the first chunk.
+//   dir 1: bend[c] = T_{c+1}^T * bend[c+1], starting from ones at the last chunk (direction only).
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+	// NP threads, NP in {32,64,128}
+	v = gsum<32>(v);
+	if (NP > 32) {
+		__syncthreads();
+		if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+		__syncthreads();
+		double t = 0.0;
+#pragma unroll
+		for (int w = 0; w < NP / 32; ++w) t += red[w];
+		v = t;
+	}
+	return v;
+}
+template <int NP>
+__device__ __forceinline__ int block_max_i(int v, int *red)
+{
+	v = gmax_i<32>(v);
+	if (NP > 32) {
+		__syncthreads();
+		if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+		__syncthreads();
+		int t = INT_MIN;
+#pragma unroll
+		for (int w = 0; w < NP / 32; ++w) t = max(t, red[w]);
+		v = t;
+	}
+	return v;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(NP) k_chain(const int32_t *__restrict__ seq_c0, const int32_t *__restrict__ seq_nc,
+                                              const double *__restrict__ T, const int32_t *__restrict__ Tex,
+                                              const double *__restrict__ model, double *__restrict__ vstart,
+                                              double *__restrict__ bend, int n_seqs)
+{
+	__shared__ double vec[NP];
+	__shared__ double red[4];
+	__shared__ int redi[4];
+	const int seq = blockIdx.x % n_seqs, dir = blockIdx.x / n_seqs;
+	const int c0 = seq_c0[seq], nc = seq_nc[seq];
+	const int i = threadIdx.x;
+	if (nc <= 1) return;
+	if (dir == 0) {
+		double v = model[M_A0 * NP + i];
+		for (int c = c0; c < c0 + nc - 1; ++c) {
+			const double *Tc = T + (size_t)c * NP * NP;
+			const int ex = Tex[(size_t)c * NP + i];
+			int e = (v > 0.0) ? ex + ilogb(v) : INT_MIN;
+			const int emax = block_max_i<NP>(e, redi);
+			__syncthreads();
+			vec[i] = (v > 0.0) ? scalbn(v, ex - emax) : 0.0;
+			__syncthreads();
+			double acc = 0.0;
+#pragma unroll 8
+			for (int j = 0; j < NP; ++j) acc = fma(__ldg(Tc + (size_t)j * NP + i), vec[j], acc);
+			const double tot = block_sum<NP>(acc, red);
+			v = acc / tot;
+			vstart[(size_t)(c + 1) * NP + i] = v;
+		}
+	} else {
+		double b = 1.0;
+		for (int c = c0 + nc - 2; c >= c0; --c) {
+			const double *Tc = T + (size_t)(c + 1) * NP * NP + (size_t)i * NP; // column i of T_{c+1}
+			__syncthreads();
+			vec[i] = b;
+			__syncthreads();
+			double d = 0.0;
+#pragma unroll 8
+			for (int j = 0; j < NP; ++j) d = fma(__ldg(Tc + j), vec[j], d);
+			const int ex = Tex[(size_t)(c + 1) * NP + i];
+			int e = (d > 0.0) ? ex + ilogb(d) : INT_MIN;
+			const int emax = block_max_i<NP>(e, redi);
+			b = (d > 0.0) ? scalbn(d, ex - emax) : 0.0;
+			bend[(size_t)c * NP + i] = b;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: forward.  One warp per chunk (G = 32 lanes x SPL states).  Writes f_u and s_u, accumulates LL.
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
+                                                 const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                 const double *__restrict__ vstart, double *__restrict__ fhat,
+                                                 double *__restrict__ sc, double *__restrict__ llpart)
+{
+	constexpr int G = 32, NP = SPL * G;
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31;
+	const Chunk ch = chunks[c];
+	const int s0 = gl * SPL;
+	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], e1[SPL], f[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = model[M_U * NP + s0 + i];
+		cV[i] = model[M_V * NP + s0 + i];
+		cW[i] = model[M_W * NP + s0 + i];
+		cZ[i] = model[M_Z * NP + s0 + i];
+		cD[i] = model[M_D * NP + s0 + i];
+		e0[i] = model[M_E0 * NP + s0 + i];
+		e1[i] = model[M_E1 * NP + s0 + i];
+	}
+	if (ch.flags & CH_FIRST) {
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
+	} else {
+		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
+	}
+	double ll = 0.0, prod = 1.0;
+	const int uend = ch.u0 + ch.len;
+	uint32_t word = 0;
+	double *fout = fhat + (size_t)ch.gb0 * NP + s0;
+	double *sout = sc + ch.gb0;
+	for (int u = ch.u0; u < uend; ++u) {
+		if (u == ch.u0 || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
+		const int x = (word >> ((u & 15) * 2)) & 3;
+		double out[SPL];
+		if (u == 0) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) out[i] = f[i];
+		} else {
+			semisep<SPL, G>(f, cW, cZ, cU, cV, cD, gl, out);
+		}
+		double t = 0.0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			const double em = (x == 0) ? e0[i] : ((x == 1) ? e1[i] : 1.0);
+			out[i] *= em;
+			t += out[i];
+		}
+		const double s = gsum<G>(t);
+		const double inv = 1.0 / s;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) f[i] = out[i] * inv;
+		store_vec<SPL>(fout, f);
+		fout += NP;
+		if (gl == 0) *sout = s;
+		++sout;
+		prod *= s; // running product with reset, as hmm_lk (khmm.c:251-258)
+		if (prod < 1e-100 || prod > 1e100) {
+			ll += log(prod);
+			prod = 1.0;
+		}
+	}
+	ll += log(prod);
+	if (gl == 0) llpart[c] = ll;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: backward + expected counts.  One warp per chunk.  Per-warp partials: part[c][S_COUNT][NP].
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
+                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                  const double *__restrict__ bend, const double *__restrict__ fhat,
+                                                  const double *__restrict__ sc, double *__restrict__ part)
+{
+	constexpr int G = 32, NP = SPL * G, PF = 4;
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31;
+	const Chunk ch = chunks[c];
+	const int s0 = gl * SPL;
+	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], e1[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = model[M_U * NP + s0 + i];
+		cV[i] = model[M_V * NP + s0 + i];
+		cW[i] = model[M_W * NP + s0 + i];
+		cZ[i] = model[M_Z * NP + s0 + i];
+		cD[i] = model[M_D * NP + s0 + i];
+		e0[i] = model[M_E0 * NP + s0 + i];
+		e1[i] = model[M_E1 * NP + s0 + i];
+	}
+	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
+
+	const int ulast = ch.u0 + ch.len - 1;
+	const double *frow = fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + s0; // row of bin ulast
+	const double *srow = sc + ch.gb0 + (ch.len - 1);
+	double fu[SPL], b[SPL], su;
+	load_vec<SPL>(frow, fu);
+	su = __ldg(srow);
+	if (ch.flags & CH_LAST) { // khmm.c:226: b_L[k] = 1/s_L
+		const double v = 1.0 / su;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = v;
+	} else { // direction from the chain, scale fixed by sum_k f_u[k] b_u[k] s_u = 1
+		double beta[SPL], dot = 0.0;
+		load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) dot = fma(fu[i], beta[i], dot);
+		dot = gsum<G>(dot);
+		const double v = 1.0 / (su * dot);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
+	}
+	// software prefetch ring: nf[j], ns[j] hold row (u-1-j) while bin u is processed
+	double nf[PF][SPL], ns[PF];
+#pragma unroll
+	for (int j = 0; j < PF; ++j) {
+		const int uu = ulast - 1 - j;
+		if (uu >= 0) {
+			load_vec<SPL>(frow - (size_t)(1 + j) * NP, nf[j]);
+			ns[j] = __ldg(srow - (1 + j));
+		} else {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) nf[j][i] = 0.0;
+			ns[j] = 1.0;
+		}
+	}
+	uint32_t word = 0;
+	for (int u = ulast; u >= ch.u0; --u) {
+		if (u == ulast || (u & 15) == 15) word = __ldg(obs + ch.ow0 + (u >> 4));
+		const int x = (word >> ((u & 15) * 2)) & 3;
+		// emission counts: bins 0..L-2 only (khmm.c:310, 317)
+		if (u != ch.Lseq - 1) {
+			const double w0 = (x == 0) ? su : 0.0, w1 = (x == 1) ? su : 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				const double fb = fu[i] * b[i];
+				aE0[i] = fma(fb, w0, aE0[i]);
+				aE1[i] = fma(fb, w1, aE1[i]);
+			}
+		}
+		if (u == 0) break; // no transition into the first bin
+		// rotate the prefetch ring
+		double fm[SPL], sm = ns[0];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) fm[i] = nf[0][i];
+#pragma unroll
+		for (int j = 0; j + 1 < PF; ++j) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) nf[j][i] = nf[j + 1][i];
+			ns[j] = ns[j + 1];
+		}
+		{
+			const int uu = u - 1 - PF;
+			if (uu >= 0) {
+				const size_t back = (size_t)(ulast - uu);
+				load_vec<SPL>(frow - back * NP, nf[PF - 1]);
+				ns[PF - 1] = __ldg(srow - back);
+			}
+		}
+		// transition u-1 -> u (khmm.c:313-318 for the counts, khmm.c:230-234 for b_{u-1})
+		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			const double em = (x == 0) ? e0[i] : ((x == 1) ? e1[i] : 1.0);
+			g[i] = em * b[i];
+		}
+		prefsuf<SPL, G>(g, cV, cZ, gl, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
+		prefsuf<SPL, G>(fm, cW, cU, gl, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
+		const double inv = 1.0 / sm;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			aRL[i] = fma(fm[i], Pg[i], aRL[i]);
+			aRU[i] = fma(fm[i], Sg[i], aRU[i]);
+			aAD[i] = fma(fm[i], g[i], aAD[i]);
+			aCL[i] = fma(g[i], Sf[i], aCL[i]);
+			aCU[i] = fma(g[i], Pf[i], aCU[i]);
+			const double bb = fma(cU[i], Pg[i], fma(cW[i], Sg[i], cD[i] * g[i]));
+			b[i] = bb * inv;
+			fu[i] = fm[i];
+		}
+		su = sm;
+	}
+	double *po = part + (size_t)c * S_COUNT * NP + s0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		po[S_E0 * NP + i] = aE0[i];
+		po[S_E1 * NP + i] = aE1[i];
+		po[S_RL * NP + i] = aRL[i] * cU[i];
+		po[S_CL * NP + i] = aCL[i] * cV[i];
+		po[S_RU * NP + i] = aRU[i] * cW[i];
+		po[S_CU * NP + i] = aCU[i] * cZ[i];
+		po[S_AD * NP + i] = aAD[i] * cD[i];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: deterministic reduction of the per-chunk partials.
+// out layout (7*N+1 doubles): [ LL | E0(N) E1(N) | RL(N) CL(N) RU(N) CU(N) AD(N) ]
+// grid = 1 + S_COUNT*N blocks, block = 256 threads; block 0 reduces LL.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part, const double *__restrict__ llpart,
+                                                int n_chunks, int N, int NP, double *__restrict__ out)
+{
+	__shared__ double sh[256];
+	const int o = blockIdx.x;
+	double acc = 0.0;
+	if (o == 0) {
+		for (int c = threadIdx.x; c < n_chunks; c += 256) acc += llpart[c];
+	} else {
+		const int row = (o - 1) / N, k = (o - 1) % N;
+		const double *p = part + (size_t)row * NP + k;
+		for (int c = threadIdx.x; c < n_chunks; c += 256) acc += p[(size_t)c * S_COUNT * NP];
+	}
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	for (int d = 128; d > 0; d >>= 1) {
+		if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[o] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: decode backward.  One warp per chunk of ONE sequence: posterior argmax / max, optional full
+// posterior and recombination probability (aux.c:167-200, khmm.c:264-293).
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_decode(const Chunk *__restrict__ chunks, int c_first, int n_chunks_seq,
+                                                const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                const double *__restrict__ bend, const double *__restrict__ fhat,
+                                                const double *__restrict__ sc, int N, int32_t *__restrict__ best_k,
+                                                double *__restrict__ best_p, double *__restrict__ post,
+                                                double *__restrict__ p_recomb)
+{
+	constexpr int G = 32, NP = SPL * G;
+	const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (w >= n_chunks_seq) return;
+	const int c = c_first + w;
+	const int gl = threadIdx.x & 31;
+	const Chunk ch = chunks[c];
+	const int s0 = gl * SPL;
+	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], e1[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = model[M_U * NP + s0 + i];
+		cV[i] = model[M_V * NP + s0 + i];
+		cW[i] = model[M_W * NP + s0 + i];
+		cZ[i] = model[M_Z * NP + s0 + i];
+		cD[i] = model[M_D * NP + s0 + i];
+		e0[i] = model[M_E0 * NP + s0 + i];
+		e1[i] = model[M_E1 * NP + s0 + i];
+	}
+	const int ulast = ch.u0 + ch.len - 1;
+	const double *frow = fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + s0;
+	const double *srow = sc + ch.gb0 + (ch.len - 1);
+	double fu[SPL], b[SPL], su;
+	load_vec<SPL>(frow, fu);
+	su = __ldg(srow);
+	if (ch.flags & CH_LAST) {
+		const double v = 1.0 / su;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = v;
+	} else {
+		double beta[SPL], dot = 0.0;
+		load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) dot = fma(fu[i], beta[i], dot);
+		dot = gsum<G>(dot);
+		const double v = 1.0 / (su * dot);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
+	}
+	uint32_t word = 0;
+	for (int u = ulast; u >= ch.u0; --u) {
+		if (u == ulast || (u & 15) == 15) word = __ldg(obs + ch.ow0 + (u >> 4));
+		const int x = (word >> ((u & 15) * 2)) & 3;
+		// posterior of bin u: gamma[k] = f*b*s (khmm.c:274); first maximum wins
+		double gmaxv = -1.0;
+		int garg = 0x7fffffff;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			const double gm = fu[i] * b[i] * su;
+			if (s0 + i < N) {
+				if (post) post[(size_t)u * N + s0 + i] = gm;
+				if (gm > gmaxv) {
+					gmaxv = gm;
+					garg = s0 + i;
+				}
+			}
+		}
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			const double ov = __shfl_xor_sync(FULLMASK, gmaxv, d);
+			const int oa = __shfl_xor_sync(FULLMASK, garg, d);
+			if (ov > gmaxv || (ov == gmaxv && oa < garg)) {
+				gmaxv = ov;
+				garg = oa;
+			}
+		}
+		if (gl == 0) {
+			best_k[u] = garg;
+			best_p[u] = gmaxv;
+		}
+		if (u == ch.Lseq - 1 && p_recomb && gl == 0) p_recomb[u] = 0.0;
+		if (u == 0) break;
+		double fm[SPL], g[SPL], out[SPL];
+		load_vec<SPL>(frow - (size_t)(ulast - (u - 1)) * NP, fm);
+		const double sm = __ldg(srow - (ulast - (u - 1)));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			const double em = (x == 0) ? e0[i] : ((x == 1) ? e1[i] : 1.0);
+			g[i] = em * b[i];
+		}
+		if (p_recomb) { // aux.c:188-193 for bin u-1: 1 - sum_l f_{u-1}[l] a[l][l] b_u[l] e_u[l]
+			double t = 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) t = fma(fm[i] * cD[i], g[i], t);
+			t = gsum<G>(t);
+			if (gl == 0) p_recomb[u - 1] = 1.0 - t;
+		}
+		semisep<SPL, G>(g, cV, cU, cZ, cW, cD, gl, out);
+		const double inv = 1.0 / sm;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			b[i] = out[i] * inv;
+			fu[i] = fm[i];
+		}
+		su = sm;
+	}
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct psmc_b200_ctx {
+	int device = 0;
+	int N = 0, NP = 0, SPL = 0;
+	int n_seqs = 0, n_chunks = 0, chunk_len = 0, n_k1 = 0;
+	int64_t total_bins = 0;
+	std::vector<int32_t> L;        // per kept sequence
+	std::vector<int32_t> seq_c0, seq_nc;
+	std::vector<int64_t> seq_gb0;
+	std::vector<Chunk> chunks;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[8] = {};
+	// device buffers
+	uint32_t *d_obs = nullptr;
+	Chunk *d_chunks = nullptr;
+	int32_t *d_k1 = nullptr, *d_seq_c0 = nullptr, *d_seq_nc = nullptr, *d_Tex = nullptr;
+	double *d_model = nullptr, *d_fhat = nullptr, *d_sc = nullptr, *d_T = nullptr, *d_vstart = nullptr, *d_bend = nullptr;
+	double *d_part = nullptr, *d_llpart = nullptr, *d_stats = nullptr;
+	// decode scratch (allocated on demand)
+	int32_t *d_bestk = nullptr;
+	double *d_bestp = nullptr, *d_post = nullptr, *d_prec = nullptr;
+	int64_t dec_cap = 0, dec_post_cap = 0;
+	// pinned host staging
+	double *h_model = nullptr, *h_stats = nullptr;
+	int64_t bytes_obs = 0, bytes_forward = 0, bytes_transfer = 0, bytes_total = 0;
+	float ms[8] = {};
+	int launches = 0;
+	bool launched = false;
+	bool fwd_valid = false; // fhat/sc/bend hold a complete forward pass + boundary chains
+};
+
+extern "C" int psmc_b200_version(void) { return PSMC_B200_VERSION; }
+extern "C" const char *psmc_b200_last_error(void) { return g_err; }
+extern "C" int psmc_b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+static int pad_states(int N)
+{
+	if (N <= 32) return 32;
+	if (N <= 64) return 64;
+	return 128;
+}
+
+static void free_ctx(psmc_b200_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaFree(c->d_obs); cudaFree(c->d_chunks); cudaFree(c->d_k1); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
+	cudaFree(c->d_Tex); cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_T);
+	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_part); cudaFree(c->d_llpart); cudaFree(c->d_stats);
+	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
+	if (c->h_model) cudaFreeHost(c->h_model);
+	if (c->h_stats) cudaFreeHost(c->h_stats);
+	for (int i = 0; i < 8; ++i)
+		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" void psmc_b200_destroy(psmc_b200_ctx *ctx) { free_ctx(ctx); }
+
+extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *const *seqs,
+                                int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags)
+{
+	(void)flags;
+	if (!out) return set_err(PSMC_B200_EINVAL, "out is NULL");
+	*out = nullptr;
+	if (n_seqs < 0 || (n_seqs > 0 && (!L || !seqs))) return set_err(PSMC_B200_EINVAL, "bad sequence arguments");
+	if (n_states < 1 || n_states > 128) return set_err(PSMC_B200_EINVAL, "n_states=%d unsupported on the GPU path (1..128)", n_states);
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+		return set_err(PSMC_B200_ENODEV, "no CUDA device available (there is no CPU fallback)");
+	if (device < 0 || device >= ndev) return set_err(PSMC_B200_ENODEV, "device %d out of range (have %d)", device, ndev);
+	CUDA_TRY(cudaSetDevice(device), PSMC_B200_ENODEV);
+
+	psmc_b200_ctx *c = new psmc_b200_ctx();
+	c->device = device;
+	c->N = n_states;
+	c->NP = pad_states(n_states);
+	c->SPL = c->NP / 32;
+	// keep non-empty sequences only (the reference reads uninitialised memory for L == 0; nothing to count there)
+	std::vector<const signed char *> sp;
+	for (int i = 0; i < n_seqs; ++i) {
+		if (L[i] < 0) { free_ctx(c); return set_err(PSMC_B200_EINVAL, "negative sequence length"); }
+		if (L[i] == 0) continue;
+		c->L.push_back(L[i]);
+		sp.push_back(seqs[i]);
+		c->total_bins += L[i];
+	}
+	c->n_seqs = (int)c->L.size();
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device), PSMC_B200_ENODEV);
+	// chunk plan: enough chunks to fill the machine with one warp per chunk
+	if (chunk_len <= 0) {
+		const char *env = getenv("PSMC_B200_CHUNK");
+		if (env && atoi(env) > 0) chunk_len = atoi(env);
+	}
+	if (chunk_len <= 0) {
+		int wps = 16;
+		const char *env = getenv("PSMC_B200_WARPS_PER_SM");
+		if (env && atoi(env) > 0) wps = atoi(env);
+		int64_t target = (int64_t)prop.multiProcessorCount * wps;
+		int64_t cl = (c->total_bins + target - 1) / (target > 0 ? target : 1);
+		if (cl < 512) cl = 512;
+		chunk_len = (int)std::min<int64_t>(cl, 1 << 24);
+	}
+	c->chunk_len = chunk_len;
+	// packed observations: every sequence starts on a 128-byte boundary (512 bins)
+	std::vector<int64_t> ow0(c->n_seqs);
+	int64_t words = 0;
+	for (int i = 0; i < c->n_seqs; ++i) {
+		ow0[i] = words;
+		int64_t w = ((int64_t)c->L[i] + 15) / 16;
+		words += (w + 31) / 32 * 32;
+	}
+	std::vector<uint32_t> packed((size_t)std::max<int64_t>(words, 32), 0xaaaaaaaau); // padding = missing
+	for (int i = 0; i < c->n_seqs; ++i) {
+		const signed char *s = sp[i];
+		uint32_t *dst = packed.data() + ow0[i];
+		for (int u = 0; u < c->L[i]; ++u) {
+			uint32_t x = (s[u] == 0) ? 0u : ((s[u] == 1) ? 1u : 2u);
+			uint32_t &w = dst[u >> 4];
+			const int sh = (u & 15) * 2;
+			w = (w & ~(3u << sh)) | (x << sh);
+		}
+	}
+	// chunks
+	int64_t gb = 0;
+	c->seq_c0.resize(c->n_seqs); c->seq_nc.resize(c->n_seqs); c->seq_gb0.resize(c->n_seqs);
+	std::vector<int32_t> k1;
+	for (int i = 0; i < c->n_seqs; ++i) {
+		const int Li = c->L[i];
+		const int nc = (Li + chunk_len - 1) / chunk_len;
+		c->seq_c0[i] = (int)c->chunks.size();
+		c->seq_nc[i] = nc;
+		c->seq_gb0[i] = gb;
+		for (int k = 0; k < nc; ++k) {
+			Chunk ch;
+			const int64_t a = (int64_t)Li * k / nc, b = (int64_t)Li * (k + 1) / nc;
+			ch.seq = i;
+			ch.flags = (k == 0 ? CH_FIRST : 0) | (k == nc - 1 ? CH_LAST : 0);
+			ch.u0 = (int)a;
+			ch.len = (int)(b - a);
+			ch.gb0 = gb + a;
+			ch.ow0 = ow0[i];
+			ch.Lseq = Li;
+			ch.pad_ = 0;
+			if (nc > 1) k1.push_back((int)c->chunks.size());
+			c->chunks.push_back(ch);
+		}
+		gb += Li;
+	}
+	c->n_chunks = (int)c->chunks.size();
+	c->n_k1 = (int)k1.size();
+	const int NP = c->NP;
+#define ALLOC(ptr, bytes)                                                                         \
+	do {                                                                                          \
+		size_t b_ = (size_t)(bytes);                                                              \
+		if (b_ == 0) b_ = 256;                                                                    \
+		cudaError_t e_ = cudaMalloc((void **)&(ptr), b_);                                         \
+		if (e_ != cudaSuccess) {                                                                  \
+			int rc_ = set_err(PSMC_B200_ECUDA, "cudaMalloc(%zu bytes) failed: %s", b_, cudaGetErrorString(e_)); \
+			free_ctx(c);                                                                          \
+			return rc_;                                                                           \
+		}                                                                                         \
+		c->bytes_total += (int64_t)b_;                                                            \
+	} while (0)
+	c->bytes_obs = (int64_t)packed.size() * 4;
+	c->bytes_forward = c->total_bins * NP * 8 + c->total_bins * 8;
+	c->bytes_transfer = (int64_t)c->n_chunks * NP * NP * 8;
+	ALLOC(c->d_obs, c->bytes_obs);
+	ALLOC(c->d_chunks, sizeof(Chunk) * (size_t)c->n_chunks);
+	ALLOC(c->d_k1, sizeof(int32_t) * (size_t)c->n_k1);
+	ALLOC(c->d_seq_c0, sizeof(int32_t) * (size_t)c->n_seqs);
+	ALLOC(c->d_seq_nc, sizeof(int32_t) * (size_t)c->n_seqs);
+	ALLOC(c->d_model, sizeof(double) * M_COUNT * NP);
+	ALLOC(c->d_fhat, (size_t)c->total_bins * NP * 8);
+	ALLOC(c->d_sc, (size_t)c->total_bins * 8);
+	ALLOC(c->d_T, (size_t)c->bytes_transfer);
+	ALLOC(c->d_Tex, sizeof(int32_t) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_vstart, sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_bend, sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_part, sizeof(double) * (size_t)c->n_chunks * S_COUNT * NP);
+	ALLOC(c->d_llpart, sizeof(double) * (size_t)c->n_chunks);
+	ALLOC(c->d_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1));
+#undef ALLOC
+#define CTRY(call)                                                                                \
+	do {                                                                                          \
+		cudaError_t e_ = (call);                                                                  \
+		if (e_ != cudaSuccess) {                                                                  \
+			int rc_ = set_err(PSMC_B200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_));   \
+			free_ctx(c);                                                                          \
+			return rc_;                                                                           \
+		}                                                                                         \
+	} while (0)
+	CTRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 8; ++i) CTRY(cudaEventCreate(&c->ev[i]));
+	CTRY(cudaMallocHost((void **)&c->h_model, sizeof(double) * M_COUNT * NP));
+	CTRY(cudaMallocHost((void **)&c->h_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1)));
+	CTRY(cudaMemcpyAsync(c->d_obs, packed.data(), (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
+	if (c->n_chunks) CTRY(cudaMemcpyAsync(c->d_chunks, c->chunks.data(), sizeof(Chunk) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream));
+	if (c->n_k1) CTRY(cudaMemcpyAsync(c->d_k1, k1.data(), sizeof(int32_t) * (size_t)c->n_k1, cudaMemcpyHostToDevice, c->stream));
+	if (c->n_seqs) {
+		CTRY(cudaMemcpyAsync(c->d_seq_c0, c->seq_c0.data(), sizeof(int32_t) * (size_t)c->n_seqs, cudaMemcpyHostToDevice, c->stream));
+		CTRY(cudaMemcpyAsync(c->d_seq_nc, c->seq_nc.data(), sizeof(int32_t) * (size_t)c->n_seqs, cudaMemcpyHostToDevice, c->stream));
+	}
+	CTRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, c->stream));
+	CTRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, c->stream));
+	CTRY(cudaStreamSynchronize(c->stream));
+#undef CTRY
+	*out = c;
+	return 0;
+}
+
+extern "C" int psmc_b200_create_cat(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat,
+                                    int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags)
+{
+	if (n_seqs < 0 || (n_seqs > 0 && (!L || !seqs_cat))) return set_err(PSMC_B200_EINVAL, "bad sequence arguments");
+	std::vector<const signed char *> p((size_t)std::max(n_seqs, 1));
+	const signed char *q = seqs_cat;
+	for (int i = 0; i < n_seqs; ++i) {
+		p[i] = q;
+		if (L[i] > 0) q += L[i];
+	}
+	return psmc_b200_create(out, n_seqs, L, p.data(), n_states, device, chunk_len, flags);
+}
+
+static int check_model(const psmc_b200_ctx *c, const psmc_b200_model *m)
+{
+	if (!m || !m->a0 || !m->e || !m->U || !m->V || !m->W || !m->Z || !m->D) return set_err(PSMC_B200_EINVAL, "model has NULL arrays");
+	if (m->n_states != c->N) return set_err(PSMC_B200_EINVAL, "model has %d states, context has %d", m->n_states, c->N);
+	const double *arr[7] = {m->a0, m->U, m->V, m->W, m->Z, m->D, m->e};
+	for (int a = 0; a < 7; ++a)
+		for (int k = 0; k < (a == 6 ? 2 : 1) * c->N; ++k)
+			if (!isfinite(arr[a][k])) return set_err(PSMC_B200_ENUMERIC, "non-finite value in the model");
+	return 0;
+}
+
+static void stage_model(psmc_b200_ctx *c, const psmc_b200_model *m)
+{
+	const int N = c->N, NP = c->NP;
+	double *h = c->h_model;
+	memset(h, 0, sizeof(double) * M_COUNT * NP);
+	for (int k = 0; k < N; ++k) {
+		h[M_A0 * NP + k] = m->a0[k];
+		h[M_E0 * NP + k] = m->e[k];
+		h[M_E1 * NP + k] = m->e[N + k];
+		h[M_U * NP + k] = (k > 0) ? m->U[k] : 0.0;       // U_0 multiplies an empty sum
+		h[M_V * NP + k] = (k < N - 1) ? m->V[k] : 0.0;   // V_{N-1} never used
+		h[M_W * NP + k] = (k < N - 1) ? m->W[k] : 0.0;   // W_{N-1} multiplies an empty sum
+		h[M_Z * NP + k] = (k > 0) ? m->Z[k] : 0.0;       // Z_0 never used
+		h[M_D * NP + k] = m->D[k];
+	}
+}
+
+template <int SPL>
+static int launch_core(psmc_b200_ctx *c, bool with_counts)
+{
+	constexpr int NP = 32 * SPL;
+	cudaStream_t st = c->stream;
+	c->launches = 0;
+	cudaEventRecord(c->ev[0], st);
+	if (c->n_k1 > 0) {
+		constexpr int G1 = 8, SPL1 = NP / G1, COLS = 16;
+		dim3 grid((unsigned)c->n_k1, NP / COLS);
+		k_transfer<SPL1, G1, COLS><<<grid, COLS * G1, 0, st>>>(c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N);
+		++c->launches;
+	}
+	cudaEventRecord(c->ev[1], st);
+	if (c->n_k1 > 0) {
+		k_chain<NP><<<2 * c->n_seqs, NP, 0, st>>>(c->d_seq_c0, c->d_seq_nc, c->d_T, c->d_Tex, c->d_model, c->d_vstart, c->d_bend, c->n_seqs);
+		++c->launches;
+	}
+	cudaEventRecord(c->ev[2], st);
+	const int wpb = 4; // warps per block
+	const int nblk = (c->n_chunks + wpb - 1) / wpb;
+	if (c->n_chunks > 0) {
+		k_forward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, c->d_fhat, c->d_sc, c->d_llpart);
+		++c->launches;
+	}
+	cudaEventRecord(c->ev[3], st);
+	if (with_counts) {
+		if (c->n_chunks > 0) {
+			k_backward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, c->d_fhat, c->d_sc, c->d_part);
+			++c->launches;
+		}
+		cudaEventRecord(c->ev[4], st);
+		k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->N, NP, c->d_stats);
+		++c->launches;
+		cudaEventRecord(c->ev[5], st);
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+	c->fwd_valid = true;
+	return 0;
+}
+
+static int launch_dispatch(psmc_b200_ctx *c, bool with_counts)
+{
+	switch (c->SPL) {
+	case 1: return launch_core<1>(c, with_counts);
+	case 2: return launch_core<2>(c, with_counts);
+	case 4: return launch_core<4>(c, with_counts);
+	}
+	return set_err(PSMC_B200_EINVAL, "internal: bad SPL");
+}
+
+extern "C" int psmc_b200_estep_launch(psmc_b200_ctx *c, const psmc_b200_model *model)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	int rc = check_model(c, model);
+	if (rc) return rc;
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA); // pinned staging buffer is reused
+	stage_model(c, model);
+	CUDA_TRY(cudaMemcpyAsync(c->d_model, c->h_model, sizeof(double) * M_COUNT * c->NP, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	rc = launch_dispatch(c, true);
+	if (rc) return rc;
+	c->launched = true;
+	return 0;
+}
+
+extern "C" void *psmc_b200_device_stats(psmc_b200_ctx *c) { return c ? (void *)c->d_stats : nullptr; }
+extern "C" int psmc_b200_stats_len(const psmc_b200_ctx *c) { return c ? S_COUNT * c->N + 1 : 0; }
+extern "C" void *psmc_b200_stream(psmc_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+static void collect_times(psmc_b200_ctx *c, bool with_counts)
+{
+	for (int i = 0; i < 8; ++i) c->ms[i] = 0.f;
+	cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]);
+	cudaEventElapsedTime(&c->ms[1], c->ev[1], c->ev[2]);
+	cudaEventElapsedTime(&c->ms[2], c->ev[2], c->ev[3]);
+	if (with_counts) {
+		cudaEventElapsedTime(&c->ms[3], c->ev[3], c->ev[4]);
+		cudaEventElapsedTime(&c->ms[4], c->ev[4], c->ev[5]);
+		cudaEventElapsedTime(&c->ms[5], c->ev[0], c->ev[5]);
+	} else {
+		cudaEventElapsedTime(&c->ms[5], c->ev[0], c->ev[3]);
+	}
+}
+
+extern "C" int psmc_b200_wait(psmc_b200_ctx *c)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	if (c->launched) collect_times(c, true);
+	return 0;
+}
+
+extern "C" int psmc_b200_unpack_stats(int32_t N, const double *raw, int64_t n_seqs_total, psmc_b200_stats *out)
+{
+	if (!raw || !out || !out->E || !out->RL || !out->CL || !out->RU || !out->CU || !out->AD)
+		return set_err(PSMC_B200_EINVAL, "NULL output arrays");
+	for (int i = 0; i < S_COUNT * N + 1; ++i)
+		if (!isfinite(raw[i])) return set_err(PSMC_B200_ENUMERIC, "non-finite value in the E-step statistics (entry %d)", i);
+	// every sequence contributes HMM_TINY to every A[k][l] and E[b][l] (khmm.c:305-308, summed by khmm.c:346-359)
+	const double tiny = (double)n_seqs_total * HMM_TINY_;
+	out->LL = raw[0];
+	const double *p = raw + 1;
+	for (int k = 0; k < N; ++k) {
+		out->E[k] = p[S_E0 * N + k] + tiny;
+		out->E[N + k] = p[S_E1 * N + k] + tiny;
+		out->RL[k] = p[S_RL * N + k] + tiny * k;
+		out->CL[k] = p[S_CL * N + k] + tiny * (N - 1 - k);
+		out->RU[k] = p[S_RU * N + k] + tiny * (N - 1 - k);
+		out->CU[k] = p[S_CU * N + k] + tiny * k;
+		out->AD[k] = p[S_AD * N + k] + tiny;
+	}
+	return 0;
+}
+
+extern "C" int psmc_b200_estep_finish(psmc_b200_ctx *c, int64_t n_seqs_total, psmc_b200_stats *out)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (!c->launched) return set_err(PSMC_B200_EINVAL, "estep_finish without estep_launch");
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	const int n = S_COUNT * c->N + 1;
+	CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	collect_times(c, true);
+	c->launched = false;
+	if (n_seqs_total < 0) n_seqs_total = c->n_seqs;
+	return psmc_b200_unpack_stats(c->N, c->h_stats, n_seqs_total, out);
+}
+
+extern "C" int psmc_b200_estep(psmc_b200_ctx *c, const psmc_b200_model *model, psmc_b200_stats *out)
+{
+	int rc = psmc_b200_estep_launch(c, model);
+	if (rc) return rc;
+	return psmc_b200_estep_finish(c, c->n_seqs, out);
+}
+
+extern "C" int psmc_b200_factorize(int32_t N, const double *a, double tol, double *U, double *V, double *W, double *Z, double *D)
+{
+	if (N < 1 || !a || !U || !V || !W || !Z || !D) return set_err(PSMC_B200_EINVAL, "bad arguments");
+	// V = last row, Z = first row, U = column 0 / a[N-1][0], W = last column / a[0][N-1]  
+	for (int k = 0; k < N; ++k) {
+		D[k] = a[(size_t)k * N + k];
+		V[k] = a[(size_t)(N - 1) * N + k];
+		Z[k] = a[k];
+		U[k] = (N > 1) ? a[(size_t)k * N] / a[(size_t)(N - 1) * N] : 0.0;
+		W[k] = (N > 1) ? a[(size_t)k * N + N - 1] / a[N - 1] : 0.0;
+	}
+	U[0] = 0.0; W[N - 1] = 0.0; V[N - 1] = 0.0; Z[0] = 0.0;
+	for (int k = 0; k < N; ++k)
+		for (int l = 0; l < N; ++l) {
+			if (l == k) continue;
+			const double r = (l < k) ? U[k] * V[l] : W[k] * Z[l];
+			const double v = a[(size_t)k * N + l];
+			if (!(fabs(r - v) <= tol * fabs(v) + 1e-300))
+				return set_err(PSMC_B200_ESTRUCT, "transition matrix is not diagonal + rank-1 lower + rank-1 upper at (%d,%d): %g vs %g", k, l, v, r);
+		}
+	return 0;
+}
+
+extern "C" int psmc_b200_estep_dense(psmc_b200_ctx *c, int32_t N, const double *a0, const double *a, const double *e,
+                                     double tol, psmc_b200_stats *out)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (N != c->N) return set_err(PSMC_B200_EINVAL, "model has %d states, context has %d", N, c->N);
+	std::vector<double> f((size_t)5 * N);
+	int rc = psmc_b200_factorize(N, a, tol, &f[0], &f[N], &f[2 * N], &f[3 * N], &f[4 * N]);
+	if (rc) return rc;
+	psmc_b200_model m;
+	m.n_states = N; m.a0 = a0; m.e = e;
+	m.U = &f[0]; m.V = &f[N]; m.W = &f[2 * N]; m.Z = &f[3 * N]; m.D = &f[4 * N];
+	return psmc_b200_estep(c, &m, out);
+}
+
+extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, int32_t seq_id, int32_t *best_k,
+                                double *best_p, double *post, double *p_recomb, double *s_out)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (seq_id < 0 || seq_id >= c->n_seqs) return set_err(PSMC_B200_EINVAL, "seq_id out of range");
+	if (!best_k || !best_p) return set_err(PSMC_B200_EINVAL, "best_k/best_p are NULL");
+	int rc = 0;
+	if (model) {
+		rc = check_model(c, model);
+		if (rc) return rc;
+	} else if (!c->fwd_valid) {
+		return set_err(PSMC_B200_EINVAL, "decode with model == NULL needs a previous estep/decode on this context");
+	}
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	const int Ls = c->L[seq_id];
+	if (c->dec_cap < Ls) {
+		cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_prec);
+		c->d_bestk = nullptr; c->d_bestp = nullptr; c->d_prec = nullptr;
+		CUDA_TRY(cudaMalloc((void **)&c->d_bestk, sizeof(int32_t) * (size_t)Ls), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMalloc((void **)&c->d_bestp, sizeof(double) * (size_t)Ls), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMalloc((void **)&c->d_prec, sizeof(double) * (size_t)Ls), PSMC_B200_ECUDA);
+		c->dec_cap = Ls;
+	}
+	if (post && c->dec_post_cap < (int64_t)Ls * c->N) {
+		cudaFree(c->d_post); c->d_post = nullptr;
+		CUDA_TRY(cudaMalloc((void **)&c->d_post, sizeof(double) * (size_t)Ls * c->N), PSMC_B200_ECUDA);
+		c->dec_post_cap = (int64_t)Ls * c->N;
+	}
+	c->launches = 0;
+	if (model) { // forward for every sequence (the chunk plan is global); later calls may pass model == NULL to reuse it
+		stage_model(c, model);
+		CUDA_TRY(cudaMemcpyAsync(c->d_model, c->h_model, sizeof(double) * M_COUNT * c->NP, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+		rc = launch_dispatch(c, false);
+		if (rc) return rc;
+	}
+	const int c0 = c->seq_c0[seq_id], nc = c->seq_nc[seq_id];
+	const int wpb = 4, nblk = (nc + wpb - 1) / wpb;
+	// per-sequence outputs are indexed by the sequence-local bin
+	const double *fh = c->d_fhat;
+	const double *scp = c->d_sc;
+	switch (c->SPL) {
+	case 1: k_decode<1><<<nblk, wpb * 32, 0, c->stream>>>(c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
+	case 2: k_decode<2><<<nblk, wpb * 32, 0, c->stream>>>(c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
+	case 4: k_decode<4><<<nblk, wpb * 32, 0, c->stream>>>(c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
+	}
+	++c->launches;
+	CUDA_TRY(cudaGetLastError(), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemcpyAsync(best_k, c->d_bestk, sizeof(int32_t) * (size_t)Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemcpyAsync(best_p, c->d_bestp, sizeof(double) * (size_t)Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	if (post) CUDA_TRY(cudaMemcpyAsync(post, c->d_post, sizeof(double) * (size_t)Ls * c->N, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	if (p_recomb) CUDA_TRY(cudaMemcpyAsync(p_recomb, c->d_prec, sizeof(double) * (size_t)Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	if (s_out) CUDA_TRY(cudaMemcpyAsync(s_out, c->d_sc + c->seq_gb0[seq_id], sizeof(double) * (size_t)Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	if (model) collect_times(c, false);
+	return 0;
+}
+
+extern "C" int psmc_b200_get_info(const psmc_b200_ctx *c, psmc_b200_info *info)
+{
+	if (!c || !info) return set_err(PSMC_B200_EINVAL, "NULL argument");
+	memset(info, 0, sizeof(*info));
+	info->device = c->device;
+	info->n_states = c->N;
+	info->n_states_padded = c->NP;
+	info->n_seqs = c->n_seqs;
+	info->n_chunks = c->n_chunks;
+	info->chunk_len = c->chunk_len;
+	info->total_bins = c->total_bins;
+	info->bytes_obs = c->bytes_obs;
+	info->bytes_forward = c->bytes_forward;
+	info->bytes_transfer = c->bytes_transfer;
+	info->bytes_total = c->bytes_total;
+	for (int i = 0; i < 8; ++i) info->ms[i] = c->ms[i];
+	info->launches = c->launches;
+	return 0;
+}

@@ -1,0 +1,137 @@
+"""GPU parity of the E-step (include/psmc_b200.h) against the CPU oracle, through the C ABI.
+
+Bar: FP64 relative 1e-10 on LL and on every expected count (north_star asks 1e-6 on the printed
+LK/TR/RS values; the E-step itself is held to a much tighter bound so EM trajectories stay together)."""
+import numpy as np
+import pytest
+
+from helpers import compare_stats, make_model, oracle_stats
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def _model(m):
+    from psmc_b200 import Model
+    return Model.from_dense(m["a0"], m["a"], m["e"])
+
+
+def _seqs(m, lengths, seed):
+    from psmc_b200 import synth
+    return synth.simulate_genome(m["a0"], m["a"], m["e"], lengths, seed, miss_frac=0.03, miss_mean=20)
+
+
+@pytest.mark.parametrize("N", [5, 23, 33, 64, 100])
+@pytest.mark.parametrize("chunk_len", [7, 64, 1 << 20])
+def test_estep_matches_oracle_ragged(oracle, N, chunk_len):
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=N)
+    seqs = _seqs(m, [1, 2, 3, 17, 300, 1000, 2049, 64, 128], seed=100 + N)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=chunk_len) as es:
+        got = es.run(_model(m))
+        info = es.info()
+    assert info["n_seqs"] == len(seqs)
+    compare_stats(got, want, TOL, N)
+
+
+def test_chunking_is_exact(oracle):
+    """the chunk plan must not change the result (it does for the reference's splitfa, which cuts the likelihood)"""
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=3)
+    seqs = _seqs(m, [5000, 1234], seed=9)
+    res = []
+    for cl in (1 << 20, 1000, 97, 16, 5):
+        with EStep(seqs, N, chunk_len=cl) as es:
+            res.append(es.run(_model(m)))
+    for r in res[1:]:
+        compare_stats(r, res[0], 1e-11, N)
+
+
+def test_estep_dense_entry_and_structure_check(oracle):
+    from psmc_b200 import EStep, Psmc200Error
+    N = 23
+    m = make_model(oracle, N, seed=1)
+    seqs = _seqs(m, [700, 300], seed=2)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=128) as es:
+        got = es.run_dense(m["a0"], m["a"], m["e"])
+        compare_stats(got, want, TOL, N)
+        capped = m["a"].copy()          # psmc_cap_matrix (aux.c:115-127) destroys the rank structure
+        capped[:, 10] = capped[:, 10:].sum(axis=1); capped[:, 11:] = 0
+        with pytest.raises(Psmc200Error) as ei:
+            es.run_dense(m["a0"], capped, m["e"])
+        assert ei.value.code == -4
+
+
+def test_missing_only_and_all_hom(oracle):
+    from psmc_b200 import EStep
+    N = 23
+    m = make_model(oracle, N, seed=5)
+    seqs = [np.full(500, 2, dtype=np.int8), np.zeros(700, dtype=np.int8), np.ones(40, dtype=np.int8)]
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=50) as es:
+        got = es.run(_model(m))
+    compare_stats(got, want, TOL, N)
+
+
+def test_empty_sequences_are_skipped(oracle):
+    from psmc_b200 import EStep
+    N = 23
+    m = make_model(oracle, N, seed=6)
+    seqs = _seqs(m, [400], seed=1)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep([np.zeros(0, dtype=np.int8), seqs[0], np.zeros(0, dtype=np.int8)], N, chunk_len=100) as es:
+        got = es.run(_model(m))
+        assert es.info()["n_seqs"] == 1
+    compare_stats(got, want, TOL, N)
+
+
+def test_medium_contig_auto_chunks(oracle):
+    """200k bins, 64 states, automatic chunk plan (the oracle needs a few seconds for this)"""
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=11)
+    seqs = _seqs(m, [150000, 50000], seed=12)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N) as es:
+        got = es.run(_model(m))
+        info = es.info()
+    assert info["n_chunks"] >= 2
+    compare_stats(got, want, TOL, N)
+
+
+def test_repeatable_bitwise(oracle):
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=2)
+    seqs = _seqs(m, [30000], seed=3)
+    with EStep(seqs, N, chunk_len=1000) as es:
+        a = es.run(_model(m)); b = es.run(_model(m))
+    assert a["LL"] == b["LL"]
+    for k in ("E", "RL", "CL", "RU", "CU", "AD"):
+        assert np.array_equal(a[k], b[k])
+
+
+@pytest.mark.parametrize("N", [23, 64])
+def test_decode_matches_oracle(oracle, N):
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=21)
+    seqs = _seqs(m, [3000, 555], seed=22)
+    with EStep(seqs, N, chunk_len=200) as es:
+        mod = _model(m)
+        for i, s in enumerate(seqs):
+            got = es.decode(mod if i == 0 else None, i, full=True, want_s=True)
+            want = oracle.decode(m["a"], m["e"], m["a0"], s, full=True)
+            f, b, sc = oracle.fwdbwd(m["a"], m["e"], m["a0"], s)
+            assert np.max(np.abs(got["s"] / sc - 1)) < 1e-11
+            assert np.max(np.abs(got["post"] - want["post"])) < 1e-11
+            assert np.max(np.abs(got["p_recomb"] - want["p_recomb"])) < 1e-10
+            assert np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
+            # argmax may legitimately differ only where two posteriors tie to ~1e-11
+            diff = got["best_k"] != want["best_k"]
+            if diff.any():
+                srt = np.sort(want["post"][diff], axis=1)
+                assert np.all(srt[:, -1] - srt[:, -2] < 1e-10)
