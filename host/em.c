@@ -1,0 +1,190 @@
+/* em.c -- one EM iteration around the GPU E-step.  Control flow of psmc_em (em.c:27-78):
+ *   E-step over every sequence  (em.c:33-55)   -> psmc_b200_estep*  (one context per GPU, contigs sharded)
+ *   Q0 offset, LK, Q before      (em.c:59-64)
+ *   Hooke-Jeeves on -Q           (em.c:15-25,65) -> O(N) model update + O(N) objective per trial point
+ *   IT line, posterior sigma     (em.c:66-74)
+ * Reproduced quirks: the objective sees |x| (em.c:22); after the search the model is left at the LAST
+ * EVALUATED trial point, not at the optimum (em.c:61-67 frees the optimum without copying it back). */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <time.h>
+#include "psmc_host.h"
+
+static double now_ms(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+typedef struct { psmch_em_t *em; int cnt; } aux_t;
+
+static double objective(int n, double *x, void *data)
+{
+	aux_t *a = (aux_t*)data;
+	psmch_em_t *em = a->em;
+	int i;
+	++a->cnt;
+	for (i = 0; i < n; ++i) em->model.params[i] = fabs(x[i]);
+	psmch_model_update(&em->sp, em->model.params, &em->model);
+	return -psmch_Q(&em->model, &em->counts);
+}
+
+int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void))
+{
+	int k, g, i, rc;
+	const char *pattern = o->pattern ? o->pattern : "4+5*3+4";
+	memset(em, 0, sizeof(*em));
+	if (psmch_space_init(&em->sp, pattern, (o->flag & PSMCH_F_DIVERG) ? 1 : 0, o->alpha0) < 0) {
+		fprintf(stderr, "psmc: bad pattern '%s'\n", pattern);
+		return -1;
+	}
+	if (o->inp_ti) {
+		em->sp.inp_ti = (double*)malloc(sizeof(double) * (em->sp.n + 1));
+		memcpy(em->sp.inp_ti, o->inp_ti, sizeof(double) * (em->sp.n + 1));
+	}
+	if (psmch_model_alloc(&em->model, &em->sp) < 0 || psmch_counts_alloc(&em->counts, em->sp.n + 1, 0) < 0) return -1;
+	em->post_sigma = (double*)calloc(em->sp.n + 1, sizeof(double));
+	/* initial parameters (core.c:32-49) */
+	if (o->inp_pa) {
+		memcpy(em->model.params, o->inp_pa, sizeof(double) * em->sp.n_params);
+	} else {
+		const double theta = -log(1.0 - (double)sq->sum_n / sq->sum_L);
+		em->model.params[0] = theta;
+		em->model.params[1] = theta / o->tr_ratio;
+		em->model.params[2] = o->max_t;
+		for (k = PSMCH_N_PARAMS; k < em->sp.n_free + PSMCH_N_PARAMS; ++k) {
+			em->model.params[k] = 1.0 + (rnd() * 2.0 - 1.0) * o->ran_init;
+			if (em->model.params[k] < 0.1) em->model.params[k] = 0.1;
+		}
+		if (em->sp.diverg) em->model.params[em->sp.n_params - 1] = o->dt0;
+	}
+	psmch_model_update(&em->sp, em->model.params, &em->model);
+	/* shard whole sequences over the GPUs: longest-processing-time first */
+	em->n_gpus = o->n_gpus;
+	em->n_seqs = sq->n_seqs;
+	em->seq_owner = (int*)calloc(sq->n_seqs > 0 ? sq->n_seqs : 1, sizeof(int));
+	{
+		int *order = (int*)malloc(sizeof(int) * (sq->n_seqs > 0 ? sq->n_seqs : 1)), j;
+		int64_t load[16] = {0};
+		for (i = 0; i < sq->n_seqs; ++i) order[i] = i;
+		for (i = 1; i < sq->n_seqs; ++i) { /* insertion sort by length, descending, stable */
+			int v = order[i];
+			for (j = i - 1; j >= 0 && sq->seqs[order[j]].L < sq->seqs[v].L; --j) order[j + 1] = order[j];
+			order[j + 1] = v;
+		}
+		for (i = 0; i < sq->n_seqs; ++i) {
+			int best = 0;
+			for (g = 1; g < em->n_gpus; ++g)
+				if (load[g] < load[best]) best = g;
+			em->seq_owner[order[i]] = best;
+			load[best] += sq->seqs[order[i]].L;
+		}
+		free(order);
+	}
+	for (g = 0; g < em->n_gpus; ++g) {
+		int32_t *L = (int32_t*)malloc(sizeof(int32_t) * (sq->n_seqs > 0 ? sq->n_seqs : 1)), ns = 0;
+		const signed char **ptr = (const signed char**)malloc(sizeof(void*) * (sq->n_seqs > 0 ? sq->n_seqs : 1));
+		for (i = 0; i < sq->n_seqs; ++i)
+			if (em->seq_owner[i] == g) { L[ns] = sq->seqs[i].L; ptr[ns] = sq->seqs[i].seq; ++ns; }
+		rc = psmc_b200_create(&em->ctx[g], ns, L, ptr, em->sp.n + 1, o->devices[g], o->chunk_len, 0);
+		free(L); free(ptr);
+		if (rc != 0) {
+			fprintf(stderr, "psmc: GPU E-step unavailable on device %d: %s\n", o->devices[g], psmc_b200_last_error());
+			return -1;
+		}
+	}
+	return 0;
+}
+
+void psmch_em_free(psmch_em_t *em)
+{
+	int g;
+	for (g = 0; g < em->n_gpus; ++g) psmc_b200_destroy(em->ctx[g]);
+	psmch_counts_free(&em->counts);
+	psmch_model_free(&em->model);
+	psmch_space_free(&em->sp);
+	free(em->post_sigma); free(em->seq_owner);
+	memset(em, 0, sizeof(*em));
+}
+
+/* E-step on all GPUs: enqueue everywhere, then sum the raw statistic vectors in device order
+ * (a fixed order keeps 1-GPU and N-GPU runs reproducible; the Python multi-process driver does the
+ * same sum with one NCCL all-reduce per iteration). */
+static int estep_all(psmch_em_t *em)
+{
+	const int N = em->sp.n + 1, len = 7 * N + 1;
+	psmc_b200_model mv;
+	psmc_b200_stats sv;
+	int g, i, rc;
+	psmch_model_view(&em->model, &mv);
+	psmch_counts_view(&em->counts, &sv);
+	if (em->n_gpus == 1) {
+		rc = psmc_b200_estep(em->ctx[0], &mv, &sv);
+		if (rc) return rc;
+	} else {
+		double *tot = (double*)calloc(len, sizeof(double)), *raw = (double*)malloc(sizeof(double) * len);
+		for (g = 0; g < em->n_gpus; ++g)
+			if ((rc = psmc_b200_estep_launch(em->ctx[g], &mv)) != 0) { free(tot); free(raw); return rc; }
+		for (g = 0; g < em->n_gpus; ++g) {
+			if ((rc = psmc_b200_estep_fetch_raw(em->ctx[g], raw)) != 0) { free(tot); free(raw); return rc; }
+			for (i = 0; i < len; ++i) tot[i] += raw[i];
+		}
+		rc = psmc_b200_unpack_stats(N, tot, em->n_seqs, &sv);
+		free(tot); free(raw);
+		if (rc) return rc;
+	}
+	em->counts.LL = sv.LL;
+	return 0;
+}
+
+int psmch_em_estep(psmch_em_t *em)
+{
+	double t0 = now_ms();
+	int rc = estep_all(em);
+	if (rc != 0) fprintf(stderr, "psmc: E-step failed: %s\n", psmc_b200_last_error());
+	em->t_estep_ms = now_ms() - t0;
+	return rc;
+}
+
+/* install an already reduced raw statistics vector (multi-process drivers: NCCL all-reduce outside) */
+int psmch_em_set_raw(psmch_em_t *em, const double *raw, int64_t n_seqs_total)
+{
+	psmc_b200_stats sv;
+	int rc;
+	psmch_counts_view(&em->counts, &sv);
+	rc = psmc_b200_unpack_stats(em->sp.n + 1, raw, n_seqs_total, &sv);
+	if (rc == 0) em->counts.LL = sv.LL;
+	return rc;
+}
+
+/* maximisation on the counts currently in em->counts (em.c:56-74) */
+int psmch_em_mstep(psmch_em_t *em, FILE *fpout)
+{
+	const int N = em->sp.n + 1, np = em->sp.n_params;
+	double *x, sum = 0.0, t1 = now_ms();
+	aux_t aux;
+	int k;
+	psmch_Q0(&em->counts);
+	em->lk = em->counts.LL;
+	x = (double*)malloc(sizeof(double) * np);
+	memcpy(x, em->model.params, sizeof(double) * np);
+	aux.em = em; aux.cnt = 0;
+	em->Q0 = psmch_Q(&em->model, &em->counts);
+	em->Q1 = -psmch_hooke_jeeves(objective, np, x, &aux, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL);
+	em->hj_calls = aux.cnt;
+	if (fpout) fprintf(fpout, "IT\t%d\n", aux.cnt);
+	free(x);
+	for (k = 0; k < N; ++k) sum += em->counts.E[k] + em->counts.E[N + k];
+	for (k = 0; k < N; ++k) em->post_sigma[k] = (em->counts.E[k] + em->counts.E[N + k]) / sum;
+	em->t_mstep_ms = now_ms() - t1;
+	return 0;
+}
+
+int psmch_em_iterate(psmch_em_t *em, FILE *fpout)
+{
+	int rc = psmch_em_estep(em);
+	if (rc != 0) return rc;
+	return psmch_em_mstep(em, fpout);
+}

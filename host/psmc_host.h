@@ -146,6 +146,9 @@ void psmch_print_header(const psmch_opts_t *o, const psmch_space_t *sp, const ps
 int  psmch_read_param(psmch_opts_t *o, psmch_space_t *sp); /* aux.c:84-113 */
 int  psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void));
 int  psmch_em_iterate(psmch_em_t *em, FILE *fpout); /* one psmc_em (em.c:27-78); prints the IT line */
+int  psmch_em_estep(psmch_em_t *em);                 /* em.c:33-55 on the GPU(s) */
+int  psmch_em_set_raw(psmch_em_t *em, const double *raw, int64_t n_seqs_total);
+int  psmch_em_mstep(psmch_em_t *em, FILE *fpout);    /* em.c:56-74 */
 void psmch_em_free(psmch_em_t *em);
 void psmch_print_round(const psmch_opts_t *o, const psmch_em_t *em, const psmch_seqs_t *sq, FILE *fp); /* aux.c:49-82 */
 int  psmch_decode(const psmch_opts_t *o, psmch_em_t *em, const psmch_seqs_t *sq, FILE *fp);          /* aux.c:129-232 */

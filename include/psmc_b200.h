@@ -86,6 +86,11 @@ int  psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, con
 int  psmc_b200_create_cat(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat,
                           int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags);
 void psmc_b200_destroy(psmc_b200_ctx *ctx);
+/* Re-upload the observation tracks (same number of sequences and the same lengths as at create) from
+ * host memory into the existing device buffers: pack to 2 bits/bin and one host->device copy.  This is
+ * the per-call input transfer of a psmc_em-style call that owns only host buffers (em.c:42-44). */
+int  psmc_b200_upload(psmc_b200_ctx *ctx, int32_t n_seqs, const int32_t *L, const signed char *const *seqs);
+int  psmc_b200_upload_cat(psmc_b200_ctx *ctx, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat);
 
 /* One E-step: forward, backward, log-likelihood and expected counts over every sequence.
  * Replaces em.c:33-55 (hmm_pre_backward + the loop over hmm_forward / hmm_backward / hmm_lk /
@@ -112,6 +117,8 @@ int  psmc_b200_stats_len(const psmc_b200_ctx *ctx);
 void *psmc_b200_stream(psmc_b200_ctx *ctx);
 int  psmc_b200_wait(psmc_b200_ctx *ctx);
 int  psmc_b200_estep_finish(psmc_b200_ctx *ctx, int64_t n_seqs_total, psmc_b200_stats *out);
+/* wait for launch() and copy the raw 7*N+1 statistics vector to the host (for a host-side sum over GPUs) */
+int  psmc_b200_estep_fetch_raw(psmc_b200_ctx *ctx, double *raw);
 /* unpack a raw statistics vector that already lives on the host (e.g. after an all-reduce) */
 int  psmc_b200_unpack_stats(int32_t n_states, const double *raw, int64_t n_seqs_total, psmc_b200_stats *out);
 

@@ -44,6 +44,8 @@ SYMBOLS = {
     "psmc_b200_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _ip, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_uint32]),
     "psmc_b200_create_cat": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _ip, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32]),
     "psmc_b200_destroy": (None, [C.c_void_p]),
+    "psmc_b200_upload": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.POINTER(C.c_void_p)]),
+    "psmc_b200_upload_cat": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.c_void_p]),
     "psmc_b200_estep": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.POINTER(CStats)]),
     "psmc_b200_estep_dense": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_double, C.POINTER(CStats)]),
     "psmc_b200_factorize": (C.c_int, [C.c_int32, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp]),
@@ -53,6 +55,7 @@ SYMBOLS = {
     "psmc_b200_stream": (C.c_void_p, [C.c_void_p]),
     "psmc_b200_wait": (C.c_int, [C.c_void_p]),
     "psmc_b200_estep_finish": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(CStats)]),
+    "psmc_b200_estep_fetch_raw": (C.c_int, [C.c_void_p, _dp]),
     "psmc_b200_unpack_stats": (C.c_int, [C.c_int32, _dp, C.c_int64, C.POINTER(CStats)]),
     "psmc_b200_decode": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.c_int32, _ip, _dp, _dp, _dp, _dp]),
     "psmc_b200_get_info": (C.c_int, [C.c_void_p, C.POINTER(CInfo)]),

@@ -42,6 +42,7 @@
 #include <limits.h>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 #include "psmc_b200.h"
 
@@ -739,6 +740,9 @@ struct psmc_b200_ctx {
 	int64_t dec_cap = 0, dec_post_cap = 0;
 	// pinned host staging
 	double *h_model = nullptr, *h_stats = nullptr;
+	uint32_t *h_obs = nullptr; // packed observations (pinned), words_obs 32-bit words
+	int64_t words_obs = 0;
+	std::vector<int64_t> seq_ow0;
 	int64_t bytes_obs = 0, bytes_forward = 0, bytes_transfer = 0, bytes_total = 0;
 	float ms[8] = {};
 	int launches = 0;
@@ -772,6 +776,7 @@ static void free_ctx(psmc_b200_ctx *c)
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
 	if (c->h_model) cudaFreeHost(c->h_model);
 	if (c->h_stats) cudaFreeHost(c->h_stats);
+	if (c->h_obs) cudaFreeHost(c->h_obs);
 	for (int i = 0; i < 8; ++i)
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -779,6 +784,44 @@ static void free_ctx(psmc_b200_ctx *c)
 }
 
 extern "C" void psmc_b200_destroy(psmc_b200_ctx *ctx) { free_ctx(ctx); }
+
+// 2 bits per bin, 16 bins per word, little end first; every sequence starts on a 128-byte boundary.
+// Symbols: 0 hom, 1 het, everything else missing (cli.c:15-32 maps to {0,1,2}).
+static void pack_range(const signed char *s, int64_t u0, int64_t u1, uint32_t *dst)
+{
+	for (int64_t w = u0 >> 4; w < (u1 + 15) >> 4; ++w) {
+		const int64_t b0 = w << 4, b1 = std::min<int64_t>(b0 + 16, u1);
+		uint32_t v = 0xaaaaaaaau; // padding = missing
+		for (int64_t u = b0; u < b1; ++u) {
+			const uint32_t x = (uint8_t)s[u];
+			const int sh = (int)(u - b0) * 2;
+			v = (v & ~(3u << sh)) | ((x > 1u ? 2u : x) << sh);
+		}
+		dst[w] = v;
+	}
+}
+static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
+{
+	for (int64_t w = 0; w < c->words_obs; ++w) c->h_obs[w] = 0xaaaaaaaau;
+	struct Job { const signed char *s; int64_t u0, u1; uint32_t *dst; };
+	std::vector<Job> jobs;
+	const int64_t step = 1 << 20; // multiple of 16
+	for (int i = 0; i < c->n_seqs; ++i)
+		for (int64_t u = 0; u < c->L[i]; u += step)
+			jobs.push_back({sp[i], u, std::min<int64_t>(u + step, c->L[i]), c->h_obs + c->seq_ow0[i]});
+	unsigned nt = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+	if (jobs.size() < 4) nt = 1;
+	if (nt == 1) {
+		for (auto &j : jobs) pack_range(j.s, j.u0, j.u1, j.dst);
+	} else {
+		std::vector<std::thread> th;
+		for (unsigned t = 0; t < nt; ++t)
+			th.emplace_back([&jobs, t, nt]() {
+				for (size_t k = t; k < jobs.size(); k += nt) pack_range(jobs[k].s, jobs[k].u0, jobs[k].u1, jobs[k].dst);
+			});
+		for (auto &x : th) x.join();
+	}
+}
 
 extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *const *seqs,
                                 int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags)
@@ -827,24 +870,15 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	}
 	c->chunk_len = chunk_len;
 	// packed observations: every sequence starts on a 128-byte boundary (512 bins)
-	std::vector<int64_t> ow0(c->n_seqs);
+	std::vector<int64_t> &ow0 = c->seq_ow0;
+	ow0.resize(c->n_seqs);
 	int64_t words = 0;
 	for (int i = 0; i < c->n_seqs; ++i) {
 		ow0[i] = words;
 		int64_t w = ((int64_t)c->L[i] + 15) / 16;
 		words += (w + 31) / 32 * 32;
 	}
-	std::vector<uint32_t> packed((size_t)std::max<int64_t>(words, 32), 0xaaaaaaaau); // padding = missing
-	for (int i = 0; i < c->n_seqs; ++i) {
-		const signed char *s = sp[i];
-		uint32_t *dst = packed.data() + ow0[i];
-		for (int u = 0; u < c->L[i]; ++u) {
-			uint32_t x = (s[u] == 0) ? 0u : ((s[u] == 1) ? 1u : 2u);
-			uint32_t &w = dst[u >> 4];
-			const int sh = (u & 15) * 2;
-			w = (w & ~(3u << sh)) | (x << sh);
-		}
-	}
+	c->words_obs = std::max<int64_t>(words, 32);
 	// chunks
 	int64_t gb = 0;
 	c->seq_c0.resize(c->n_seqs); c->seq_nc.resize(c->n_seqs); c->seq_gb0.resize(c->n_seqs);
@@ -886,7 +920,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		}                                                                                         \
 		c->bytes_total += (int64_t)b_;                                                            \
 	} while (0)
-	c->bytes_obs = (int64_t)packed.size() * 4;
+	c->bytes_obs = c->words_obs * 4;
 	c->bytes_forward = c->total_bins * NP * 8 + c->total_bins * 8;
 	c->bytes_transfer = (int64_t)c->n_chunks * NP * NP * 8;
 	ALLOC(c->d_obs, c->bytes_obs);
@@ -918,7 +952,9 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	for (int i = 0; i < 8; ++i) CTRY(cudaEventCreate(&c->ev[i]));
 	CTRY(cudaMallocHost((void **)&c->h_model, sizeof(double) * M_COUNT * NP));
 	CTRY(cudaMallocHost((void **)&c->h_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1)));
-	CTRY(cudaMemcpyAsync(c->d_obs, packed.data(), (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
+	CTRY(cudaMallocHost((void **)&c->h_obs, (size_t)c->bytes_obs));
+	pack_all(c, sp.data());
+	CTRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
 	if (c->n_chunks) CTRY(cudaMemcpyAsync(c->d_chunks, c->chunks.data(), sizeof(Chunk) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream));
 	if (c->n_k1) CTRY(cudaMemcpyAsync(c->d_k1, k1.data(), sizeof(int32_t) * (size_t)c->n_k1, cudaMemcpyHostToDevice, c->stream));
 	if (c->n_seqs) {
@@ -944,6 +980,38 @@ extern "C" int psmc_b200_create_cat(psmc_b200_ctx **out, int32_t n_seqs, const i
 		if (L[i] > 0) q += L[i];
 	}
 	return psmc_b200_create(out, n_seqs, L, p.data(), n_states, device, chunk_len, flags);
+}
+
+extern "C" int psmc_b200_upload(psmc_b200_ctx *c, int32_t n_seqs, const int32_t *L, const signed char *const *seqs)
+{
+	if (!c || (n_seqs > 0 && (!L || !seqs))) return set_err(PSMC_B200_EINVAL, "NULL argument");
+	std::vector<const signed char *> sp;
+	int k = 0;
+	for (int i = 0; i < n_seqs; ++i) {
+		if (L[i] == 0) continue;
+		if (k >= c->n_seqs || L[i] != c->L[k]) return set_err(PSMC_B200_EINVAL, "upload: sequence lengths differ from the ones the context was created with");
+		sp.push_back(seqs[i]);
+		++k;
+	}
+	if (k != c->n_seqs) return set_err(PSMC_B200_EINVAL, "upload: %d sequences given, context holds %d", k, c->n_seqs);
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	pack_all(c, sp.data());
+	CUDA_TRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	c->fwd_valid = false;
+	return 0;
+}
+
+extern "C" int psmc_b200_upload_cat(psmc_b200_ctx *c, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat)
+{
+	if (n_seqs < 0 || (n_seqs > 0 && (!L || !seqs_cat))) return set_err(PSMC_B200_EINVAL, "bad sequence arguments");
+	std::vector<const signed char *> p((size_t)std::max(n_seqs, 1));
+	const signed char *q = seqs_cat;
+	for (int i = 0; i < n_seqs; ++i) {
+		p[i] = q;
+		if (L[i] > 0) q += L[i];
+	}
+	return psmc_b200_upload(c, n_seqs, L, p.data());
 }
 
 static int check_model(const psmc_b200_ctx *c, const psmc_b200_model *m)
@@ -1103,6 +1171,20 @@ extern "C" int psmc_b200_estep_finish(psmc_b200_ctx *c, int64_t n_seqs_total, ps
 	c->launched = false;
 	if (n_seqs_total < 0) n_seqs_total = c->n_seqs;
 	return psmc_b200_unpack_stats(c->N, c->h_stats, n_seqs_total, out);
+}
+
+extern "C" int psmc_b200_estep_fetch_raw(psmc_b200_ctx *c, double *raw)
+{
+	if (!c || !raw) return set_err(PSMC_B200_EINVAL, "NULL argument");
+	if (!c->launched) return set_err(PSMC_B200_EINVAL, "estep_fetch_raw without estep_launch");
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	const int n = S_COUNT * c->N + 1;
+	CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	collect_times(c, true);
+	c->launched = false;
+	memcpy(raw, c->h_stats, sizeof(double) * n);
+	return 0;
 }
 
 extern "C" int psmc_b200_estep(psmc_b200_ctx *c, const psmc_b200_model *model, psmc_b200_stats *out)
