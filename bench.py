@@ -318,7 +318,9 @@ def run_own(args):
     dt_e2e = timed(args.steps, upload=True)
     ci = CInfo()
     lib.psmc_b200_get_info(ctx, ctypes.byref(ci))
-    inf = {"n_chunks": ci.n_chunks, "chunk_len": ci.chunk_len}
+    inf = {"n_chunks": ci.n_chunks, "chunk_len": ci.chunk_len, "warm_len": ci.warm_len, "fallbacks": ci.fallbacks,
+           "repaired_fwd": ci.repaired_fwd, "repaired_bwd": ci.repaired_bwd, "failed_fwd": ci.failed_fwd, "failed_bwd": ci.failed_bwd,
+           "fwd_mismatch": ci.fwd_mismatch, "bwd_mismatch": ci.bwd_mismatch}
     obs_bytes = ci.bytes_obs
     if world > 1:
         t = torch.tensor([float(obs_bytes)], dtype=torch.float64, device="cuda")
@@ -360,7 +362,7 @@ def run_own(args):
                             "algorithmic_bytes_per_bin": alg_bytes_per_bin, "bins_per_launch": my_bins, "peak_source": peak_src,
                             "estep_ms": estep_ms, "kernels": per_kernel},
                "estep": {"bins_per_s": total_bins / (estep_ms * 1e-3) if world == 1 else None, "ms": estep_ms,
-                         "mstep_ms": st["t_mstep_ms"], "hj_calls": st["hj_calls"], "chunks": inf["n_chunks"], "chunk_len": inf["chunk_len"]},
+                         "mstep_ms": st["t_mstep_ms"], "hj_calls": st["hj_calls"], "chunks": inf["n_chunks"], "chunk_len": inf["chunk_len"], "fast_path": inf},
                "final": {"lk": st["lk"], "theta": float(st["params"][0]), "rho": float(st["params"][1])}}
         if cb:
             out["cpu_baseline"] = cb

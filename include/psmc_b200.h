@@ -68,6 +68,13 @@ typedef struct {
 	 * [3] backward+counts kernel  [4] reduction kernel        [5] whole E-step (first launch .. last) */
 	float ms[8];
 	int32_t launches; /* kernels launched by the last run */
+	/* fast path (warm-up overlaps + boundary certificate): overlap in bins (0 = disabled), how many E-steps of this
+	 * context had to be redone with the exact transfer-matrix path, and the largest boundary mismatches
+	 * (Hilbert projective metric) seen by the last certificate */
+	int32_t warm_len, fallbacks;
+	double fwd_mismatch, bwd_mismatch;
+	/* last run: boundary failures seen by the repair rounds (summed over rounds) and chunks they recomputed */
+	int32_t failed_fwd, repaired_fwd, failed_bwd, repaired_bwd;
 } psmc_b200_info;
 
 int  psmc_b200_version(void);
@@ -130,6 +137,12 @@ int  psmc_b200_unpack_stats(int32_t n_states, const double *raw, int64_t n_seqs_
  *   post[L*N] (optional), p_recomb[L] (optional, 0 at the last bin), s_out[L] (optional; hmm_data_t::s, aux.c:159-164). */
 int  psmc_b200_decode(psmc_b200_ctx *ctx, const psmc_b200_model *model, int32_t seq_id,
                       int32_t *best_k, double *best_p, double *post, double *p_recomb, double *s_out);
+
+/* Fast-path control: warm_len = bins of warm-up overlap per chunk (0 = always use the exact transfer-matrix
+ * path; < 0 = keep), eps = certificate tolerance in Hilbert's projective metric (<= 0 = keep; default 1e-12).
+ * Boundaries the overlap does not reach are repaired locally; if the final certificate still fails, that
+ * E-step is silently redone with the transfer-matrix path (counted in psmc_b200_info::fallbacks). */
+int  psmc_b200_set_warm(psmc_b200_ctx *ctx, int32_t warm_len, double eps);
 
 int  psmc_b200_get_info(const psmc_b200_ctx *ctx, psmc_b200_info *info);
 

@@ -33,7 +33,9 @@ class CInfo(C.Structure):
                 ("n_seqs", C.c_int32), ("n_chunks", C.c_int32), ("chunk_len", C.c_int32),
                 ("total_bins", C.c_int64), ("bytes_obs", C.c_int64), ("bytes_forward", C.c_int64),
                 ("bytes_transfer", C.c_int64), ("bytes_total", C.c_int64),
-                ("ms", C.c_float * 8), ("launches", C.c_int32)]
+                ("ms", C.c_float * 8), ("launches", C.c_int32),
+                ("warm_len", C.c_int32), ("fallbacks", C.c_int32), ("fwd_mismatch", C.c_double), ("bwd_mismatch", C.c_double),
+                ("failed_fwd", C.c_int32), ("repaired_fwd", C.c_int32), ("failed_bwd", C.c_int32), ("repaired_bwd", C.c_int32)]
 
 
 # every symbol include/psmc_b200.h declares: name -> (restype, argtypes)
@@ -58,6 +60,7 @@ SYMBOLS = {
     "psmc_b200_estep_fetch_raw": (C.c_int, [C.c_void_p, _dp]),
     "psmc_b200_unpack_stats": (C.c_int, [C.c_int32, _dp, C.c_int64, C.POINTER(CStats)]),
     "psmc_b200_decode": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.c_int32, _ip, _dp, _dp, _dp, _dp]),
+    "psmc_b200_set_warm": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "psmc_b200_get_info": (C.c_int, [C.c_void_p, C.POINTER(CInfo)]),
 }
 

@@ -226,10 +226,16 @@ __device__ __forceinline__ double pow2i(int k) { return __hiloint2double((1023 +
 template <int SPL, int G, int COLS>
 __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ chunks, const int32_t *__restrict__ k1_list,
                                                       const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                      double *__restrict__ T, int32_t *__restrict__ Tex, int N)
+                                                      double *__restrict__ T, int32_t *__restrict__ Tex, int N,
+                                                      const int32_t *__restrict__ flag, int sel)
 {
 	constexpr int NP = SPL * G;
-	const int c = k1_list[blockIdx.x];
+	// sel 0: chunk list (transfer mode).  sel 1 / 2: repair rounds of the warm-up mode, one block row per chunk, only
+	// chunks inside a run of failed boundaries that the chain has to cross: forward  flag[c] && flag[c+1],
+	// backward flag[c] && flag[c-1] (flag has guard entries at -1 and n_chunks).
+	const int c = sel == 0 ? k1_list[blockIdx.x] : (int)blockIdx.x;
+	if (sel == 1 && !(flag[c] && flag[c + 1])) return;
+	if (sel == 2 && !(flag[c] && flag[c - 1])) return;
 	const Chunk ch = chunks[c];
 	const int gl = threadIdx.x % G;
 	const int col = blockIdx.y * COLS + threadIdx.x / G;
@@ -324,6 +330,43 @@ __device__ __forceinline__ int block_max_i(int v, int *red)
 	return v;
 }
 
+// v <- normalise(T_c v): thread i holds v[i]; returns the new v[i]  (column-major mantissas + per-column exponents)
+template <int NP>
+__device__ __forceinline__ double chain_fwd_step(const double *__restrict__ Tc, const int32_t *__restrict__ Texc, double v,
+                                                 double *vec, double *red, int *redi)
+{
+	const int i = threadIdx.x;
+	const int ex = Texc[i];
+	int e = (v > 0.0) ? ex + ilogb(v) : INT_MIN;
+	const int emax = block_max_i<NP>(e, redi);
+	__syncthreads();
+	vec[i] = (v > 0.0) ? scalbn(v, ex - emax) : 0.0;
+	__syncthreads();
+	double acc = 0.0;
+#pragma unroll 8
+	for (int j = 0; j < NP; ++j) acc = fma(__ldg(Tc + (size_t)j * NP + i), vec[j], acc);
+	const double tot = block_sum<NP>(acc, red);
+	return acc / tot;
+}
+// b <- T_c^T b (direction only, rescaled so that the largest entry is ~1)
+template <int NP>
+__device__ __forceinline__ double chain_bwd_step(const double *__restrict__ Tc, const int32_t *__restrict__ Texc, double b,
+                                                 double *vec, int *redi)
+{
+	const int i = threadIdx.x;
+	const double *col = Tc + (size_t)i * NP; // column i of T_c
+	__syncthreads();
+	vec[i] = b;
+	__syncthreads();
+	double d = 0.0;
+#pragma unroll 8
+	for (int j = 0; j < NP; ++j) d = fma(__ldg(col + j), vec[j], d);
+	const int ex = Texc[i];
+	int e = (d > 0.0) ? ex + ilogb(d) : INT_MIN;
+	const int emax = block_max_i<NP>(e, redi);
+	return (d > 0.0) ? scalbn(d, ex - emax) : 0.0;
+}
+
 template <int NP>
 __global__ void __launch_bounds__(NP) k_chain(const int32_t *__restrict__ seq_c0, const int32_t *__restrict__ seq_nc,
                                               const double *__restrict__ T, const int32_t *__restrict__ Tex,
@@ -340,90 +383,135 @@ __global__ void __launch_bounds__(NP) k_chain(const int32_t *__restrict__ seq_c0
 	if (dir == 0) {
 		double v = model[M_A0 * NP + i];
 		for (int c = c0; c < c0 + nc - 1; ++c) {
-			const double *Tc = T + (size_t)c * NP * NP;
-			const int ex = Tex[(size_t)c * NP + i];
-			int e = (v > 0.0) ? ex + ilogb(v) : INT_MIN;
-			const int emax = block_max_i<NP>(e, redi);
-			__syncthreads();
-			vec[i] = (v > 0.0) ? scalbn(v, ex - emax) : 0.0;
-			__syncthreads();
-			double acc = 0.0;
-#pragma unroll 8
-			for (int j = 0; j < NP; ++j) acc = fma(__ldg(Tc + (size_t)j * NP + i), vec[j], acc);
-			const double tot = block_sum<NP>(acc, red);
-			v = acc / tot;
+			v = chain_fwd_step<NP>(T + (size_t)c * NP * NP, Tex + (size_t)c * NP, v, vec, red, redi);
 			vstart[(size_t)(c + 1) * NP + i] = v;
 		}
 	} else {
 		double b = 1.0;
 		for (int c = c0 + nc - 2; c >= c0; --c) {
-			const double *Tc = T + (size_t)(c + 1) * NP * NP + (size_t)i * NP; // column i of T_{c+1}
-			__syncthreads();
-			vec[i] = b;
-			__syncthreads();
-			double d = 0.0;
-#pragma unroll 8
-			for (int j = 0; j < NP; ++j) d = fma(__ldg(Tc + j), vec[j], d);
-			const int ex = Tex[(size_t)(c + 1) * NP + i];
-			int e = (d > 0.0) ? ex + ilogb(d) : INT_MIN;
-			const int emax = block_max_i<NP>(e, redi);
-			b = (d > 0.0) ? scalbn(d, ex - emax) : 0.0;
+			b = chain_bwd_step<NP>(T + (size_t)(c + 1) * NP * NP, Tex + (size_t)(c + 1) * NP, b, vec, redi);
+			bend[(size_t)c * NP + i] = b;
+		}
+	}
+}
+
+// Repair rounds of the warm-up mode: one block per chunk; only the HEAD of a run of failed boundaries works.
+//   dir 0 (forward): head = flag[c] && !flag[c-1]; the exact vector in front of the run is the last stored vector of
+//          chunk c-1; vstart of every chunk of the run follows by the transfer operators of the run.
+//   dir 1 (backward): head = flag[c] && !flag[c+1]; the exact direction at the end of chunk c is bexact[c].
+template <int NP>
+__global__ void __launch_bounds__(NP) k_chain_runs(const Chunk *__restrict__ chunks, const int32_t *__restrict__ flag, int dir,
+                                                   const double *__restrict__ T, const int32_t *__restrict__ Tex,
+                                                   const double *__restrict__ fhat, const double *__restrict__ bexact,
+                                                   double *__restrict__ vstart, double *__restrict__ bend)
+{
+	__shared__ double vec[NP];
+	__shared__ double red[4];
+	__shared__ int redi[4];
+	int c = blockIdx.x;
+	const int i = threadIdx.x;
+	if (dir == 0) {
+		if (!flag[c] || flag[c - 1]) return;
+		double v = fhat[((size_t)chunks[c].gb0 - 1) * NP + i];
+		vstart[(size_t)c * NP + i] = v;
+		while (flag[c + 1]) {
+			v = chain_fwd_step<NP>(T + (size_t)c * NP * NP, Tex + (size_t)c * NP, v, vec, red, redi);
+			++c;
+			vstart[(size_t)c * NP + i] = v;
+		}
+	} else {
+		if (!flag[c] || flag[c + 1]) return;
+		double b = bexact[(size_t)c * NP + i];
+		bend[(size_t)c * NP + i] = b;
+		while (flag[c - 1]) {
+			b = chain_bwd_step<NP>(T + (size_t)c * NP * NP, Tex + (size_t)c * NP, b, vec, redi);
+			--c;
 			bend[(size_t)c * NP + i] = b;
 		}
 	}
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: forward.  One warp per chunk (G = 32 lanes x SPL states).  Writes f_u and s_u, accumulates LL.
+// Per-lane model constants of a warp that holds one state vector (G = 32 lanes x SPL states).
 // ------------------------------------------------------------------------------------------------
 template <int SPL>
-__global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
-                                                 const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                 const double *__restrict__ vstart, double *__restrict__ fhat,
-                                                 double *__restrict__ sc, double *__restrict__ llpart)
+struct LaneModel {
+	double U[SPL], V[SPL], W[SPL], Z[SPL], D[SPL], e0[SPL], e1[SPL];
+	__device__ __forceinline__ void load(const double *__restrict__ model, int s0)
+	{
+		constexpr int NP = SPL * 32;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			U[i] = model[M_U * NP + s0 + i];
+			V[i] = model[M_V * NP + s0 + i];
+			W[i] = model[M_W * NP + s0 + i];
+			Z[i] = model[M_Z * NP + s0 + i];
+			D[i] = model[M_D * NP + s0 + i];
+			e0[i] = model[M_E0 * NP + s0 + i];
+			e1[i] = model[M_E1 * NP + s0 + i];
+		}
+	}
+};
+
+// Hilbert projective mismatch max_i(x_i/y_i) / min_i(x_i/y_i) - 1 of two vectors held like state vectors
+// (states >= N ignored); 1e300 if their supports differ.  Same value in every lane.
+template <int SPL>
+__device__ __forceinline__ double warp_mismatch(const double (&x)[SPL], const double (&y)[SPL], int s0, int N)
 {
-	constexpr int G = 32, NP = SPL * G;
-	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (c >= n_chunks) return;
-	const int gl = threadIdx.x & 31;
-	const Chunk ch = chunks[c];
-	const int s0 = gl * SPL;
-	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], e1[SPL], f[SPL];
+	double mx = 0.0, mn = 1e300;
+	bool bad = false;
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) {
-		cU[i] = model[M_U * NP + s0 + i];
-		cV[i] = model[M_V * NP + s0 + i];
-		cW[i] = model[M_W * NP + s0 + i];
-		cZ[i] = model[M_Z * NP + s0 + i];
-		cD[i] = model[M_D * NP + s0 + i];
-		e0[i] = model[M_E0 * NP + s0 + i];
-		e1[i] = model[M_E1 * NP + s0 + i];
+		if (s0 + i < N) {
+			if ((x[i] > 0.0) != (y[i] > 0.0)) bad = true;
+			else if (x[i] > 0.0) {
+				const double r = x[i] / y[i];
+				mx = fmax(mx, r);
+				mn = fmin(mn, r);
+			}
+		}
 	}
-	if (ch.flags & CH_FIRST) {
 #pragma unroll
-		for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
-	} else {
-		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
+	for (int d = 16; d > 0; d >>= 1) {
+		mx = fmax(mx, __shfl_xor_sync(FULLMASK, mx, d));
+		mn = fmin(mn, __shfl_xor_sync(FULLMASK, mn, d));
 	}
+	bad = __any_sync(FULLMASK, bad);
+	return (!bad && mn < 1e300 && mn > 0.0) ? mx / mn - 1.0 : 1e300;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward over bins [ubeg, u0+len) of chunk ch by one warp, starting from f (the normalised forward
+// vector of bin ubeg-1, or a0 when ubeg == 0).  Bins >= u0 are stored (f_u, s_u) and enter the
+// log-likelihood; bins < u0 are warm-up.  If fwarm_c != nullptr the vector reached at bin u0-1 is saved
+// there.  On return f is the vector of the chunk's last bin.  (khmm.c:171-185 with O(N) transitions.)
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__device__ __forceinline__ double forward_chunk(const Chunk &ch, int ubeg, const LaneModel<SPL> &M, double (&f)[SPL], int gl,
+                                                const uint32_t *__restrict__ obs, double *__restrict__ fhat,
+                                                double *__restrict__ sc, double *__restrict__ fwarm_c)
+{
+	constexpr int G = 32, NP = SPL * G;
+	const int s0 = gl * SPL;
 	double ll = 0.0, prod = 1.0;
 	const int uend = ch.u0 + ch.len;
 	uint32_t word = 0;
 	double *fout = fhat + (size_t)ch.gb0 * NP + s0;
 	double *sout = sc + ch.gb0;
-	for (int u = ch.u0; u < uend; ++u) {
-		if (u == ch.u0 || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
+	for (int u = ubeg; u < uend; ++u) {
+		if (u == ubeg || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
 		const int x = (word >> ((u & 15) * 2)) & 3;
 		double out[SPL];
 		if (u == 0) {
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) out[i] = f[i];
 		} else {
-			semisep<SPL, G>(f, cW, cZ, cU, cV, cD, gl, out);
+			semisep<SPL, G>(f, M.W, M.Z, M.U, M.V, M.D, gl, out);
 		}
 		double t = 0.0;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) {
-			const double em = (x == 0) ? e0[i] : ((x == 1) ? e1[i] : 1.0);
+			const double em = (x == 0) ? M.e0[i] : ((x == 1) ? M.e1[i] : 1.0);
 			out[i] *= em;
 			t += out[i];
 		}
@@ -431,70 +519,140 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 		const double inv = 1.0 / s;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) f[i] = out[i] * inv;
-		store_vec<SPL>(fout, f);
-		fout += NP;
-		if (gl == 0) *sout = s;
-		++sout;
-		prod *= s; // running product with reset, as hmm_lk (khmm.c:251-258)
-		if (prod < 1e-100 || prod > 1e100) {
-			ll += log(prod);
-			prod = 1.0;
+		if (u >= ch.u0) {
+			store_vec<SPL>(fout, f);
+			fout += NP;
+			if (gl == 0) *sout = s;
+			++sout;
+			prod *= s; // running product with reset, as hmm_lk (khmm.c:251-258)
+			if (prod < 1e-100 || prod > 1e100) {
+				ll += log(prod);
+				prod = 1.0;
+			}
+		} else if (u == ch.u0 - 1 && fwarm_c) {
+			store_vec<SPL>(fwarm_c + s0, f);
 		}
 	}
-	ll += log(prod);
+	return ll + log(prod);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: forward.  One warp per chunk.
+//   warm == 0 : the exact start vector comes from the boundary chain (vstart, transfer mode).
+//   warm  > 0 : the warp starts `warm` bins to the LEFT of its chunk from the stationary vector, runs
+//               the same recursion without storing (the HMM forgets its start geometrically) and saves
+//               the vector it reached at the bin before its chunk (fwarm[c]) for the certificate.
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
+                                                 const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                 const double *__restrict__ vstart, int warm, double *__restrict__ fhat,
+                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm)
+{
+	constexpr int NP = SPL * 32;
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0);
+	double f[SPL];
+	int ubeg = ch.u0;
+	if ((ch.flags & CH_FIRST) || warm > 0) {
+		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - warm);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
+	} else {
+		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
+	}
+	const double ll = forward_chunk<SPL>(ch, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	if (gl == 0) llpart[c] = ll;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: backward + expected counts.  One warp per chunk.  Per-warp partials: part[c][S_COUNT][NP].
+// K3r: forward repair round (warm-up mode).  Boundary c (between chunks c-1 and c) "fails" when
+// fwarm[c] differs from the last stored vector of chunk c-1 by more than eps (Hilbert metric).
+// A warp acts only as the HEAD of a run of failed boundaries (its own fails, its left neighbour's
+// passes, so the left neighbour's stored vectors are final): it recomputes chunk c from the exact
+// vector, then keeps going through the following chunks whose boundaries also failed at kernel start
+// (nobody else touches those).  The boundary after the run is re-examined by the next round.
+// stat[0] += failed boundaries seen at kernel start, stat[1] += chunks recomputed.
 // ------------------------------------------------------------------------------------------------
 template <int SPL>
-__global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
-                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                  const double *__restrict__ bend, const double *__restrict__ fhat,
-                                                  const double *__restrict__ sc, double *__restrict__ part)
+__device__ __forceinline__ double fwd_boundary_mismatch(const Chunk &ch, int c, const double *__restrict__ fhat,
+                                                        const double *__restrict__ fwarm, int s0, int N)
 {
-	constexpr int G = 32, NP = SPL * G, PF = 4;
+	constexpr int NP = SPL * 32;
+	double x[SPL], y[SPL];
+	load_vec<SPL>(fwarm + (size_t)c * NP + s0, x);
+	load_vec<SPL>(fhat + ((size_t)ch.gb0 - 1) * NP + s0, y);
+	return warp_mismatch<SPL>(x, y, s0, N);
+}
+
+// flag_f[c] = 1 iff the boundary in front of chunk c currently fails (evaluated once per round, so that the
+// repair kernel takes its decisions on a frozen picture); stat[0] += failures
+template <int SPL>
+__global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
+                                                  const double *__restrict__ fhat, const double *__restrict__ fwarm,
+                                                  int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat)
+{
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31;
 	const Chunk ch = chunks[c];
-	const int s0 = gl * SPL;
-	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], e1[SPL];
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) {
-		cU[i] = model[M_U * NP + s0 + i];
-		cV[i] = model[M_V * NP + s0 + i];
-		cW[i] = model[M_W * NP + s0 + i];
-		cZ[i] = model[M_Z * NP + s0 + i];
-		cD[i] = model[M_D * NP + s0 + i];
-		e0[i] = model[M_E0 * NP + s0 + i];
-		e1[i] = model[M_E1 * NP + s0 + i];
+	int fl = 0;
+	if (!(ch.flags & CH_FIRST)) fl = fwd_boundary_mismatch<SPL>(ch, c, fhat, fwarm, gl * SPL, N) > eps ? 1 : 0;
+	if (gl == 0) {
+		flag_f[c] = fl;
+		if (fl) atomicAdd(&stat[0], 1ull);
 	}
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict__ chunks, int n_chunks,
+                                                        const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                        const int32_t *__restrict__ flag_f, const double *__restrict__ vstart,
+                                                        double *__restrict__ fhat, double *__restrict__ sc,
+                                                        double *__restrict__ llpart, double *__restrict__ fwarm,
+                                                        unsigned long long *__restrict__ stat)
+{
+	constexpr int NP = SPL * 32;
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks || !flag_f[c]) return;
+	const int gl = threadIdx.x & 31, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0);
+	double f[SPL];
+	load_vec<SPL>(vstart + (size_t)c * NP + s0, f); // exact vector of the bin before the chunk (k_chain_runs)
+	store_vec<SPL>(fwarm + (size_t)c * NP + s0, f);  // this boundary agrees by construction from now on
+	const double ll = forward_chunk<SPL>(ch, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
+	if (gl == 0) {
+		llpart[c] = ll;
+		atomicAdd(&stat[1], 1ull);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward over chunk ch by one warp from b = b_{ulast} (reference scaling), accumulating the expected
+// counts into part_c; on return b is the vector of bin u0-1 (if u0 > 0).  (khmm.c:226-235, 310-318.)
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__device__ __forceinline__ void backward_chunk(const Chunk &ch, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
+                                               const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
+                                               const double *__restrict__ sc, double *__restrict__ part_c)
+{
+	constexpr int G = 32, NP = SPL * G, PF = 4;
+	const int s0 = gl * SPL;
 	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
-
 	const int ulast = ch.u0 + ch.len - 1;
 	const double *frow = fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + s0; // row of bin ulast
 	const double *srow = sc + ch.gb0 + (ch.len - 1);
-	double fu[SPL], b[SPL], su;
+	double fu[SPL], su;
 	load_vec<SPL>(frow, fu);
 	su = __ldg(srow);
-	if (ch.flags & CH_LAST) { // khmm.c:226: b_L[k] = 1/s_L
-		const double v = 1.0 / su;
-#pragma unroll
-		for (int i = 0; i < SPL; ++i) b[i] = v;
-	} else { // direction from the chain, scale fixed by sum_k f_u[k] b_u[k] s_u = 1
-		double beta[SPL], dot = 0.0;
-		load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
-#pragma unroll
-		for (int i = 0; i < SPL; ++i) dot = fma(fu[i], beta[i], dot);
-		dot = gsum<G>(dot);
-		const double v = 1.0 / (su * dot);
-#pragma unroll
-		for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
-	}
 	// software prefetch ring: nf[j], ns[j] hold row (u-1-j) while bin u is processed
 	double nf[PF][SPL], ns[PF];
 #pragma unroll
@@ -546,11 +704,11 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL];
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) {
-			const double em = (x == 0) ? e0[i] : ((x == 1) ? e1[i] : 1.0);
+			const double em = (x == 0) ? M.e0[i] : ((x == 1) ? M.e1[i] : 1.0);
 			g[i] = em * b[i];
 		}
-		prefsuf<SPL, G>(g, cV, cZ, gl, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
-		prefsuf<SPL, G>(fm, cW, cU, gl, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
+		prefsuf<SPL, G>(g, M.V, M.Z, gl, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
+		prefsuf<SPL, G>(fm, M.W, M.U, gl, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
 		const double inv = 1.0 / sm;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) {
@@ -559,22 +717,205 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 			aAD[i] = fma(fm[i], g[i], aAD[i]);
 			aCL[i] = fma(g[i], Sf[i], aCL[i]);
 			aCU[i] = fma(g[i], Pf[i], aCU[i]);
-			const double bb = fma(cU[i], Pg[i], fma(cW[i], Sg[i], cD[i] * g[i]));
+			const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i]));
 			b[i] = bb * inv;
 			fu[i] = fm[i];
 		}
 		su = sm;
 	}
-	double *po = part + (size_t)c * S_COUNT * NP + s0;
+	double *po = part_c + s0;
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) {
 		po[S_E0 * NP + i] = aE0[i];
 		po[S_E1 * NP + i] = aE1[i];
-		po[S_RL * NP + i] = aRL[i] * cU[i];
-		po[S_CL * NP + i] = aCL[i] * cV[i];
-		po[S_RU * NP + i] = aRU[i] * cW[i];
-		po[S_CU * NP + i] = aCU[i] * cZ[i];
-		po[S_AD * NP + i] = aAD[i] * cD[i];
+		po[S_RL * NP + i] = aRL[i] * M.U[i];
+		po[S_CL * NP + i] = aCL[i] * M.V[i];
+		po[S_RU * NP + i] = aRU[i] * M.W[i];
+		po[S_CU * NP + i] = aCU[i] * M.Z[i];
+		po[S_AD * NP + i] = aAD[i] * M.D[i];
+	}
+}
+
+// b_{ulast} in the reference's scaling from a direction beta: sum_k f[k] b[k] s = 1 (khmm.c:237 sanity identity)
+template <int SPL>
+__device__ __forceinline__ void scale_boundary(const Chunk &ch, const double (&beta)[SPL], double (&b)[SPL], int gl,
+                                               const double *__restrict__ fhat, const double *__restrict__ sc)
+{
+	constexpr int NP = SPL * 32;
+	double fu[SPL], dot = 0.0;
+	load_vec<SPL>(fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + gl * SPL, fu);
+	const double su = __ldg(sc + ch.gb0 + (ch.len - 1));
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) dot = fma(fu[i], beta[i], dot);
+	dot = gsum<32>(dot);
+	const double v = 1.0 / (su * dot);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
+}
+
+// sum-normalised copy of b to dst (direction of the backward vector at a chunk boundary)
+template <int SPL>
+__device__ __forceinline__ void publish_direction(const double (&b)[SPL], double *__restrict__ dst, int gl)
+{
+	double t = 0.0, nb[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) t += b[i];
+	t = 1.0 / gsum<32>(t);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) nb[i] = b[i] * t;
+	store_vec<SPL>(dst + gl * SPL, nb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: backward + expected counts.  One warp per chunk.  Per-warp partials: part[c][S_COUNT][NP].
+//   warm == 0 : the direction of b at the chunk's last bin comes from the boundary chain (bend).
+//   warm  > 0 : the warp first runs the bare backward recursion (direction only) from `warm` bins to the
+//               RIGHT of its chunk, starting from ones, and saves the direction it reached (bwarm[c]);
+//               the chunk to the right publishes the direction it computed for the same bin (bexact[c]).
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
+                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                  const double *__restrict__ bend, int warm, const double *__restrict__ fhat,
+                                                  const double *__restrict__ sc, double *__restrict__ part,
+                                                  double *__restrict__ bwarm, double *__restrict__ bexact)
+{
+	constexpr int G = 32, NP = SPL * G;
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0);
+	const int ulast = ch.u0 + ch.len - 1;
+	double b[SPL];
+	if (ch.flags & CH_LAST) { // khmm.c:226: b_L[k] = 1/s_L
+		const double v = 1.0 / __ldg(sc + ch.gb0 + (ch.len - 1));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = v;
+	} else {
+		double beta[SPL];
+		if (warm > 0) {
+			const int z0 = min(ch.Lseq - 1, ulast + warm);
+			uint32_t word = 0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
+			for (int u = z0; u > ulast; --u) {
+				if (u == z0 || (u & 15) == 15) word = __ldg(obs + ch.ow0 + (u >> 4));
+				const int x = (word >> ((u & 15) * 2)) & 3;
+				double g[SPL], out[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) {
+					const double em = (x == 0) ? M.e0[i] : ((x == 1) ? M.e1[i] : 1.0);
+					g[i] = em * beta[i];
+				}
+				semisep<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, gl, out);
+				if (((z0 - u) & 7) == 7) { // exact power-of-two rescale, same factor in every lane
+					double t = 0.0;
+#pragma unroll
+					for (int i = 0; i < SPL; ++i) t += out[i];
+					t = gsum<G>(t);
+					const double scl = (t > 1e-290 && t < 1e290) ? pow2i(-exponent_of(t)) : 1.0;
+#pragma unroll
+					for (int i = 0; i < SPL; ++i) beta[i] = out[i] * scl;
+				} else {
+#pragma unroll
+					for (int i = 0; i < SPL; ++i) beta[i] = out[i];
+				}
+			}
+			publish_direction<SPL>(beta, bwarm + (size_t)c * NP, gl);
+		} else {
+			load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
+		}
+		scale_boundary<SPL>(ch, beta, b, gl, fhat, sc);
+	}
+	backward_chunk<SPL>(ch, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP);
+	if (warm > 0 && !(ch.flags & CH_FIRST)) publish_direction<SPL>(b, bexact + (size_t)(c - 1) * NP, gl); // b of the last bin of chunk c-1
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4r: backward repair round (warm-up mode), mirror image of K3r.  Boundary c (at the END of chunk c)
+// fails when bwarm[c] differs from bexact[c].  The head of a run (its own boundary fails, the boundary at
+// the end of chunk c+1 passes or chunk c+1 ends its sequence, so bexact[c] is final) recomputes chunk c
+// from bexact[c], republishes bexact[c-1] and keeps going left while the next boundary fails.
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__device__ __forceinline__ double bwd_boundary_mismatch(int c, const double *__restrict__ bwarm, const double *__restrict__ bexact, int s0, int N)
+{
+	constexpr int NP = SPL * 32;
+	double x[SPL], y[SPL];
+	load_vec<SPL>(bwarm + (size_t)c * NP + s0, x);
+	load_vec<SPL>(bexact + (size_t)c * NP + s0, y);
+	return warp_mismatch<SPL>(x, y, s0, N);
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
+                                                  const double *__restrict__ bwarm, const double *__restrict__ bexact,
+                                                  int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat)
+{
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31;
+	int fl = 0;
+	if (!(chunks[c].flags & CH_LAST)) fl = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, gl * SPL, N) > eps ? 1 : 0;
+	if (gl == 0) {
+		flag_b[c] = fl;
+		if (fl) atomicAdd(&stat[2], 1ull);
+	}
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict__ chunks, int n_chunks,
+                                                         const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                         const int32_t *__restrict__ flag_b, const double *__restrict__ bend,
+                                                         const double *__restrict__ fhat, const double *__restrict__ sc,
+                                                         double *__restrict__ part, double *__restrict__ bwarm,
+                                                         double *__restrict__ bexact, unsigned long long *__restrict__ stat)
+{
+	constexpr int NP = SPL * 32;
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks || !flag_b[c]) return;
+	const int gl = threadIdx.x & 31, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0);
+	double beta[SPL], b[SPL];
+	load_vec<SPL>(bend + (size_t)c * NP + s0, beta);           // exact direction at the chunk's last bin (k_chain_runs)
+	publish_direction<SPL>(beta, bwarm + (size_t)c * NP, gl);  // this boundary agrees by construction from now on
+	scale_boundary<SPL>(ch, beta, b, gl, fhat, sc);
+	backward_chunk<SPL>(ch, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP);
+	if (gl == 0) atomicAdd(&stat[3], 1ull);
+	// the boundary to the left: if it belongs to the same run, chunk c-1 republishes nothing new (its own bend came from
+	// the chain); publishing the direction computed here keeps bexact[c-1] consistent for the next round's marks
+	if (!(ch.flags & CH_FIRST)) publish_direction<SPL>(b, bexact + (size_t)(c - 1) * NP, gl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c: final certificate of the warm-up mode.  One warp per internal chunk boundary c|c+1.
+//   forward : fwarm[c+1] vs the last stored vector of chunk c;   backward: bwarm[c] vs bexact[c].
+// If every boundary agrees to eps (Hilbert projective metric), the boundary vectors are a fixed point of
+// the exact recursion and, by induction from the exactly known sequence start (forward) and sequence end
+// (backward), every chunk was computed from the exact vector (to eps).
+// cert[0] = boundaries that fail, cert[1] / cert[2] = largest forward / backward mismatch (double bits).
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_certify(const Chunk *__restrict__ chunks, int n_chunks, int N,
+                                                 const double *__restrict__ fhat, const double *__restrict__ fwarm,
+                                                 const double *__restrict__ bwarm, const double *__restrict__ bexact,
+                                                 double eps, unsigned long long *__restrict__ cert)
+{
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	if (ch.flags & CH_LAST) return;
+	const double mf = fwd_boundary_mismatch<SPL>(chunks[c + 1], c + 1, fhat, fwarm, s0, N);
+	const double mb = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, s0, N);
+	if (gl == 0) {
+		if (!(mf <= eps) || !(mb <= eps)) atomicAdd(&cert[0], 1ull);
+		atomicMax(&cert[1], (unsigned long long)__double_as_longlong(mf));
+		atomicMax(&cert[2], (unsigned long long)__double_as_longlong(mb));
 	}
 }
 
@@ -734,6 +1075,15 @@ struct psmc_b200_ctx {
 	int32_t *d_k1 = nullptr, *d_seq_c0 = nullptr, *d_seq_nc = nullptr, *d_Tex = nullptr;
 	double *d_model = nullptr, *d_fhat = nullptr, *d_sc = nullptr, *d_T = nullptr, *d_vstart = nullptr, *d_bend = nullptr;
 	double *d_part = nullptr, *d_llpart = nullptr, *d_stats = nullptr;
+	double *d_fwarm = nullptr, *d_bwarm = nullptr, *d_bexact = nullptr; // warm-up mode: boundary vectors for the certificate
+	int32_t *d_flag = nullptr; // n_chunks + 2 boundary flags of the current repair round (entries -1 and n_chunks are always 0)
+	unsigned long long *d_cert = nullptr, *h_cert = nullptr;            // [failed boundaries, max fwd mismatch bits, max bwd mismatch bits]
+	int warm_len = 0;          // bins of warm-up overlap (0 = always use the transfer-matrix path)
+	double cert_eps = 1e-12;
+	bool mode_warm = false, certified = true;
+	int fallbacks = 0, repair_rounds = 3;
+	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
+	double mis_f = 0.0, mis_b = 0.0;
 	// decode scratch (allocated on demand)
 	int32_t *d_bestk = nullptr;
 	double *d_bestp = nullptr, *d_post = nullptr, *d_prec = nullptr;
@@ -772,7 +1122,8 @@ static void free_ctx(psmc_b200_ctx *c)
 	cudaSetDevice(c->device);
 	cudaFree(c->d_obs); cudaFree(c->d_chunks); cudaFree(c->d_k1); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
 	cudaFree(c->d_Tex); cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_T);
-	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_part); cudaFree(c->d_llpart); cudaFree(c->d_stats);
+	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_fwarm); cudaFree(c->d_bwarm); cudaFree(c->d_bexact); cudaFree(c->d_cert); cudaFree(c->d_flag);
+	if (c->h_cert) cudaFreeHost(c->h_cert); cudaFree(c->d_part); cudaFree(c->d_llpart); cudaFree(c->d_stats);
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
 	if (c->h_model) cudaFreeHost(c->h_model);
 	if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -869,6 +1220,15 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		chunk_len = (int)std::min<int64_t>(cl, 1 << 24);
 	}
 	c->chunk_len = chunk_len;
+	{ // warm-up overlap: PSMC_B200_WARM=0 disables the fast path (always transfer matrices)
+		const char *env = getenv("PSMC_B200_WARM");
+		c->warm_len = env ? atoi(env) : 8192;
+		if (c->warm_len < 0) c->warm_len = 0;
+		env = getenv("PSMC_B200_REPAIR_ROUNDS");
+		if (env && atoi(env) >= 0) c->repair_rounds = atoi(env);
+		env = getenv("PSMC_B200_CERT_EPS");
+		if (env && atof(env) > 0) c->cert_eps = atof(env);
+	}
 	// packed observations: every sequence starts on a 128-byte boundary (512 bins)
 	std::vector<int64_t> &ow0 = c->seq_ow0;
 	ow0.resize(c->n_seqs);
@@ -938,6 +1298,11 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	ALLOC(c->d_part, sizeof(double) * (size_t)c->n_chunks * S_COUNT * NP);
 	ALLOC(c->d_llpart, sizeof(double) * (size_t)c->n_chunks);
 	ALLOC(c->d_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1));
+	ALLOC(c->d_fwarm, sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_bwarm, sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_bexact, sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_cert, sizeof(unsigned long long) * 8);
+	ALLOC(c->d_flag, sizeof(int32_t) * (size_t)(c->n_chunks + 2));
 #undef ALLOC
 #define CTRY(call)                                                                                \
 	do {                                                                                          \
@@ -952,6 +1317,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	for (int i = 0; i < 8; ++i) CTRY(cudaEventCreate(&c->ev[i]));
 	CTRY(cudaMallocHost((void **)&c->h_model, sizeof(double) * M_COUNT * NP));
 	CTRY(cudaMallocHost((void **)&c->h_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1)));
+	CTRY(cudaMallocHost((void **)&c->h_cert, sizeof(unsigned long long) * 8));
 	CTRY(cudaMallocHost((void **)&c->h_obs, (size_t)c->bytes_obs));
 	pack_all(c, sp.data());
 	CTRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
@@ -962,6 +1328,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		CTRY(cudaMemcpyAsync(c->d_seq_nc, c->seq_nc.data(), sizeof(int32_t) * (size_t)c->n_seqs, cudaMemcpyHostToDevice, c->stream));
 	}
 	CTRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, c->stream));
+	CTRY(cudaMemsetAsync(c->d_flag, 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), c->stream));
 	CTRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, c->stream));
 	CTRY(cudaStreamSynchronize(c->stream));
 #undef CTRY
@@ -1050,9 +1417,9 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	c->launches = 0;
 	cudaEventRecord(c->ev[0], st);
 	if (c->n_k1 > 0) {
-		constexpr int G1 = 8, SPL1 = NP / G1, COLS = 16;
+		constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 		dim3 grid((unsigned)c->n_k1, NP / COLS);
-		k_transfer<SPL1, G1, COLS><<<grid, COLS * G1, 0, st>>>(c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N);
+		k_transfer<SPL1, G1, COLS><<<grid, COLS * G1, 0, st>>>(c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[1], st);
@@ -1064,13 +1431,13 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	const int wpb = 4; // warps per block
 	const int nblk = (c->n_chunks + wpb - 1) / wpb;
 	if (c->n_chunks > 0) {
-		k_forward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, c->d_fhat, c->d_sc, c->d_llpart);
+		k_forward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, 0, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[3], st);
 	if (with_counts) {
 		if (c->n_chunks > 0) {
-			k_backward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, c->d_fhat, c->d_sc, c->d_part);
+			k_backward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, 0, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact);
 			++c->launches;
 		}
 		cudaEventRecord(c->ev[4], st);
@@ -1084,8 +1451,59 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	return 0;
 }
 
+// fast path: warm-up overlaps instead of transfer matrices; boundaries the overlap did not reach are
+// repaired locally (k_forward_repair / k_backward_repair, a fixed number of rounds), then certified.
+template <int SPL>
+static int launch_warm(psmc_b200_ctx *c)
+{
+	constexpr int NP = 32 * SPL;
+	cudaStream_t st = c->stream;
+	cudaMemsetAsync(c->d_cert, 0, sizeof(unsigned long long) * 8, st);
+	cudaEventRecord(c->ev[0], st);
+	cudaEventRecord(c->ev[1], st);
+	cudaEventRecord(c->ev[2], st);
+	const int wpb = 4, nblk = (c->n_chunks + wpb - 1) / wpb;
+	k_forward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, c->warm_len, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm);
+	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
+	const dim3 gridT((unsigned)c->n_chunks, NP / COLS);
+	for (int r = 0; r < c->repair_rounds; ++r) {
+		k_mark_fwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4);
+		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_chunks, nullptr, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, c->d_flag + 1, 1);
+		k_chain_runs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_chunks, c->d_flag + 1, 0, c->d_T, c->d_Tex, c->d_fhat, c->d_bexact, c->d_vstart, c->d_bend);
+		k_forward_repair<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_flag + 1, c->d_vstart, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, c->d_cert + 4);
+	}
+	cudaEventRecord(c->ev[3], st);
+	k_backward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, c->warm_len, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact);
+	for (int r = 0; r < c->repair_rounds; ++r) {
+		k_mark_bwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag + 1, c->d_cert + 4);
+		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_chunks, nullptr, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, c->d_flag + 1, 2);
+		k_chain_runs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_chunks, c->d_flag + 1, 1, c->d_T, c->d_Tex, c->d_fhat, c->d_bexact, c->d_vstart, c->d_bend);
+		k_backward_repair<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_flag + 1, c->d_bend, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact, c->d_cert + 4);
+	}
+	cudaEventRecord(c->ev[4], st);
+	k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->N, NP, c->d_stats);
+	k_certify<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, c->d_cert);
+	cudaEventRecord(c->ev[5], st);
+	c->launches = 4 + 8 * c->repair_rounds;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+	c->fwd_valid = false; // bend[] is not filled in this mode; decode runs its own forward pass
+	c->mode_warm = true;
+	c->certified = false;
+	return 0;
+}
+
 static int launch_dispatch(psmc_b200_ctx *c, bool with_counts)
 {
+	c->mode_warm = false;
+	c->certified = true;
+	if (with_counts && c->warm_len > 0 && c->n_k1 > 0) {
+		switch (c->SPL) {
+		case 1: return launch_warm<1>(c);
+		case 2: return launch_warm<2>(c);
+		case 4: return launch_warm<4>(c);
+		}
+	}
 	switch (c->SPL) {
 	case 1: return launch_core<1>(c, with_counts);
 	case 2: return launch_core<2>(c, with_counts);
@@ -1128,11 +1546,39 @@ static void collect_times(psmc_b200_ctx *c, bool with_counts)
 	}
 }
 
+// Wait for the stream; in warm-up mode read the certificate and, if any boundary failed it, redo the
+// E-step with the exact transfer-matrix path (same stream, same output buffers).
+static int sync_and_certify(psmc_b200_ctx *c)
+{
+	const bool need = c->mode_warm && !c->certified;
+	if (need) CUDA_TRY(cudaMemcpyAsync(c->h_cert, c->d_cert, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	if (need) {
+		c->certified = true;
+		long long bf = (long long)c->h_cert[1], bb = (long long)c->h_cert[2];
+		memcpy(&c->mis_f, &bf, sizeof(double));
+		memcpy(&c->mis_b, &bb, sizeof(double));
+		c->rep_fwd_fail = (long long)c->h_cert[4]; c->rep_fwd_chunks = (long long)c->h_cert[5];
+		c->rep_bwd_fail = (long long)c->h_cert[6]; c->rep_bwd_chunks = (long long)c->h_cert[7];
+		if (c->h_cert[0] > 0) {
+			++c->fallbacks;
+			const int keep = c->warm_len;
+			c->warm_len = 0;
+			int rc = launch_dispatch(c, true);
+			c->warm_len = keep;
+			if (rc) return rc;
+			CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+		}
+	}
+	return 0;
+}
+
 extern "C" int psmc_b200_wait(psmc_b200_ctx *c)
 {
 	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	int rc = sync_and_certify(c);
+	if (rc) return rc;
 	if (c->launched) collect_times(c, true);
 	return 0;
 }
@@ -1165,6 +1611,8 @@ extern "C" int psmc_b200_estep_finish(psmc_b200_ctx *c, int64_t n_seqs_total, ps
 	if (!c->launched) return set_err(PSMC_B200_EINVAL, "estep_finish without estep_launch");
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
 	const int n = S_COUNT * c->N + 1;
+	int rc = sync_and_certify(c);
+	if (rc) return rc;
 	CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	collect_times(c, true);
@@ -1179,6 +1627,8 @@ extern "C" int psmc_b200_estep_fetch_raw(psmc_b200_ctx *c, double *raw)
 	if (!c->launched) return set_err(PSMC_B200_EINVAL, "estep_fetch_raw without estep_launch");
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
 	const int n = S_COUNT * c->N + 1;
+	int rc = sync_and_certify(c);
+	if (rc) return rc;
 	CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	collect_times(c, true);
@@ -1289,6 +1739,14 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
 	return 0;
 }
 
+extern "C" int psmc_b200_set_warm(psmc_b200_ctx *c, int32_t warm_len, double eps)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (warm_len >= 0) c->warm_len = warm_len;
+	if (eps > 0) c->cert_eps = eps;
+	return 0;
+}
+
 extern "C" int psmc_b200_get_info(const psmc_b200_ctx *c, psmc_b200_info *info)
 {
 	if (!c || !info) return set_err(PSMC_B200_EINVAL, "NULL argument");
@@ -1306,5 +1764,13 @@ extern "C" int psmc_b200_get_info(const psmc_b200_ctx *c, psmc_b200_info *info)
 	info->bytes_total = c->bytes_total;
 	for (int i = 0; i < 8; ++i) info->ms[i] = c->ms[i];
 	info->launches = c->launches;
+	info->warm_len = c->warm_len;
+	info->fallbacks = c->fallbacks;
+	info->fwd_mismatch = c->mis_f;
+	info->bwd_mismatch = c->mis_b;
+	info->repaired_fwd = (int32_t)c->rep_fwd_chunks;
+	info->repaired_bwd = (int32_t)c->rep_bwd_chunks;
+	info->failed_fwd = (int32_t)c->rep_fwd_fail;
+	info->failed_bwd = (int32_t)c->rep_bwd_fail;
 	return 0;
 }

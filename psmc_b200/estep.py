@@ -157,6 +157,10 @@ class EStep:
                                                   _d(s) if want_s else None))
         return dict(best_k=bk, best_p=bp, post=post, p_recomb=pr, s=s)
 
+    def set_warm(self, warm_len=-1, eps=0.0):
+        """warm-up overlap in bins (0 = exact transfer-matrix path only) and certificate tolerance"""
+        check(self.lib, self.lib.psmc_b200_set_warm(self.h, warm_len, eps))
+
     def info(self):
         inf = CInfo()
         check(self.lib, self.lib.psmc_b200_get_info(self.h, C.byref(inf)))

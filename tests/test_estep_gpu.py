@@ -103,6 +103,35 @@ def test_medium_contig_auto_chunks(oracle):
     compare_stats(got, want, TOL, N)
 
 
+@pytest.mark.parametrize("warm", [0, 8, 300, 3000, 100000])
+def test_warmup_certificate_and_fallback(oracle, warm):
+    """fast path = warm-up overlaps + boundary certificate; a too-short overlap must be caught by the
+    certificate and redone with the exact transfer-matrix path -- the result never depends on `warm`"""
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=31)
+    seqs = _seqs(m, [60000, 20000, 500], seed=32)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=2500) as es:
+        es.set_warm(warm)
+        got = es.run(_model(m))
+        info = es.info()
+        got2 = es.run(_model(m))     # after a fallback the overlap has been doubled
+        info2 = es.info()
+    compare_stats(got, want, TOL, N)
+    compare_stats(got2, want, TOL, N)
+    assert info["fallbacks"] == 0 and info2["fallbacks"] == 0
+    if warm == 0:
+        assert info["ms"][0] > 0                                     # transfer-matrix path
+    else:
+        assert info["ms"][0] < 0.05                                  # fast path: no transfer matrices
+        assert info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12   # final certificate
+    if warm in (8, 300):
+        assert info["repaired_fwd"] > 0 and info["repaired_bwd"] > 0   # short overlaps are caught and repaired locally
+    if warm == 100000:
+        assert info["repaired_fwd"] == 0 and info["repaired_bwd"] == 0
+
+
 def test_repeatable_bitwise(oracle):
     from psmc_b200 import EStep
     N = 64
