@@ -213,6 +213,19 @@ __device__ __forceinline__ int obs_at(const uint32_t *__restrict__ obs, int64_t 
 	return (__ldg(obs + ow0 + (u >> 4)) >> ((u & 15) * 2)) & 3;
 }
 
+// Loop bounds of a warp-per-chunk kernel come from a per-thread load; broadcasting them from lane 0 lets ptxas
+// prove they are warp-uniform, otherwise every shuffle in the loop is wrapped in WARPSYNC/ENDCOLLECTIVE (3x the
+// instruction count, measured with ncu on B200).
+__device__ __forceinline__ Chunk uniform_chunk(Chunk ch)
+{
+	ch.seq = __shfl_sync(FULLMASK, ch.seq, 0);
+	ch.flags = __shfl_sync(FULLMASK, ch.flags, 0);
+	ch.u0 = __shfl_sync(FULLMASK, ch.u0, 0);
+	ch.len = __shfl_sync(FULLMASK, ch.len, 0);
+	ch.Lseq = __shfl_sync(FULLMASK, ch.Lseq, 0);
+	return ch;
+}
+
 // exact power-of-two rescale helpers: k = floor(log2(x)) for a normal positive x
 __device__ __forceinline__ int exponent_of(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
 __device__ __forceinline__ double pow2i(int k) { return __hiloint2double((1023 + k) << 20, 0); } // |k| < 1022
@@ -553,7 +566,7 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = chunks[c];
+	const Chunk ch = uniform_chunk(chunks[c]);
 	LaneModel<SPL> M;
 	M.load(model, s0);
 	double f[SPL];
@@ -620,7 +633,7 @@ __global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict_
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks || !flag_f[c]) return;
 	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = chunks[c];
+	const Chunk ch = uniform_chunk(chunks[c]);
 	LaneModel<SPL> M;
 	M.load(model, s0);
 	double f[SPL];
@@ -784,7 +797,7 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = chunks[c];
+	const Chunk ch = uniform_chunk(chunks[c]);
 	LaneModel<SPL> M;
 	M.load(model, s0);
 	const int ulast = ch.u0 + ch.len - 1;
@@ -877,7 +890,7 @@ __global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks || !flag_b[c]) return;
 	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = chunks[c];
+	const Chunk ch = uniform_chunk(chunks[c]);
 	LaneModel<SPL> M;
 	M.load(model, s0);
 	double beta[SPL], b[SPL];
@@ -963,7 +976,7 @@ __global__ void __launch_bounds__(128) k_decode(const Chunk *__restrict__ chunks
 	if (w >= n_chunks_seq) return;
 	const int c = c_first + w;
 	const int gl = threadIdx.x & 31;
-	const Chunk ch = chunks[c];
+	const Chunk ch = uniform_chunk(chunks[c]);
 	const int s0 = gl * SPL;
 	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], e1[SPL];
 #pragma unroll
