@@ -62,15 +62,7 @@ def make_genome(scale=1.0, lengths=None):
     return seqs
 
 
-def lpt_shards(lengths, n):
-    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
-    load = [0] * n
-    owner = [0] * len(lengths)
-    for i in order:
-        g = min(range(n), key=lambda r: load[r])
-        owner[i] = g
-        load[g] += lengths[i]
-    return owner
+from psmc_b200.sharding import lpt_shards  # noqa: E402
 
 
 class ClockSampler:

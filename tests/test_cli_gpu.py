@@ -1,0 +1,99 @@
+"""End-to-end drop-in check on the GPU: the `psmc` driver (host/psmc: host C + CUDA E-step) against the golden
+.psmc files written by the UNMODIFIED reference for the same inputs and flags.
+
+Tolerances (DESIGN.md 'Parity'): the E-step itself agrees to 1e-10; the printed EM trajectory of the reference moves by
+1e-6..1e-4 under a one-ulp change of the E-step counts (Hooke-Jeeves), so LK is held to 1e-7 and parameters to that band."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from psmc_text import compare_rounds, fields, parse
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+PSMC = os.path.join(ROOT, "host", "psmc")
+
+TOL = {"LK": (1e-7, 1e-6), "RI": (1e-3, 2e-7), "TR": (5e-5, 2e-6), "MT": (5e-5, 2e-6), "MM": (5e-5, 2e-6),
+       "RS": (1e-3, 3e-6), "PA": (1e-3, 3e-6), "*": (1e-6, 1e-6)}
+
+
+def run(args, tmp_path, name="o.psmc"):
+    out = str(tmp_path / name)
+    r = subprocess.run([PSMC] + args + ["-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return parse(out), r.stderr
+
+
+def test_config1_em_matches_reference(tmp_path):
+    got, _ = run(["-N5", "-t5", "-r1", "-p", "4+5*3+4", os.path.join(G, "c1.psmcfa.gz")], tmp_path)
+    worst = compare_rounds(got, parse(os.path.join(G, "c1.psmc")), TOL)
+    print("worst relative deviations:", worst)
+
+
+def test_64_states_ragged_contigs_em_matches_reference(tmp_path):
+    args = ["-N4", "-t15", "-r5", "-p", "4+25*2+4+6", os.path.join(G, "small64.psmcfa.gz")]
+    got, _ = run(args, tmp_path)
+    compare_rounds(got, parse(os.path.join(G, "small64.psmc")), TOL)
+    got2, _ = run(args + ["--chunk", "777"], tmp_path, "o2.psmc")       # chunk plan must not matter
+    compare_rounds(got2, got, {"*": (1e-6, 1e-6), "LK": (1e-7, 1e-6), "TR": (5e-5, 2e-6), "MT": (5e-5, 2e-6), "MM": (5e-5, 2e-6), "RS": (1e-3, 3e-6), "PA": (1e-3, 3e-6), "RI": (1e-3, 2e-7)})
+
+
+def test_first_round_is_tight(tmp_path):
+    """round 1 (one E-step + one M-step from identical start values) before trajectories can drift"""
+    got, _ = run(["-N1", "-t5", "-r1", "-p", "4+5*3+4", os.path.join(G, "c1.psmcfa.gz")], tmp_path)
+    want = parse(os.path.join(G, "c1.psmc"))
+    lk_g = [float(fields(l)[1][0]) for l in got if l.startswith("LK")]
+    lk_w = [float(fields(l)[1][0]) for l in want if l.startswith("LK")]
+    assert abs(lk_g[1] - lk_w[1]) <= 1e-9 * abs(lk_w[1])
+
+
+def test_decode_fixed_parameters_matches_reference(tmp_path):
+    fa, par = os.path.join(G, "c1.psmcfa.gz"), os.path.join(G, "c1_params.txt")
+    got, _ = run(["-N0", "-i", par, "-d", fa], tmp_path)
+    want = parse(os.path.join(G, "c1_decode.psmc"))
+    tc_g = [l for l in got if l.startswith("TC")]; tc_w = [l for l in want if l.startswith("TC")]
+    assert tc_g == tc_w
+    dc_g = [l for l in got if l.startswith("DC")]; dc_w = [l for l in want if l.startswith("DC")]
+    same = sum(a == b for a, b in zip(dc_g, dc_w))
+    assert len(dc_g) == len(dc_w) and same >= 0.995 * len(dc_w), (len(dc_g), len(dc_w), same)
+    # everything before the decoding block is the usual header + round 0
+    assert [l for l in got if l[:2] not in ("TC", "DC")] == [l for l in want if l[:2] not in ("TC", "DC")]
+
+
+def test_full_decode_and_prob_match_reference(tmp_path):
+    fa, par = os.path.join(G, "c1.psmcfa.gz"), os.path.join(G, "c1_params.txt")
+    got, _ = run(["-N0", "-i", par, "-D", fa], tmp_path)
+    want = gzip.open(os.path.join(G, "c1_fulldecode.psmc.gz"), "rt").read().splitlines()
+    df_g = [l for l in got if l.startswith("DF")]; df_w = [l for l in want if l.startswith("DF")]
+    assert len(df_g) == len(df_w) == 10000
+    A = np.array([[float(x) for x in l.split("\t")[1:]] for l in df_g])
+    B = np.array([[float(x) for x in l.split("\t")[1:]] for l in df_w])
+    assert np.array_equal(A[:, 0], B[:, 0])
+    assert np.max(np.abs(A[:, 1] - B[:, 1])) <= 2e-6           # recombination probability, %lf
+    assert np.max(np.abs(A[:, 2:] - B[:, 2:])) <= 1.0001e-4    # posteriors, %.4f
+    got, _ = run(["-N0", "-i", par, "-s", fa], tmp_path, "p.psmc")
+    pr_g = [l for l in got if l.startswith("PR")][0].split("\t"); pr_w = [l for l in parse(os.path.join(G, "c1_prob.psmc")) if l.startswith("PR")][0].split("\t")
+    assert pr_g[:3] == pr_w[:3]
+    assert np.max(np.abs(np.array(pr_g[3:], dtype=float) - np.array(pr_w[3:], dtype=float))) <= 1.0001e-3
+
+
+def test_two_gpus_equal_one(tmp_path):
+    import psmc_b200
+    if psmc_b200.load_library().psmc_b200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    args = ["-N3", "-t15", "-r5", "-p", "4+25*2+4+6", os.path.join(G, "small64.psmcfa.gz")]
+    one, _ = run(args, tmp_path, "g1.psmc")
+    two, _ = run(args + ["--gpus", "2"], tmp_path, "g2.psmc")
+    compare_rounds(two, one, {"*": (1e-6, 1e-6), "LK": (1e-7, 1e-6), "TR": (5e-5, 2e-6), "MT": (5e-5, 2e-6), "MM": (5e-5, 2e-6), "RS": (1e-3, 3e-6), "PA": (1e-3, 3e-6), "RI": (1e-3, 2e-7)})
+
+
+def test_unsupported_options_fail_loudly(tmp_path):
+    fa = os.path.join(G, "c1.psmcfa.gz")
+    for extra in (["-S"], ["-c", "/dev/null"], ["-d", "-C", "5"]):
+        r = subprocess.run([PSMC, "-N1"] + extra + [fa], capture_output=True, text=True)
+        assert r.returncode != 0 and "not supported" in r.stderr
