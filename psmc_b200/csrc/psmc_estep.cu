@@ -93,28 +93,39 @@ enum { S_E0 = 0, S_E1, S_RL, S_CL, S_RU, S_CU, S_AD, S_COUNT };
 // lane-group primitives: a vector of NP = G*SPL states is held by G consecutive lanes, SPL states
 // per lane (state = gl*SPL + i).  G is a power of two <= 32.
 // ------------------------------------------------------------------------------------------------
+// Kogge-Stone scans over the lanes of a group.  A step is "x += (source lane inside my group) ? shuffled x : 0";
+// written as an FMA with a per-lane 0/1 mask it costs 2 SHFL + 1 DFMA (the obvious if/select form compiles to
+// 2 SHFL + DADD + 2 FSEL + moves and made the chunk kernels issue-bound: 231 instructions per bin, ncu).
 template <int G>
-__device__ __forceinline__ double gscan_up(double t, int gl) // exclusive prefix over the lanes of a group
-{
-	double x = __shfl_up_sync(FULLMASK, t, 1, G);
-	if (gl == 0) x = 0.0;
+struct ScanMasks {
+	static constexpr int STEPS = (G == 32 ? 5 : G == 16 ? 4 : G == 8 ? 3 : G == 4 ? 2 : G == 2 ? 1 : 0);
+	double up[STEPS + 1], dn[STEPS + 1]; // [k]: distance 2^k; [STEPS] is unused padding for G == 1
+	__device__ __forceinline__ void init(int gl)
+	{
 #pragma unroll
-	for (int d = 1; d < G; d <<= 1) {
-		double y = __shfl_up_sync(FULLMASK, x, d, G);
-		if (gl >= d) x += y;
+		for (int k = 0; k < STEPS; ++k) {
+			up[k] = (gl >= (1 << k)) ? 1.0 : 0.0;
+			dn[k] = (gl + (1 << k) < G) ? 1.0 : 0.0;
+		}
+		up[STEPS] = dn[STEPS] = 0.0;
 	}
+};
+template <int G>
+__device__ __forceinline__ double gscan_up(double t, const ScanMasks<G> &m) // exclusive prefix over the lanes of a group
+{
+	if (G == 1) return 0.0;
+	double x = __shfl_up_sync(FULLMASK, t, 1, G) * m.up[0];
+#pragma unroll
+	for (int k = 0; k < ScanMasks<G>::STEPS; ++k) x = fma(__shfl_up_sync(FULLMASK, x, 1 << k, G), m.up[k], x);
 	return x;
 }
 template <int G>
-__device__ __forceinline__ double gscan_down(double t, int gl) // exclusive suffix over the lanes of a group
+__device__ __forceinline__ double gscan_down(double t, const ScanMasks<G> &m) // exclusive suffix over the lanes of a group
 {
-	double x = __shfl_down_sync(FULLMASK, t, 1, G);
-	if (gl == G - 1) x = 0.0;
+	if (G == 1) return 0.0;
+	double x = __shfl_down_sync(FULLMASK, t, 1, G) * m.dn[0];
 #pragma unroll
-	for (int d = 1; d < G; d <<= 1) {
-		double y = __shfl_down_sync(FULLMASK, x, d, G);
-		if (gl + d < G) x += y;
-	}
+	for (int k = 0; k < ScanMasks<G>::STEPS; ++k) x = fma(__shfl_down_sync(FULLMASK, x, 1 << k, G), m.dn[k], x);
 	return x;
 }
 template <int G>
@@ -123,6 +134,19 @@ __device__ __forceinline__ double gsum(double t) // all-reduce over the lanes of
 #pragma unroll
 	for (int d = G >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULLMASK, t, d, G);
 	return t;
+}
+// reciprocal of a positive normal double: hardware seed + two Newton steps (~1 ulp; the IEEE division drags a
+// slow path and a range check into the loop)
+__device__ __forceinline__ double fast_rcp(double s)
+{
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+	double e = fma(-s, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-s, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-s, r, 1.0);
+	return fma(r, e, r);
 }
 template <int G>
 __device__ __forceinline__ int gmax_i(int t)
@@ -138,7 +162,7 @@ __device__ __forceinline__ int gmax_i(int t)
 template <int SPL, int G>
 __device__ __forceinline__ void semisep(const double (&x)[SPL], const double (&pm)[SPL], const double (&pc)[SPL],
                                         const double (&sm)[SPL], const double (&sc)[SPL], const double (&D)[SPL],
-                                        int gl, double (&out)[SPL])
+                                        const ScanMasks<G> &mk, double (&out)[SPL])
 {
 	double tp = 0.0, ts = 0.0;
 #pragma unroll
@@ -146,7 +170,7 @@ __device__ __forceinline__ void semisep(const double (&x)[SPL], const double (&p
 		tp = fma(x[i], pm[i], tp);
 		ts = fma(x[i], sm[i], ts);
 	}
-	double p = gscan_up<G>(tp, gl), s = gscan_down<G>(ts, gl);
+	double p = gscan_up<G>(tp, mk), s = gscan_down<G>(ts, mk);
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) {
 		out[i] = fma(pc[i], p, D[i] * x[i]);
@@ -162,7 +186,7 @@ __device__ __forceinline__ void semisep(const double (&x)[SPL], const double (&p
 // exclusive prefix P[i] = sum_{j<i} pm[j] x[j] and exclusive suffix S[i] = sum_{j>i} sm[j] x[j]
 template <int SPL, int G>
 __device__ __forceinline__ void prefsuf(const double (&x)[SPL], const double (&pm)[SPL], const double (&sm)[SPL],
-                                        int gl, double (&P)[SPL], double (&S)[SPL])
+                                        const ScanMasks<G> &mk, double (&P)[SPL], double (&S)[SPL])
 {
 	double tp = 0.0, ts = 0.0;
 #pragma unroll
@@ -170,7 +194,7 @@ __device__ __forceinline__ void prefsuf(const double (&x)[SPL], const double (&p
 		tp = fma(x[i], pm[i], tp);
 		ts = fma(x[i], sm[i], ts);
 	}
-	double p = gscan_up<G>(tp, gl), s = gscan_down<G>(ts, gl);
+	double p = gscan_up<G>(tp, mk), s = gscan_down<G>(ts, mk);
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) {
 		P[i] = p;
@@ -243,12 +267,10 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
                                                       const int32_t *__restrict__ flag, int sel)
 {
 	constexpr int NP = SPL * G;
-	// sel 0: chunk list (transfer mode).  sel 1 / 2: repair rounds of the warm-up mode, one block row per chunk, only
-	// chunks inside a run of failed boundaries that the chain has to cross: forward  flag[c] && flag[c+1],
-	// backward flag[c] && flag[c-1] (flag has guard entries at -1 and n_chunks).
+	// sel 0: chunk list (transfer mode).  sel 3: repair rounds of the warm-up mode: `chunks` is the SUB-chunk table,
+	// one block row per sub-chunk, only those whose parent chunk is flagged (flag has guard entries at -1 and n).
 	const int c = sel == 0 ? k1_list[blockIdx.x] : (int)blockIdx.x;
-	if (sel == 1 && !(flag[c] && flag[c + 1])) return;
-	if (sel == 2 && !(flag[c] && flag[c - 1])) return;
+	if (sel == 3 && !flag[k1_list[c]]) return; // k1_list = parent chunk of every sub-chunk in this mode
 	const Chunk ch = chunks[c];
 	const int gl = threadIdx.x % G;
 	const int col = blockIdx.y * COLS + threadIdx.x / G;
@@ -267,6 +289,8 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
 	int ex = 0;
 	const int uend = ch.u0 + ch.len;
 	uint32_t word = 0;
+	ScanMasks<G> mk;
+	mk.init(gl);
 	for (int u = ch.u0; u < uend; ++u) {
 		if (u == ch.u0 || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
 		const int x = (word >> ((u & 15) * 2)) & 3;
@@ -275,7 +299,7 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) out[i] = f[i];
 		} else {
-			semisep<SPL, G>(f, cW, cZ, cU, cV, cD, gl, out);
+			semisep<SPL, G>(f, cW, cZ, cU, cV, cD, mk, out);
 		}
 		if (x == 0) {
 #pragma unroll
@@ -408,38 +432,68 @@ __global__ void __launch_bounds__(NP) k_chain(const int32_t *__restrict__ seq_c0
 	}
 }
 
-// Repair rounds of the warm-up mode: one block per chunk; only the HEAD of a run of failed boundaries works.
+// Repair rounds of the warm-up mode.  Flagged chunks are repaired at SUB-chunk granularity (every chunk is pre-split
+// into pieces of ~1.5k bins) so that the latency-bound pieces of a repair (transfer operators, recompute) are short.
+// One block per chunk; only the HEAD of a run of failed boundaries works and walks the sub-chunks of its run.
 //   dir 0 (forward): head = flag[c] && !flag[c-1]; the exact vector in front of the run is the last stored vector of
-//          chunk c-1; vstart of every chunk of the run follows by the transfer operators of the run.
-//   dir 1 (backward): head = flag[c] && !flag[c+1]; the exact direction at the end of chunk c is bexact[c].
+//          chunk c-1; vsub[s] (start vector of every sub-chunk of the run) follows through the sub-chunk operators.
+//   dir 1 (backward): head = flag[c] && !flag[c+1]; the exact direction at the end of chunk c is bexact[c];
+//          bsub[s] = direction of b at the last bin of sub-chunk s.
 template <int NP>
-__global__ void __launch_bounds__(NP) k_chain_runs(const Chunk *__restrict__ chunks, const int32_t *__restrict__ flag, int dir,
+__global__ void __launch_bounds__(NP) k_chain_subs(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
+                                                   const int32_t *__restrict__ chunk_sub0, const int32_t *__restrict__ flag, int dir,
                                                    const double *__restrict__ T, const int32_t *__restrict__ Tex,
                                                    const double *__restrict__ fhat, const double *__restrict__ bexact,
-                                                   double *__restrict__ vstart, double *__restrict__ bend)
+                                                   double *__restrict__ vsub, double *__restrict__ bsub)
 {
 	__shared__ double vec[NP];
 	__shared__ double red[4];
 	__shared__ int redi[4];
-	int c = blockIdx.x;
-	const int i = threadIdx.x;
+	const int c = blockIdx.x, i = threadIdx.x;
 	if (dir == 0) {
 		if (!flag[c] || flag[c - 1]) return;
-		double v = fhat[((size_t)chunks[c].gb0 - 1) * NP + i];
-		vstart[(size_t)c * NP + i] = v;
-		while (flag[c + 1]) {
-			v = chain_fwd_step<NP>(T + (size_t)c * NP * NP, Tex + (size_t)c * NP, v, vec, red, redi);
-			++c;
-			vstart[(size_t)c * NP + i] = v;
+		int s = chunk_sub0[c];
+		double v = fhat[((size_t)subs[s].gb0 - 1) * NP + i];
+		vsub[(size_t)s * NP + i] = v;
+		while (s + 1 < n_sub && flag[parent[s + 1]]) {
+			v = chain_fwd_step<NP>(T + (size_t)s * NP * NP, Tex + (size_t)s * NP, v, vec, red, redi);
+			++s;
+			vsub[(size_t)s * NP + i] = v;
 		}
 	} else {
 		if (!flag[c] || flag[c + 1]) return;
+		int s = chunk_sub0[c + 1] - 1;
 		double b = bexact[(size_t)c * NP + i];
-		bend[(size_t)c * NP + i] = b;
-		while (flag[c - 1]) {
-			b = chain_bwd_step<NP>(T + (size_t)c * NP * NP, Tex + (size_t)c * NP, b, vec, redi);
-			--c;
-			bend[(size_t)c * NP + i] = b;
+		bsub[(size_t)s * NP + i] = b;
+		while (s - 1 >= 0 && flag[parent[s - 1]]) {
+			b = chain_bwd_step<NP>(T + (size_t)s * NP * NP, Tex + (size_t)s * NP, b, vec, redi);
+			--s;
+			bsub[(size_t)s * NP + i] = b;
+		}
+	}
+}
+
+// after a repair round: fold the per-sub-chunk results of every flagged chunk back into the per-chunk arrays
+// (dir 0: log-likelihood partials; dir 1: expected-count partials).  One block per chunk.
+__global__ void __launch_bounds__(128) k_fold(const int32_t *__restrict__ chunk_sub0, const int32_t *__restrict__ flag, int dir, int NP,
+                                              const double *__restrict__ llsub, double *__restrict__ llpart,
+                                              const double *__restrict__ partsub, double *__restrict__ part)
+{
+	const int c = blockIdx.x;
+	if (!flag[c]) return;
+	const int s0 = chunk_sub0[c], s1 = chunk_sub0[c + 1];
+	if (dir == 0) {
+		if (threadIdx.x == 0) {
+			double t = 0.0;
+			for (int s = s0; s < s1; ++s) t += llsub[s];
+			llpart[c] = t;
+		}
+	} else {
+		const int n = S_COUNT * NP;
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+			double t = 0.0;
+			for (int s = s0; s < s1; ++s) t += partsub[(size_t)s * n + j];
+			part[(size_t)c * n + j] = t;
 		}
 	}
 }
@@ -447,12 +501,19 @@ __global__ void __launch_bounds__(NP) k_chain_runs(const Chunk *__restrict__ chu
 // ------------------------------------------------------------------------------------------------
 // Per-lane model constants of a warp that holds one state vector (G = 32 lanes x SPL states).
 // ------------------------------------------------------------------------------------------------
+// emission of symbol x in a state with hom-emission e0: x = 0 -> e0, x = 1 -> 1 - e0 (bit-identical to the host's
+// e[1][k] = 1.0 - e[0][k], core.c:125), x = 2 (missing) -> 1 (khmm.c:21); branch-free: em = c1 * e0 + c0
+__device__ __forceinline__ void emis_coef(int x, double &c0, double &c1)
+{
+	c0 = (x == 0) ? 0.0 : 1.0;
+	c1 = (x == 0) ? 1.0 : ((x == 1) ? -1.0 : 0.0);
+}
+
 template <int SPL>
 struct LaneModel {
-	double U[SPL], V[SPL], W[SPL], Z[SPL], D[SPL], e0[SPL], e1[SPL];
-	__device__ __forceinline__ void load(const double *__restrict__ model, int s0)
+	double U[SPL], V[SPL], W[SPL], Z[SPL], D[SPL], e0[SPL];
+	__device__ __forceinline__ void load(const double *__restrict__ model, int s0, int NP)
 	{
-		constexpr int NP = SPL * 32;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) {
 			U[i] = model[M_U * NP + s0 + i];
@@ -461,7 +522,6 @@ struct LaneModel {
 			Z[i] = model[M_Z * NP + s0 + i];
 			D[i] = model[M_D * NP + s0 + i];
 			e0[i] = model[M_E0 * NP + s0 + i];
-			e1[i] = model[M_E1 * NP + s0 + i];
 		}
 	}
 };
@@ -494,81 +554,126 @@ __device__ __forceinline__ double warp_mismatch(const double (&x)[SPL], const do
 }
 
 // ------------------------------------------------------------------------------------------------
-// Forward over bins [ubeg, u0+len) of chunk ch by one warp, starting from f (the normalised forward
+// Work assignment of the chunk kernels: a state vector is held by a GROUP of G consecutive lanes (SPL = NP/G
+// states per lane), so a warp runs 32/G chunks side by side in lock step.  Narrow groups make the scans
+// work-efficient (log2 G shuffle rounds shared by 32/G chunks) and give the FP64 pipe independent work.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+struct GroupId {
+	int c, gl;
+	bool valid;
+	__device__ __forceinline__ GroupId(int n_chunks)
+	{
+		const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+		gl = lane % G;
+		c = warp * (32 / G) + lane / G;
+		valid = c < n_chunks;
+		if (!valid) c = n_chunks - 1; // idle groups shadow a real chunk so that every address they form stays legal
+	}
+};
+
+// trip count of a lock-step loop: the largest count of the warp's groups, identical in every lane (and provably so
+// for ptxas, which otherwise wraps every shuffle of the loop in WARPSYNC/ENDCOLLECTIVE)
+__device__ __forceinline__ int warp_trips(int n)
+{
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) n = max(n, __shfl_xor_sync(FULLMASK, n, d));
+	return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward over bins [ubeg, u0+len) of chunk ch by one lane group, starting from f (the normalised forward
 // vector of bin ubeg-1, or a0 when ubeg == 0).  Bins >= u0 are stored (f_u, s_u) and enter the
 // log-likelihood; bins < u0 are warm-up.  If fwarm_c != nullptr the vector reached at bin u0-1 is saved
 // there.  On return f is the vector of the chunk's last bin.  (khmm.c:171-185 with O(N) transitions.)
 // ------------------------------------------------------------------------------------------------
-template <int SPL>
-__device__ __forceinline__ double forward_chunk(const Chunk &ch, int ubeg, const LaneModel<SPL> &M, double (&f)[SPL], int gl,
-                                                const uint32_t *__restrict__ obs, double *__restrict__ fhat,
+template <int SPL, int G>
+__device__ __forceinline__ double forward_chunk(const Chunk &ch, bool valid, int ubeg, const LaneModel<SPL> &M, double (&f)[SPL],
+                                                int gl, const uint32_t *__restrict__ obs, double *__restrict__ fhat,
                                                 double *__restrict__ sc, double *__restrict__ fwarm_c)
 {
-	constexpr int G = 32, NP = SPL * G;
+	// The recursion carries g_u = (M_u g_{u-1}) * rho_u with the ONE-STEP-DELAYED scale rho_u = 1 / sum(g_{u-1}).
+	// Then sum(g_u) = s_u exactly (the reference's scale factor, khmm.c:183-184) and f_u = g_u / s_u, while the
+	// reduction and the division that produce rho_{u+1} overlap the next transition instead of sitting on the
+	// dependency chain (the chain per bin is scan + combine only).  On entry f is normalised (rho = 1).
+	constexpr int NP = SPL * G;
 	const int s0 = gl * SPL;
 	double ll = 0.0, prod = 1.0;
 	const int uend = ch.u0 + ch.len;
+	const int trips = warp_trips(valid ? uend - ubeg : 0);
 	uint32_t word = 0;
-	double *fout = fhat + (size_t)ch.gb0 * NP + s0;
-	double *sout = sc + ch.gb0;
-	for (int u = ubeg; u < uend; ++u) {
-		if (u == ubeg || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
-		const int x = (word >> ((u & 15) * 2)) & 3;
-		double out[SPL];
-		if (u == 0) {
+	double g[SPL], rho = 1.0;
 #pragma unroll
-			for (int i = 0; i < SPL; ++i) out[i] = f[i];
-		} else {
-			semisep<SPL, G>(f, M.W, M.Z, M.U, M.V, M.D, gl, out);
-		}
-		double t = 0.0;
+	for (int i = 0; i < SPL; ++i) g[i] = f[i];
+	ScanMasks<G> mk;
+	mk.init(gl);
+	for (int t = 0; t < trips; ++t) {
+		const int u = ubeg + t;
+		const bool act = valid && u < uend;
+		const int uo = act ? u : uend - 1; // idle groups keep reading a legal word
+		if (t == 0 || (uo & 15) == 0) word = __ldg(obs + ch.ow0 + (uo >> 4));
+		const int x = (word >> ((uo & 15) * 2)) & 3;
+		double out[SPL];
+		semisep<SPL, G>(g, M.W, M.Z, M.U, M.V, M.D, mk, out);
+		double tsum = 0.0, c0, c1;
+		emis_coef(x, c0, c1);
+		c0 *= rho;
+		c1 *= rho;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) {
-			const double em = (x == 0) ? M.e0[i] : ((x == 1) ? M.e1[i] : 1.0);
-			out[i] *= em;
-			t += out[i];
+			out[i] = ((u == 0) ? g[i] : out[i]) * fma(c1, M.e0[i], c0); // first bin of a sequence: no transition (khmm.c:171-174)
+			tsum += out[i];
 		}
-		const double s = gsum<G>(t);
-		const double inv = 1.0 / s;
+		const double s = gsum<G>(tsum); // = s_u
+		const double inv = fast_rcp(s);
+		if (act) {
 #pragma unroll
-		for (int i = 0; i < SPL; ++i) f[i] = out[i] * inv;
-		if (u >= ch.u0) {
-			store_vec<SPL>(fout, f);
-			fout += NP;
-			if (gl == 0) *sout = s;
-			++sout;
-			prod *= s; // running product with reset, as hmm_lk (khmm.c:251-258)
-			if (prod < 1e-100 || prod > 1e100) {
-				ll += log(prod);
-				prod = 1.0;
+			for (int i = 0; i < SPL; ++i) g[i] = out[i];
+			rho = inv;
+			if (u >= ch.u0) {
+				double fn[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) fn[i] = out[i] * inv;
+				store_vec<SPL>(fhat + ((size_t)ch.gb0 + (u - ch.u0)) * NP + s0, fn);
+				if (gl == 0) sc[ch.gb0 + (u - ch.u0)] = s;
+				prod *= s; // running product with reset, as hmm_lk (khmm.c:251-258)
+				if (prod < 1e-100 || prod > 1e100) {
+					ll += log(prod);
+					prod = 1.0;
+				}
+			} else if (u == ch.u0 - 1 && fwarm_c) {
+				double fn[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) fn[i] = out[i] * inv;
+				store_vec<SPL>(fwarm_c + s0, fn);
 			}
-		} else if (u == ch.u0 - 1 && fwarm_c) {
-			store_vec<SPL>(fwarm_c + s0, f);
 		}
 	}
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) f[i] = g[i] * rho; // normalised vector of the last bin
 	return ll + log(prod);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: forward.  One warp per chunk.
+// K3: forward.  One lane group per chunk.
 //   warm == 0 : the exact start vector comes from the boundary chain (vstart, transfer mode).
-//   warm  > 0 : the warp starts `warm` bins to the LEFT of its chunk from the stationary vector, runs
+//   warm  > 0 : the group starts `warm` bins to the LEFT of its chunk from the stationary vector, runs
 //               the same recursion without storing (the HMM forgets its start geometrically) and saves
 //               the vector it reached at the bin before its chunk (fwarm[c]) for the certificate.
 // ------------------------------------------------------------------------------------------------
-template <int SPL>
+template <int SPL, int G>
 __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                  const double *__restrict__ vstart, int warm, double *__restrict__ fhat,
                                                  double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm)
 {
-	constexpr int NP = SPL * 32;
-	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (c >= n_chunks) return;
-	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = uniform_chunk(chunks[c]);
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
-	M.load(model, s0);
+	M.load(model, s0, NP);
 	double f[SPL];
 	int ubeg = ch.u0;
 	if ((ch.flags & CH_FIRST) || warm > 0) {
@@ -578,8 +683,8 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	} else {
 		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
 	}
-	const double ll = forward_chunk<SPL>(ch, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
-	if (gl == 0) llpart[c] = ll;
+	const double ll = forward_chunk<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
+	if (gl == 0 && id.valid) llpart[c] = ll;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -621,41 +726,44 @@ __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chun
 	}
 }
 
-template <int SPL>
-__global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict__ chunks, int n_chunks,
+template <int SPL, int G>
+__global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
+                                                        const int32_t *__restrict__ chunk_sub0,
                                                         const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                        const int32_t *__restrict__ flag_f, const double *__restrict__ vstart,
+                                                        const int32_t *__restrict__ flag_f, const double *__restrict__ vsub,
                                                         double *__restrict__ fhat, double *__restrict__ sc,
-                                                        double *__restrict__ llpart, double *__restrict__ fwarm,
+                                                        double *__restrict__ llsub, double *__restrict__ fwarm,
                                                         unsigned long long *__restrict__ stat)
 {
-	constexpr int NP = SPL * 32;
-	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (c >= n_chunks || !flag_f[c]) return;
-	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = uniform_chunk(chunks[c]);
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_sub);
+	const int s = id.c, gl = id.gl, s0 = gl * SPL;
+	const int pc = parent[s];
+	const bool valid = id.valid && flag_f[pc] != 0;
+	if (!__any_sync(FULLMASK, valid)) return;
+	const Chunk ch = subs[s];
 	LaneModel<SPL> M;
-	M.load(model, s0);
+	M.load(model, s0, NP);
 	double f[SPL];
-	load_vec<SPL>(vstart + (size_t)c * NP + s0, f); // exact vector of the bin before the chunk (k_chain_runs)
-	store_vec<SPL>(fwarm + (size_t)c * NP + s0, f);  // this boundary agrees by construction from now on
-	const double ll = forward_chunk<SPL>(ch, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
-	if (gl == 0) {
-		llpart[c] = ll;
+	load_vec<SPL>(vsub + (size_t)s * NP + s0, f);                                              // exact vector of the bin before the sub-chunk (k_chain_subs)
+	if (valid && chunk_sub0[pc] == s) store_vec<SPL>(fwarm + (size_t)pc * NP + s0, f);        // the chunk boundary agrees by construction from now on
+	const double ll = forward_chunk<SPL, G>(ch, valid, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
+	if (gl == 0 && valid) {
+		llsub[s] = ll;
 		atomicAdd(&stat[1], 1ull);
 	}
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward over chunk ch by one warp from b = b_{ulast} (reference scaling), accumulating the expected
+// Backward over chunk ch by one lane group from b = b_{ulast} (reference scaling), accumulating the expected
 // counts into part_c; on return b is the vector of bin u0-1 (if u0 > 0).  (khmm.c:226-235, 310-318.)
 // ------------------------------------------------------------------------------------------------
-template <int SPL>
-__device__ __forceinline__ void backward_chunk(const Chunk &ch, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
+template <int SPL, int G>
+__device__ __forceinline__ void backward_chunk(const Chunk &ch, bool valid, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
                                                const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
                                                const double *__restrict__ sc, double *__restrict__ part_c)
 {
-	constexpr int G = 32, NP = SPL * G, PF = 4;
+	constexpr int NP = SPL * G, PF = 4;
 	const int s0 = gl * SPL;
 	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
 #pragma unroll
@@ -680,12 +788,18 @@ __device__ __forceinline__ void backward_chunk(const Chunk &ch, const LaneModel<
 			ns[j] = 1.0;
 		}
 	}
+	const int trips = warp_trips(valid ? ch.len : 0);
 	uint32_t word = 0;
-	for (int u = ulast; u >= ch.u0; --u) {
-		if (u == ulast || (u & 15) == 15) word = __ldg(obs + ch.ow0 + (u >> 4));
-		const int x = (word >> ((u & 15) * 2)) & 3;
+	ScanMasks<G> mk;
+	mk.init(gl);
+	for (int t = 0; t < trips; ++t) {
+		const int u = ulast - t;
+		const bool act = valid && u >= ch.u0;
+		const int uo = act ? u : ch.u0;
+		if (t == 0 || (uo & 15) == 15) word = __ldg(obs + ch.ow0 + (uo >> 4));
+		const int x = (word >> ((uo & 15) * 2)) & 3;
 		// emission counts: bins 0..L-2 only (khmm.c:310, 317)
-		if (u != ch.Lseq - 1) {
+		if (act && u != ch.Lseq - 1) {
 			const double w0 = (x == 0) ? su : 0.0, w1 = (x == 1) ? su : 0.0;
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) {
@@ -694,18 +808,18 @@ __device__ __forceinline__ void backward_chunk(const Chunk &ch, const LaneModel<
 				aE1[i] = fma(fb, w1, aE1[i]);
 			}
 		}
-		if (u == 0) break; // no transition into the first bin
+		const bool trans = act && u > 0; // no transition into the first bin of a sequence
 		// rotate the prefetch ring
 		double fm[SPL], sm = ns[0];
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) fm[i] = nf[0][i];
+		if (act) {
 #pragma unroll
-		for (int j = 0; j + 1 < PF; ++j) {
+			for (int j = 0; j + 1 < PF; ++j) {
 #pragma unroll
-			for (int i = 0; i < SPL; ++i) nf[j][i] = nf[j + 1][i];
-			ns[j] = ns[j + 1];
-		}
-		{
+				for (int i = 0; i < SPL; ++i) nf[j][i] = nf[j + 1][i];
+				ns[j] = ns[j + 1];
+			}
 			const int uu = u - 1 - PF;
 			if (uu >= 0) {
 				const size_t back = (size_t)(ulast - uu);
@@ -714,136 +828,143 @@ __device__ __forceinline__ void backward_chunk(const Chunk &ch, const LaneModel<
 			}
 		}
 		// transition u-1 -> u (khmm.c:313-318 for the counts, khmm.c:230-234 for b_{u-1})
-		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL];
+		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
+		emis_coef(x, c0, c1);
 #pragma unroll
-		for (int i = 0; i < SPL; ++i) {
-			const double em = (x == 0) ? M.e0[i] : ((x == 1) ? M.e1[i] : 1.0);
-			g[i] = em * b[i];
-		}
-		prefsuf<SPL, G>(g, M.V, M.Z, gl, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
-		prefsuf<SPL, G>(fm, M.W, M.U, gl, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
-		const double inv = 1.0 / sm;
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
+		prefsuf<SPL, G>(g, M.V, M.Z, mk, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
+		prefsuf<SPL, G>(fm, M.W, M.U, mk, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
+		if (trans) {
+			const double inv = fast_rcp(sm);
 #pragma unroll
-		for (int i = 0; i < SPL; ++i) {
-			aRL[i] = fma(fm[i], Pg[i], aRL[i]);
-			aRU[i] = fma(fm[i], Sg[i], aRU[i]);
-			aAD[i] = fma(fm[i], g[i], aAD[i]);
-			aCL[i] = fma(g[i], Sf[i], aCL[i]);
-			aCU[i] = fma(g[i], Pf[i], aCU[i]);
-			const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i]));
-			b[i] = bb * inv;
-			fu[i] = fm[i];
+			for (int i = 0; i < SPL; ++i) {
+				aRL[i] = fma(fm[i], Pg[i], aRL[i]);
+				aRU[i] = fma(fm[i], Sg[i], aRU[i]);
+				aAD[i] = fma(fm[i], g[i], aAD[i]);
+				aCL[i] = fma(g[i], Sf[i], aCL[i]);
+				aCU[i] = fma(g[i], Pf[i], aCU[i]);
+				const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i]));
+				b[i] = bb * inv;
+				fu[i] = fm[i];
+			}
+			su = sm;
 		}
-		su = sm;
 	}
-	double *po = part_c + s0;
+	if (valid) {
+		double *po = part_c + s0;
 #pragma unroll
-	for (int i = 0; i < SPL; ++i) {
-		po[S_E0 * NP + i] = aE0[i];
-		po[S_E1 * NP + i] = aE1[i];
-		po[S_RL * NP + i] = aRL[i] * M.U[i];
-		po[S_CL * NP + i] = aCL[i] * M.V[i];
-		po[S_RU * NP + i] = aRU[i] * M.W[i];
-		po[S_CU * NP + i] = aCU[i] * M.Z[i];
-		po[S_AD * NP + i] = aAD[i] * M.D[i];
+		for (int i = 0; i < SPL; ++i) {
+			po[S_E0 * NP + i] = aE0[i];
+			po[S_E1 * NP + i] = aE1[i];
+			po[S_RL * NP + i] = aRL[i] * M.U[i];
+			po[S_CL * NP + i] = aCL[i] * M.V[i];
+			po[S_RU * NP + i] = aRU[i] * M.W[i];
+			po[S_CU * NP + i] = aCU[i] * M.Z[i];
+			po[S_AD * NP + i] = aAD[i] * M.D[i];
+		}
 	}
 }
 
 // b_{ulast} in the reference's scaling from a direction beta: sum_k f[k] b[k] s = 1 (khmm.c:237 sanity identity)
-template <int SPL>
+template <int SPL, int G>
 __device__ __forceinline__ void scale_boundary(const Chunk &ch, const double (&beta)[SPL], double (&b)[SPL], int gl,
                                                const double *__restrict__ fhat, const double *__restrict__ sc)
 {
-	constexpr int NP = SPL * 32;
+	constexpr int NP = SPL * G;
 	double fu[SPL], dot = 0.0;
 	load_vec<SPL>(fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + gl * SPL, fu);
 	const double su = __ldg(sc + ch.gb0 + (ch.len - 1));
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) dot = fma(fu[i], beta[i], dot);
-	dot = gsum<32>(dot);
+	dot = gsum<G>(dot);
 	const double v = 1.0 / (su * dot);
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
 }
 
 // sum-normalised copy of b to dst (direction of the backward vector at a chunk boundary)
-template <int SPL>
-__device__ __forceinline__ void publish_direction(const double (&b)[SPL], double *__restrict__ dst, int gl)
+template <int SPL, int G>
+__device__ __forceinline__ void publish_direction(const double (&b)[SPL], double *__restrict__ dst, int gl, bool doit)
 {
 	double t = 0.0, nb[SPL];
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) t += b[i];
-	t = 1.0 / gsum<32>(t);
+	t = 1.0 / gsum<G>(t);
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) nb[i] = b[i] * t;
-	store_vec<SPL>(dst + gl * SPL, nb);
+	if (doit) store_vec<SPL>(dst + gl * SPL, nb);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: backward + expected counts.  One warp per chunk.  Per-warp partials: part[c][S_COUNT][NP].
+// K4: backward + expected counts.  One lane group per chunk.  Per-chunk partials: part[c][S_COUNT][NP].
 //   warm == 0 : the direction of b at the chunk's last bin comes from the boundary chain (bend).
-//   warm  > 0 : the warp first runs the bare backward recursion (direction only) from `warm` bins to the
+//   warm  > 0 : the group first runs the bare backward recursion (direction only) from `warm` bins to the
 //               RIGHT of its chunk, starting from ones, and saves the direction it reached (bwarm[c]);
 //               the chunk to the right publishes the direction it computed for the same bin (bexact[c]).
 // ------------------------------------------------------------------------------------------------
-template <int SPL>
+template <int SPL, int G>
 __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
                                                   const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                   const double *__restrict__ bend, int warm, const double *__restrict__ fhat,
                                                   const double *__restrict__ sc, double *__restrict__ part,
                                                   double *__restrict__ bwarm, double *__restrict__ bexact)
 {
-	constexpr int G = 32, NP = SPL * G;
-	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (c >= n_chunks) return;
-	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = uniform_chunk(chunks[c]);
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
-	M.load(model, s0);
+	M.load(model, s0, NP);
 	const int ulast = ch.u0 + ch.len - 1;
-	double b[SPL];
-	if (ch.flags & CH_LAST) { // khmm.c:226: b_L[k] = 1/s_L
+	const bool is_last = (ch.flags & CH_LAST) != 0;
+	double beta[SPL], b[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
+	if (warm > 0) { // lock-step warm-up of all groups of the warp (groups at a sequence end have nothing to do)
+		const int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
+		const int trips = warp_trips(id.valid ? z0 - ulast : 0);
+		uint32_t word = 0;
+		ScanMasks<G> mk;
+		mk.init(gl);
+		for (int t = 0; t < trips; ++t) {
+			const int u = z0 - t;
+			const bool act = id.valid && u > ulast;
+			const int uo = act ? u : ulast;
+			if (t == 0 || (uo & 15) == 15) word = __ldg(obs + ch.ow0 + (uo >> 4));
+			const int x = (word >> ((uo & 15) * 2)) & 3;
+			double g[SPL], out[SPL], c0, c1;
+			emis_coef(x, c0, c1);
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * beta[i];
+			semisep<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, mk, out);
+			double scl = 1.0;
+			if ((t & 7) == 7) { // exact power-of-two rescale, same factor in every lane of the group
+				double tt = 0.0;
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) tt += out[i];
+				tt = gsum<G>(tt);
+				if (tt > 1e-290 && tt < 1e290) scl = pow2i(-exponent_of(tt));
+			}
+			if (act) {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) beta[i] = out[i] * scl;
+			}
+		}
+		publish_direction<SPL, G>(beta, bwarm + (size_t)c * NP, gl, id.valid && !is_last);
+	} else if (!is_last) {
+		load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
+	}
+	// (the groups of a warp differ in is_last: everything containing a shuffle runs unconditionally, then selects)
+	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
+	if (is_last) { // khmm.c:226: b_L[k] = 1/s_L
 		const double v = 1.0 / __ldg(sc + ch.gb0 + (ch.len - 1));
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) b[i] = v;
-	} else {
-		double beta[SPL];
-		if (warm > 0) {
-			const int z0 = min(ch.Lseq - 1, ulast + warm);
-			uint32_t word = 0;
-#pragma unroll
-			for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
-			for (int u = z0; u > ulast; --u) {
-				if (u == z0 || (u & 15) == 15) word = __ldg(obs + ch.ow0 + (u >> 4));
-				const int x = (word >> ((u & 15) * 2)) & 3;
-				double g[SPL], out[SPL];
-#pragma unroll
-				for (int i = 0; i < SPL; ++i) {
-					const double em = (x == 0) ? M.e0[i] : ((x == 1) ? M.e1[i] : 1.0);
-					g[i] = em * beta[i];
-				}
-				semisep<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, gl, out);
-				if (((z0 - u) & 7) == 7) { // exact power-of-two rescale, same factor in every lane
-					double t = 0.0;
-#pragma unroll
-					for (int i = 0; i < SPL; ++i) t += out[i];
-					t = gsum<G>(t);
-					const double scl = (t > 1e-290 && t < 1e290) ? pow2i(-exponent_of(t)) : 1.0;
-#pragma unroll
-					for (int i = 0; i < SPL; ++i) beta[i] = out[i] * scl;
-				} else {
-#pragma unroll
-					for (int i = 0; i < SPL; ++i) beta[i] = out[i];
-				}
-			}
-			publish_direction<SPL>(beta, bwarm + (size_t)c * NP, gl);
-		} else {
-			load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
-		}
-		scale_boundary<SPL>(ch, beta, b, gl, fhat, sc);
 	}
-	backward_chunk<SPL>(ch, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP);
-	if (warm > 0 && !(ch.flags & CH_FIRST)) publish_direction<SPL>(b, bexact + (size_t)(c - 1) * NP, gl); // b of the last bin of chunk c-1
+	backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP);
+	// b now belongs to the last bin of chunk c-1: publish its direction for the certificate
+	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && warm > 0 && !(ch.flags & CH_FIRST));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -878,30 +999,33 @@ __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chun
 	}
 }
 
-template <int SPL>
-__global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict__ chunks, int n_chunks,
+template <int SPL, int G>
+__global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
+                                                         const int32_t *__restrict__ chunk_sub0, const Chunk *__restrict__ chunks,
                                                          const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                         const int32_t *__restrict__ flag_b, const double *__restrict__ bend,
+                                                         const int32_t *__restrict__ flag_b, const double *__restrict__ bsub,
                                                          const double *__restrict__ fhat, const double *__restrict__ sc,
-                                                         double *__restrict__ part, double *__restrict__ bwarm,
+                                                         double *__restrict__ partsub, double *__restrict__ bwarm,
                                                          double *__restrict__ bexact, unsigned long long *__restrict__ stat)
 {
-	constexpr int NP = SPL * 32;
-	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (c >= n_chunks || !flag_b[c]) return;
-	const int gl = threadIdx.x & 31, s0 = gl * SPL;
-	const Chunk ch = uniform_chunk(chunks[c]);
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_sub);
+	const int s = id.c, gl = id.gl, s0 = gl * SPL;
+	const int pc = parent[s];
+	const bool valid = id.valid && flag_b[pc] != 0;
+	if (!__any_sync(FULLMASK, valid)) return;
+	const Chunk ch = subs[s];
 	LaneModel<SPL> M;
-	M.load(model, s0);
+	M.load(model, s0, NP);
 	double beta[SPL], b[SPL];
-	load_vec<SPL>(bend + (size_t)c * NP + s0, beta);           // exact direction at the chunk's last bin (k_chain_runs)
-	publish_direction<SPL>(beta, bwarm + (size_t)c * NP, gl);  // this boundary agrees by construction from now on
-	scale_boundary<SPL>(ch, beta, b, gl, fhat, sc);
-	backward_chunk<SPL>(ch, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP);
-	if (gl == 0) atomicAdd(&stat[3], 1ull);
-	// the boundary to the left: if it belongs to the same run, chunk c-1 republishes nothing new (its own bend came from
-	// the chain); publishing the direction computed here keeps bexact[c-1] consistent for the next round's marks
-	if (!(ch.flags & CH_FIRST)) publish_direction<SPL>(b, bexact + (size_t)(c - 1) * NP, gl);
+	load_vec<SPL>(bsub + (size_t)s * NP + s0, beta);                                                           // exact direction at the sub-chunk's last bin (k_chain_subs)
+	publish_direction<SPL, G>(beta, bwarm + (size_t)pc * NP, gl, valid && chunk_sub0[pc + 1] - 1 == s);       // the chunk boundary agrees by construction from now on
+	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
+	backward_chunk<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP);
+	if (gl == 0 && valid) atomicAdd(&stat[3], 1ull);
+	// the first sub-chunk of a chunk ends at the boundary to chunk pc-1: publish the direction computed here
+	publish_direction<SPL, G>(b, bexact + (size_t)(pc > 0 ? pc - 1 : 0) * NP, gl,
+	                          valid && chunk_sub0[pc] == s && !(chunks[pc].flags & CH_FIRST));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1010,6 +1134,8 @@ __global__ void __launch_bounds__(128) k_decode(const Chunk *__restrict__ chunks
 		for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
 	}
 	uint32_t word = 0;
+	ScanMasks<G> mk;
+	mk.init(gl);
 	for (int u = ulast; u >= ch.u0; --u) {
 		if (u == ulast || (u & 15) == 15) word = __ldg(obs + ch.ow0 + (u >> 4));
 		const int x = (word >> ((u & 15) * 2)) & 3;
@@ -1057,7 +1183,7 @@ __global__ void __launch_bounds__(128) k_decode(const Chunk *__restrict__ chunks
 			t = gsum<G>(t);
 			if (gl == 0) p_recomb[u - 1] = 1.0 - t;
 		}
-		semisep<SPL, G>(g, cV, cU, cZ, cW, cD, gl, out);
+		semisep<SPL, G>(g, cV, cU, cZ, cW, cD, mk, out);
 		const double inv = 1.0 / sm;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) {
@@ -1089,12 +1215,19 @@ struct psmc_b200_ctx {
 	double *d_model = nullptr, *d_fhat = nullptr, *d_sc = nullptr, *d_T = nullptr, *d_vstart = nullptr, *d_bend = nullptr;
 	double *d_part = nullptr, *d_llpart = nullptr, *d_stats = nullptr;
 	double *d_fwarm = nullptr, *d_bwarm = nullptr, *d_bexact = nullptr; // warm-up mode: boundary vectors for the certificate
+	// sub-chunk tables of the repair rounds
+	int n_sub = 0, sub_len = 1536;
+	Chunk *d_sub = nullptr;
+	int32_t *d_sub_parent = nullptr, *d_chunk_sub0 = nullptr, *d_Texsub = nullptr;
+	double *d_Tsub = nullptr, *d_vsub = nullptr, *d_bsub = nullptr, *d_llsub = nullptr, *d_partsub = nullptr;
 	int32_t *d_flag = nullptr; // n_chunks + 2 boundary flags of the current repair round (entries -1 and n_chunks are always 0)
 	unsigned long long *d_cert = nullptr, *h_cert = nullptr;            // [failed boundaries, max fwd mismatch bits, max bwd mismatch bits]
 	int warm_len = 0;          // bins of warm-up overlap (0 = always use the transfer-matrix path)
 	double cert_eps = 1e-12;
 	bool mode_warm = false, certified = true;
 	int fallbacks = 0, repair_rounds = 3;
+	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
+	int g_fwd = 32, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
 	double mis_f = 0.0, mis_b = 0.0;
 	// decode scratch (allocated on demand)
@@ -1112,6 +1245,9 @@ struct psmc_b200_ctx {
 	bool launched = false;
 	bool fwd_valid = false; // fhat/sc/bend hold a complete forward pass + boundary chains
 };
+
+template <int NP>
+static void chunk_slots(const psmc_b200_ctx *c, int *slots_fwd, int *slots_bwd);
 
 extern "C" int psmc_b200_version(void) { return PSMC_B200_VERSION; }
 extern "C" const char *psmc_b200_last_error(void) { return g_err; }
@@ -1136,6 +1272,7 @@ static void free_ctx(psmc_b200_ctx *c)
 	cudaFree(c->d_obs); cudaFree(c->d_chunks); cudaFree(c->d_k1); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
 	cudaFree(c->d_Tex); cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_T);
 	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_fwarm); cudaFree(c->d_bwarm); cudaFree(c->d_bexact); cudaFree(c->d_cert); cudaFree(c->d_flag);
+	cudaFree(c->d_sub); cudaFree(c->d_sub_parent); cudaFree(c->d_chunk_sub0); cudaFree(c->d_Texsub); cudaFree(c->d_Tsub); cudaFree(c->d_vsub); cudaFree(c->d_bsub); cudaFree(c->d_llsub); cudaFree(c->d_partsub);
 	if (c->h_cert) cudaFreeHost(c->h_cert); cudaFree(c->d_part); cudaFree(c->d_llpart); cudaFree(c->d_stats);
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
 	if (c->h_model) cudaFreeHost(c->h_model);
@@ -1218,17 +1355,33 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	c->n_seqs = (int)c->L.size();
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device), PSMC_B200_ENODEV);
-	// chunk plan: enough chunks to fill the machine with one warp per chunk
+	// chunk plan.  The chunk kernels are latency-bound and every block lives as long as the kernel, so the plan
+	// must fit in ONE resident wave: chunks <= SMs x resident chunk slots of the tighter of the two kernels
+	// (one block too many doubles the kernel time; more chunks than that only add warm-up work).
+	{
+		const char *env = getenv("PSMC_B200_G_FWD");
+		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_fwd = atoi(env);
+		env = getenv("PSMC_B200_G_BWD");
+		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bwd = atoi(env);
+	}
 	if (chunk_len <= 0) {
 		const char *env = getenv("PSMC_B200_CHUNK");
 		if (env && atoi(env) > 0) chunk_len = atoi(env);
 	}
 	if (chunk_len <= 0) {
-		int wps = 16;
-		const char *env = getenv("PSMC_B200_WARPS_PER_SM");
-		if (env && atoi(env) > 0) wps = atoi(env);
-		int64_t target = (int64_t)prop.multiProcessorCount * wps;
-		int64_t cl = (c->total_bins + target - 1) / (target > 0 ? target : 1);
+		int sf = 4, sb = 4;
+		switch (c->NP) {
+		case 32: chunk_slots<32>(c, &sf, &sb); break;
+		case 64: chunk_slots<64>(c, &sf, &sb); break;
+		default: chunk_slots<128>(c, &sf, &sb); break;
+		}
+		int per_sm = std::min(sf, sb);
+		const char *env = getenv("PSMC_B200_CHUNKS_PER_SM");
+		if (env && atoi(env) > 0) per_sm = atoi(env);
+		c->slots_fwd = sf; c->slots_bwd = sb;
+		int64_t target = (int64_t)prop.multiProcessorCount * per_sm - c->n_seqs; // every sequence rounds its chunk count up
+		if (target < 1) target = 1;
+		int64_t cl = (c->total_bins + target - 1) / target;
 		if (cl < 512) cl = 512;
 		chunk_len = (int)std::min<int64_t>(cl, 1 << 24);
 	}
@@ -1279,6 +1432,30 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		gb += Li;
 	}
 	c->n_chunks = (int)c->chunks.size();
+	// sub-chunks (repair granularity): every chunk split into equal pieces of about sub_len bins
+	std::vector<Chunk> subs;
+	std::vector<int32_t> sub_parent, chunk_sub0((size_t)c->n_chunks + 1, 0);
+	{
+		const char *env = getenv("PSMC_B200_SUB_LEN");
+		if (env && atoi(env) >= 64) c->sub_len = atoi(env);
+		for (int ci = 0; ci < c->n_chunks; ++ci) {
+			const Chunk &pc = c->chunks[ci];
+			const int ns = std::max(1, (pc.len + c->sub_len - 1) / c->sub_len);
+			chunk_sub0[ci] = (int32_t)subs.size();
+			for (int k = 0; k < ns; ++k) {
+				Chunk sc_ = pc;
+				const int64_t a = (int64_t)pc.len * k / ns, b = (int64_t)pc.len * (k + 1) / ns;
+				sc_.u0 = pc.u0 + (int)a;
+				sc_.len = (int)(b - a);
+				sc_.gb0 = pc.gb0 + a;
+				sc_.flags = ((pc.flags & CH_FIRST) && k == 0 ? CH_FIRST : 0) | ((pc.flags & CH_LAST) && k == ns - 1 ? CH_LAST : 0);
+				subs.push_back(sc_);
+				sub_parent.push_back(ci);
+			}
+		}
+		chunk_sub0[c->n_chunks] = (int32_t)subs.size();
+		c->n_sub = (int)subs.size();
+	}
 	c->n_k1 = (int)k1.size();
 	const int NP = c->NP;
 #define ALLOC(ptr, bytes)                                                                         \
@@ -1316,6 +1493,15 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	ALLOC(c->d_bexact, sizeof(double) * (size_t)c->n_chunks * NP);
 	ALLOC(c->d_cert, sizeof(unsigned long long) * 8);
 	ALLOC(c->d_flag, sizeof(int32_t) * (size_t)(c->n_chunks + 2));
+	ALLOC(c->d_sub, sizeof(Chunk) * (size_t)c->n_sub);
+	ALLOC(c->d_sub_parent, sizeof(int32_t) * (size_t)c->n_sub);
+	ALLOC(c->d_chunk_sub0, sizeof(int32_t) * (size_t)(c->n_chunks + 1));
+	ALLOC(c->d_Tsub, sizeof(double) * (size_t)c->n_sub * NP * NP);
+	ALLOC(c->d_Texsub, sizeof(int32_t) * (size_t)c->n_sub * NP);
+	ALLOC(c->d_vsub, sizeof(double) * (size_t)c->n_sub * NP);
+	ALLOC(c->d_bsub, sizeof(double) * (size_t)c->n_sub * NP);
+	ALLOC(c->d_llsub, sizeof(double) * (size_t)c->n_sub);
+	ALLOC(c->d_partsub, sizeof(double) * (size_t)c->n_sub * S_COUNT * NP);
 #undef ALLOC
 #define CTRY(call)                                                                                \
 	do {                                                                                          \
@@ -1335,6 +1521,11 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	pack_all(c, sp.data());
 	CTRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
 	if (c->n_chunks) CTRY(cudaMemcpyAsync(c->d_chunks, c->chunks.data(), sizeof(Chunk) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream));
+	if (c->n_sub) {
+		CTRY(cudaMemcpyAsync(c->d_sub, subs.data(), sizeof(Chunk) * (size_t)c->n_sub, cudaMemcpyHostToDevice, c->stream));
+		CTRY(cudaMemcpyAsync(c->d_sub_parent, sub_parent.data(), sizeof(int32_t) * (size_t)c->n_sub, cudaMemcpyHostToDevice, c->stream));
+	}
+	CTRY(cudaMemcpyAsync(c->d_chunk_sub0, chunk_sub0.data(), sizeof(int32_t) * (size_t)(c->n_chunks + 1), cudaMemcpyHostToDevice, c->stream));
 	if (c->n_k1) CTRY(cudaMemcpyAsync(c->d_k1, k1.data(), sizeof(int32_t) * (size_t)c->n_k1, cudaMemcpyHostToDevice, c->stream));
 	if (c->n_seqs) {
 		CTRY(cudaMemcpyAsync(c->d_seq_c0, c->seq_c0.data(), sizeof(int32_t) * (size_t)c->n_seqs, cudaMemcpyHostToDevice, c->stream));
@@ -1422,6 +1613,68 @@ static void stage_model(psmc_b200_ctx *c, const psmc_b200_model *m)
 	}
 }
 
+// ---- lane-group width dispatch: G lanes per chunk, 32/G chunks per warp, SPL = NP/G states per lane ----
+// forward kernels are instantiated for SPL <= 8, backward kernels (7*SPL accumulators per lane) for SPL <= 4.
+static inline int blocks_for(int n_chunks, int G) { const int per_block = 4 * (32 / G); return (n_chunks + per_block - 1) / per_block; }
+
+template <int NP>
+static void run_forward(psmc_b200_ctx *c, int warm)
+{
+	cudaStream_t st = c->stream;
+#define FWD(G_) k_forward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
+	if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8);
+	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWD(16);
+	else FWD(32);
+#undef FWD
+}
+template <int NP>
+static void run_forward_repair(psmc_b200_ctx *c)
+{
+	cudaStream_t st = c->stream;
+#define FWR(G_) k_forward_repair<NP / G_, G_><<<blocks_for(c->n_sub, G_), 128, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4)
+	if (c->g_fwd == 8 && NP / 8 <= 8) FWR(8);
+	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWR(16);
+	else FWR(32);
+#undef FWR
+}
+template <int NP>
+static void run_backward(psmc_b200_ctx *c, int warm)
+{
+	cudaStream_t st = c->stream;
+#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, warm, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact)
+	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8);
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16);
+	else BWD(32);
+#undef BWD
+}
+template <int NP>
+static void run_backward_repair(psmc_b200_ctx *c)
+{
+	cudaStream_t st = c->stream;
+#define BWR(G_) k_backward_repair<NP / G_, G_><<<blocks_for(c->n_sub, G_), 128, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_chunks, c->d_obs, c->d_model, c->d_flag + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
+	if (c->g_bwd == 8 && NP / 8 <= 4) BWR(8);
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWR(16);
+	else BWR(32);
+#undef BWR
+}
+
+// resident chunk slots per SM of the selected forward / backward kernels (blocks of 128 threads)
+template <int NP>
+static void chunk_slots(const psmc_b200_ctx *c, int *slots_fwd, int *slots_bwd)
+{
+	int bf = 1, bb = 1, gf = 32, gb = 32;
+#define OCC(K_, G_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, K_<NP / G_, G_>, 128, 0)
+	if (c->g_fwd == 8 && NP / 8 <= 8) { gf = 8; OCC(k_forward, 8, bf); }
+	else if (c->g_fwd <= 16 && NP / 16 <= 8) { gf = 16; OCC(k_forward, 16, bf); }
+	else OCC(k_forward, 32, bf);
+	if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCC(k_backward, 8, bb); }
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) { gb = 16; OCC(k_backward, 16, bb); }
+	else OCC(k_backward, 32, bb);
+#undef OCC
+	*slots_fwd = bf * 4 * (32 / gf);
+	*slots_bwd = bb * 4 * (32 / gb);
+}
+
 template <int SPL>
 static int launch_core(psmc_b200_ctx *c, bool with_counts)
 {
@@ -1441,16 +1694,14 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[2], st);
-	const int wpb = 4; // warps per block
-	const int nblk = (c->n_chunks + wpb - 1) / wpb;
 	if (c->n_chunks > 0) {
-		k_forward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, 0, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm);
+		run_forward<NP>(c, 0);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[3], st);
 	if (with_counts) {
 		if (c->n_chunks > 0) {
-			k_backward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, 0, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact);
+			run_backward<NP>(c, 0);
 			++c->launches;
 		}
 		cudaEventRecord(c->ev[4], st);
@@ -1476,28 +1727,30 @@ static int launch_warm(psmc_b200_ctx *c)
 	cudaEventRecord(c->ev[1], st);
 	cudaEventRecord(c->ev[2], st);
 	const int wpb = 4, nblk = (c->n_chunks + wpb - 1) / wpb;
-	k_forward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, c->warm_len, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm);
+	run_forward<NP>(c, c->warm_len);
 	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
-	const dim3 gridT((unsigned)c->n_chunks, NP / COLS);
+	const dim3 gridT((unsigned)c->n_sub, NP / COLS);
 	for (int r = 0; r < c->repair_rounds; ++r) {
 		k_mark_fwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4);
-		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_chunks, nullptr, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, c->d_flag + 1, 1);
-		k_chain_runs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_chunks, c->d_flag + 1, 0, c->d_T, c->d_Tex, c->d_fhat, c->d_bexact, c->d_vstart, c->d_bend);
-		k_forward_repair<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_flag + 1, c->d_vstart, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, c->d_cert + 4);
+		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3);
+		k_chain_subs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
+		run_forward_repair<NP>(c);
+		k_fold<<<c->n_chunks, 128, 0, st>>>(c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[3], st);
-	k_backward<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, c->warm_len, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact);
+	run_backward<NP>(c, c->warm_len);
 	for (int r = 0; r < c->repair_rounds; ++r) {
 		k_mark_bwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag + 1, c->d_cert + 4);
-		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_chunks, nullptr, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, c->d_flag + 1, 2);
-		k_chain_runs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_chunks, c->d_flag + 1, 1, c->d_T, c->d_Tex, c->d_fhat, c->d_bexact, c->d_vstart, c->d_bend);
-		k_backward_repair<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_flag + 1, c->d_bend, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact, c->d_cert + 4);
+		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3);
+		k_chain_subs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 1, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
+		run_backward_repair<NP>(c);
+		k_fold<<<c->n_chunks, 128, 0, st>>>(c->d_chunk_sub0, c->d_flag + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[4], st);
 	k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->N, NP, c->d_stats);
 	k_certify<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, c->d_cert);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 4 + 8 * c->repair_rounds;
+	c->launches = 4 + 10 * c->repair_rounds;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 	c->fwd_valid = false; // bend[] is not filled in this mode; decode runs its own forward pass
