@@ -349,7 +349,10 @@ def run_own(args):
                        "what": "psmch_em_iterate from host buffers; every step re-packs and re-sends all contigs (H2D), sends the model, reads the statistics back"},
                "gpu_launches": int(n_launch),
                "clocks": clocks,
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            # dram__bytes_read+write of k_forward + k_backward per bin from the committed ncu --set full capture
+                            # (profiles/r01_ncu_full_forward_backward.txt: 3.688 GB + 3.760 GB over 7 187 491 bins), scaled to this launch
+                            "traffic": 1036.3 * my_bins / 1e9, "traffic_unit": "GB per E-step (k_forward + k_backward; ncu, scaled per bin)",
                             "kernel": "whole E-step (all kernels of one iteration on rank 0; dominant: %s)" % names[dom],
                             "algorithmic_bytes_per_bin": alg_bytes_per_bin, "bins_per_launch": my_bins, "peak_source": peak_src,
                             "estep_ms": estep_ms, "kernels": per_kernel},

@@ -664,7 +664,7 @@ __device__ __forceinline__ double forward_chunk(const Chunk &ch, bool valid, int
 template <int SPL, int G>
 __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                 const double *__restrict__ vstart, int warm, double *__restrict__ fhat,
+                                                 const double *__restrict__ vstart, int warm, int use_prev, double *__restrict__ fhat,
                                                  double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm)
 {
 	constexpr int NP = SPL * G;
@@ -678,8 +678,16 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	int ubeg = ch.u0;
 	if ((ch.flags & CH_FIRST) || warm > 0) {
 		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - warm);
+		if (use_prev && ubeg > 0) {
+			// warm start: the vector the PREVIOUS E-step stored for bin ubeg-1 (the parameters moved only a little since;
+			// any positive vector is a legal start -- the certificate decides -- so a stale or concurrently rewritten row is harmless)
+			const double *row = fhat + ((size_t)ch.gb0 - (size_t)(ch.u0 - ubeg) - 1) * NP + s0;
 #pragma unroll
-		for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
+			for (int i = 0; i < SPL; ++i) f[i] = fmax(row[i], 1e-300);
+		} else {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
+		}
 	} else {
 		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
 	}
@@ -761,7 +769,8 @@ __global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict_
 template <int SPL, int G>
 __device__ __forceinline__ void backward_chunk(const Chunk &ch, bool valid, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
                                                const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
-                                               const double *__restrict__ sc, double *__restrict__ part_c)
+                                               const double *__restrict__ sc, double *__restrict__ part_c,
+                                               double *__restrict__ bsave_c = nullptr, int usave = -1)
 {
 	constexpr int NP = SPL * G, PF = 4;
 	const int s0 = gl * SPL;
@@ -798,6 +807,7 @@ __device__ __forceinline__ void backward_chunk(const Chunk &ch, bool valid, cons
 		const int uo = act ? u : ch.u0;
 		if (t == 0 || (uo & 15) == 15) word = __ldg(obs + ch.ow0 + (uo >> 4));
 		const int x = (word >> ((uo & 15) * 2)) & 3;
+		if (act && u == usave && bsave_c) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
 		// emission counts: bins 0..L-2 only (khmm.c:310, 317)
 		if (act && u != ch.Lseq - 1) {
 			const double w0 = (x == 0) ? su : 0.0, w1 = (x == 1) ? su : 0.0;
@@ -907,7 +917,8 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
                                                   const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                   const double *__restrict__ bend, int warm, const double *__restrict__ fhat,
                                                   const double *__restrict__ sc, double *__restrict__ part,
-                                                  double *__restrict__ bwarm, double *__restrict__ bexact)
+                                                  double *__restrict__ bwarm, double *__restrict__ bexact,
+                                                  const double *__restrict__ bsave_prev, double *__restrict__ bsave_next, int warm_next)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
@@ -922,7 +933,16 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
 	if (warm > 0) { // lock-step warm-up of all groups of the warp (groups at a sequence end have nothing to do)
-		const int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
+		int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
+		if (bsave_prev && !is_last) {
+			// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin
+			// min(ulast + warm, last bin of the right neighbour) -- see usave below
+			const Chunk nx = chunks[c + 1];
+			z0 = min(ulast + warm, nx.u0 + nx.len - 1);
+			const double *row = bsave_prev + (size_t)c * NP + s0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) beta[i] = fmax(row[i], 1e-300);
+		}
 		const int trips = warp_trips(id.valid ? z0 - ulast : 0);
 		uint32_t word = 0;
 		ScanMasks<G> mk;
@@ -962,7 +982,10 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) b[i] = v;
 	}
-	backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP);
+	// the bin whose b the left neighbour will start its next overlap from (inside this chunk)
+	const int usave = (ch.flags & CH_FIRST) ? -1 : min(ch.u0 - 1 + warm_next, ulast);
+	backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
+	                       bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
 	// b now belongs to the last bin of chunk c-1: publish its direction for the certificate
 	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && warm > 0 && !(ch.flags & CH_FIRST));
 }
@@ -1214,7 +1237,11 @@ struct psmc_b200_ctx {
 	int32_t *d_k1 = nullptr, *d_seq_c0 = nullptr, *d_seq_nc = nullptr, *d_Tex = nullptr;
 	double *d_model = nullptr, *d_fhat = nullptr, *d_sc = nullptr, *d_T = nullptr, *d_vstart = nullptr, *d_bend = nullptr;
 	double *d_part = nullptr, *d_llpart = nullptr, *d_stats = nullptr;
-	double *d_fwarm = nullptr, *d_bwarm = nullptr, *d_bexact = nullptr; // warm-up mode: boundary vectors for the certificate
+	double *d_fwarm = nullptr, *d_bwarm = nullptr, *d_bexact = nullptr;
+	double *d_bsave[2] = {nullptr, nullptr}; // backward warm-start directions, double-buffered over E-steps
+	int bsave_cur = 0;         // index of the buffer the NEXT E-step reads
+	bool have_prev = false;    // fhat / d_bsave[bsave_cur] hold a previous E-step of the same data
+	int warm_hot = 0;          // overlap when warm-started from the previous E-step (PSMC_B200_WARM_HOT; 0 = always cold: early EM iterations move the model too much for a short overlap to reach the certificate) // warm-up mode: boundary vectors for the certificate
 	// sub-chunk tables of the repair rounds
 	int n_sub = 0, sub_len = 1536;
 	Chunk *d_sub = nullptr;
@@ -1271,7 +1298,7 @@ static void free_ctx(psmc_b200_ctx *c)
 	cudaSetDevice(c->device);
 	cudaFree(c->d_obs); cudaFree(c->d_chunks); cudaFree(c->d_k1); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
 	cudaFree(c->d_Tex); cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_T);
-	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_fwarm); cudaFree(c->d_bwarm); cudaFree(c->d_bexact); cudaFree(c->d_cert); cudaFree(c->d_flag);
+	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_fwarm); cudaFree(c->d_bwarm); cudaFree(c->d_bexact); cudaFree(c->d_cert); cudaFree(c->d_flag); cudaFree(c->d_bsave[0]); cudaFree(c->d_bsave[1]);
 	cudaFree(c->d_sub); cudaFree(c->d_sub_parent); cudaFree(c->d_chunk_sub0); cudaFree(c->d_Texsub); cudaFree(c->d_Tsub); cudaFree(c->d_vsub); cudaFree(c->d_bsub); cudaFree(c->d_llsub); cudaFree(c->d_partsub);
 	if (c->h_cert) cudaFreeHost(c->h_cert); cudaFree(c->d_part); cudaFree(c->d_llpart); cudaFree(c->d_stats);
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
@@ -1390,6 +1417,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		const char *env = getenv("PSMC_B200_WARM");
 		c->warm_len = env ? atoi(env) : 8192;
 		if (c->warm_len < 0) c->warm_len = 0;
+		env = getenv("PSMC_B200_WARM_HOT");
+		if (env && atoi(env) >= 0) c->warm_hot = atoi(env);
 		env = getenv("PSMC_B200_REPAIR_ROUNDS");
 		if (env && atoi(env) >= 0) c->repair_rounds = atoi(env);
 		env = getenv("PSMC_B200_CERT_EPS");
@@ -1491,6 +1520,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	ALLOC(c->d_fwarm, sizeof(double) * (size_t)c->n_chunks * NP);
 	ALLOC(c->d_bwarm, sizeof(double) * (size_t)c->n_chunks * NP);
 	ALLOC(c->d_bexact, sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_bsave[0], sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_bsave[1], sizeof(double) * (size_t)c->n_chunks * NP);
 	ALLOC(c->d_cert, sizeof(unsigned long long) * 8);
 	ALLOC(c->d_flag, sizeof(int32_t) * (size_t)(c->n_chunks + 2));
 	ALLOC(c->d_sub, sizeof(Chunk) * (size_t)c->n_sub);
@@ -1569,7 +1600,7 @@ extern "C" int psmc_b200_upload(psmc_b200_ctx *c, int32_t n_seqs, const int32_t 
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	pack_all(c, sp.data());
 	CUDA_TRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
-	c->fwd_valid = false;
+	c->fwd_valid = false; // (have_prev stays: stale vectors are still legal warm starts, the certificate decides)
 	return 0;
 }
 
@@ -1618,10 +1649,10 @@ static void stage_model(psmc_b200_ctx *c, const psmc_b200_model *m)
 static inline int blocks_for(int n_chunks, int G) { const int per_block = 4 * (32 / G); return (n_chunks + per_block - 1) / per_block; }
 
 template <int NP>
-static void run_forward(psmc_b200_ctx *c, int warm)
+static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
-#define FWD(G_) k_forward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
+#define FWD(G_) k_forward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
 	if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8);
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWD(16);
 	else FWD(32);
@@ -1638,10 +1669,10 @@ static void run_forward_repair(psmc_b200_ctx *c)
 #undef FWR
 }
 template <int NP>
-static void run_backward(psmc_b200_ctx *c, int warm)
+static void run_backward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
-#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, warm, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact)
+#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, warm, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact, use_prev ? c->d_bsave[c->bsave_cur] : nullptr, c->d_bsave[c->bsave_cur ^ 1], c->warm_hot)
 	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8);
 	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16);
 	else BWD(32);
@@ -1695,14 +1726,15 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	}
 	cudaEventRecord(c->ev[2], st);
 	if (c->n_chunks > 0) {
-		run_forward<NP>(c, 0);
+		run_forward<NP>(c, 0, 0);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[3], st);
 	if (with_counts) {
 		if (c->n_chunks > 0) {
-			run_backward<NP>(c, 0);
+			run_backward<NP>(c, 0, 0);
 			++c->launches;
+			c->bsave_cur ^= 1; // this pass saved the warm-start directions of the next one
 		}
 		cudaEventRecord(c->ev[4], st);
 		k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->N, NP, c->d_stats);
@@ -1712,6 +1744,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 	c->fwd_valid = true;
+	if (with_counts) c->have_prev = true;
 	return 0;
 }
 
@@ -1727,7 +1760,9 @@ static int launch_warm(psmc_b200_ctx *c)
 	cudaEventRecord(c->ev[1], st);
 	cudaEventRecord(c->ev[2], st);
 	const int wpb = 4, nblk = (c->n_chunks + wpb - 1) / wpb;
-	run_forward<NP>(c, c->warm_len);
+	const int hot = (c->have_prev && c->warm_hot > 0) ? 1 : 0;
+	const int wl = hot ? c->warm_hot : c->warm_len;
+	run_forward<NP>(c, wl, hot);
 	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 	const dim3 gridT((unsigned)c->n_sub, NP / COLS);
 	for (int r = 0; r < c->repair_rounds; ++r) {
@@ -1738,7 +1773,8 @@ static int launch_warm(psmc_b200_ctx *c)
 		k_fold<<<c->n_chunks, 128, 0, st>>>(c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[3], st);
-	run_backward<NP>(c, c->warm_len);
+	run_backward<NP>(c, wl, hot);
+	c->bsave_cur ^= 1;
 	for (int r = 0; r < c->repair_rounds; ++r) {
 		k_mark_bwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag + 1, c->d_cert + 4);
 		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3);
@@ -1756,6 +1792,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	c->fwd_valid = false; // bend[] is not filled in this mode; decode runs its own forward pass
 	c->mode_warm = true;
 	c->certified = false;
+	c->have_prev = true;
 	return 0;
 }
 
