@@ -27,8 +27,12 @@ static double objective(int n, double *x, void *data)
 	int i;
 	++a->cnt;
 	for (i = 0; i < n; ++i) em->model.params[i] = fabs(x[i]);
-	psmch_model_update(&em->sp, em->model.params, &em->model);
-	return -psmch_Q(&em->model, &em->counts);
+	if (em->exact_mstep) {
+		psmch_model_update(&em->sp, em->model.params, &em->model);
+		return -psmch_Q(&em->model, &em->counts);
+	}
+	psmch_model_update_fast(&em->sp, em->model.params, &em->model); /* exp/log through libmvec: a few ulp from the scalar path */
+	return -psmch_Q_fast(&em->model, &em->counts);
 }
 
 int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void))
@@ -63,6 +67,7 @@ int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq,
 	psmch_model_update(&em->sp, em->model.params, &em->model);
 	/* shard whole sequences over the GPUs: longest-processing-time first */
 	em->n_gpus = o->n_gpus;
+	em->exact_mstep = getenv("PSMC_B200_EXACT_MSTEP") != 0; /* scalar libm in every trial evaluation */
 	em->n_seqs = sq->n_seqs;
 	em->seq_owner = (int*)calloc(sq->n_seqs > 0 ? sq->n_seqs : 1, sizeof(int));
 	{
@@ -176,6 +181,8 @@ int psmch_em_mstep(psmch_em_t *em, FILE *fpout)
 	em->hj_calls = aux.cnt;
 	if (fpout) fprintf(fpout, "IT\t%d\n", aux.cnt);
 	free(x);
+	/* the model stays at the LAST EVALUATED trial point (em.c:61-67), recomputed with the scalar bit-reproducible path */
+	psmch_model_update(&em->sp, em->model.params, &em->model);
 	for (k = 0; k < N; ++k) sum += em->counts.E[k] + em->counts.E[N + k];
 	for (k = 0; k < N; ++k) em->post_sigma[k] = (em->counts.E[k] + em->counts.E[N + k]) / sum;
 	em->t_mstep_ms = now_ms() - t1;

@@ -101,3 +101,33 @@ double psmch_Q(const psmch_model_t *m, const psmch_counts_t *c)
 	}
 	return sum - c->Q0;
 }
+
+/* psmch_Q with all 7N logarithms in one vectorised sweep (same guards, same value to rounding). */
+void psmch_vlog(int n, const double *x, double *y);
+double psmch_vdot(int n, const double *a, const double *b);
+
+double psmch_Q_fast(const psmch_model_t *m, const psmch_counts_t *c)
+{
+	const int N = m->N;
+	double *x = m->vw + 4 * (N + 2), *w = x + 7 * N, *lg = w + 7 * N; /* vw: 4*(N+2) used by the model, then 3 x 7N here */
+	int k, n = 0;
+	for (k = 0; k < 2 * N; ++k)
+		if (m->e[k] <= 0.0) return -PSMCH_INF;
+	for (k = 0; k < N; ++k) {
+		if (m->D[k] <= 0.0) return -PSMCH_INF;
+		if (k > 0 && (m->U[k] * m->V[0] <= 0.0 || m->U[N - 1] * m->V[k - 1] <= 0.0)) return -PSMCH_INF;
+		if (k < N - 1 && (m->W[k] * m->Z[N - 1] <= 0.0 || m->W[0] * m->Z[k + 1] <= 0.0)) return -PSMCH_INF;
+	}
+	for (k = 0; k < 2 * N; ++k) { x[n] = m->e[k]; w[n] = c->E[k]; ++n; }
+	for (k = 0; k < N; ++k) { x[n] = m->D[k]; w[n] = c->AD[k]; ++n; }
+	for (k = 1; k < N; ++k) {
+		x[n] = fabs(m->U[k]); w[n] = c->RL[k]; ++n;
+		x[n] = fabs(m->Z[k]); w[n] = c->CU[k]; ++n;
+	}
+	for (k = 0; k < N - 1; ++k) {
+		x[n] = fabs(m->W[k]); w[n] = c->RU[k]; ++n;
+		x[n] = fabs(m->V[k]); w[n] = c->CL[k]; ++n;
+	}
+	psmch_vlog(n, x, lg);
+	return psmch_vdot(n, w, lg) - c->Q0;
+}

@@ -78,11 +78,13 @@ typedef struct {
 	double *U, *V, *W, *Z, *D;         /* N each */
 	double C_pi, C_sigma;
 	double *lam, *alp, *bet, *qax, *tau; /* scratch */
+	double *vw;                          /* scratch of the vectorised trial evaluations */
 } psmch_model_t;
 
 int  psmch_model_alloc(psmch_model_t *m, const psmch_space_t *sp);
 void psmch_model_free(psmch_model_t *m);
 void psmch_model_update(const psmch_space_t *sp, const double *params, psmch_model_t *m); /* core.c:61-133 */
+void psmch_model_update_fast(const psmch_space_t *sp, const double *params, psmch_model_t *m); /* same, exp/log via libmvec: trial points of the M-step only */
 void psmch_model_dense(const psmch_model_t *m, double *a /* N*N */);
 void psmch_avg_t(const psmch_space_t *sp, const psmch_model_t *m, double *avg_t);           /* core.c:135-162 */
 void psmch_model_view(const psmch_model_t *m, psmc_b200_model *v);
@@ -103,6 +105,7 @@ void   psmch_counts_view(psmch_counts_t *c, psmc_b200_stats *v);
 void   psmch_counts_from_dense(psmch_counts_t *c); /* marginals of c->A */
 double psmch_Q0(psmch_counts_t *c);                 /* khmm.c:326-342; transition part needs c->A, else a marginal surrogate */
 double psmch_Q(const psmch_model_t *m, const psmch_counts_t *c); /* khmm.c:363-382 in O(N) on the factored model */
+double psmch_Q_fast(const psmch_model_t *m, const psmch_counts_t *c); /* same value to a few ulp; logs via libmvec (uses m->vw) */
 
 /* ---- Hooke-Jeeves ---------------------------------------------------------------------------- */
 typedef double (*psmch_func_t)(int n, double *x, void *data);
@@ -138,6 +141,7 @@ typedef struct {
 	int *seq_owner; /* per sequence: which context holds it */
 	int64_t n_seqs;
 	int hj_calls;
+	int exact_mstep; /* PSMC_B200_EXACT_MSTEP: trial evaluations with scalar libm instead of libmvec */
 	double t_estep_ms, t_mstep_ms; /* wall time of the last iteration */
 } psmch_em_t;
 

@@ -163,13 +163,17 @@ void psmch_py_em_counts(void *h, double *E, double *RL, double *CL, double *RU, 
 /* ---- M-step on caller-supplied counts (no GPU involved): used by the CPU tests --------------------
  * params: in = start point, out = last evaluated point (the reference's quirk); res = {Q0(before), Q1, calls, Q0_offset}
  * A may be NULL (then the structured marginals are taken as given). */
-typedef struct { psmch_space_t *sp; psmch_model_t *m; psmch_counts_t *c; int cnt; } maux_t;
+typedef struct { psmch_space_t *sp; psmch_model_t *m; psmch_counts_t *c; int cnt, fast; } maux_t;
 static double mobjective(int n, double *x, void *data)
 {
 	maux_t *a = (maux_t*)data;
 	int i;
 	++a->cnt;
 	for (i = 0; i < n; ++i) a->m->params[i] = x[i] < 0 ? -x[i] : x[i];
+	if (a->fast) {
+		psmch_model_update_fast(a->sp, a->m->params, a->m);
+		return -psmch_Q_fast(a->m, a->c);
+	}
 	psmch_model_update(a->sp, a->m->params, a->m);
 	return -psmch_Q(a->m, a->c);
 }
@@ -197,11 +201,12 @@ int psmch_py_mstep(const char *pattern, double alpha0, double *params, const dou
 	res[0] = psmch_Q(&m, &c);
 	x = (double*)malloc(sizeof(double) * sp.n_params);
 	memcpy(x, params, sizeof(double) * sp.n_params);
-	a.sp = &sp; a.m = &m; a.c = &c; a.cnt = 0;
+	a.sp = &sp; a.m = &m; a.c = &c; a.cnt = 0; a.fast = getenv("PSMC_B200_EXACT_MSTEP") == 0;
 	res[1] = -psmch_hooke_jeeves(mobjective, sp.n_params, x, &a, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL);
 	res[2] = a.cnt;
 	memcpy(params, m.params, sizeof(double) * sp.n_params);
 	free(x);
+	psmch_model_update(&sp, m.params, &m);
 	psmch_counts_free(&c); psmch_model_free(&m); psmch_space_free(&sp);
 	return 0;
 }
