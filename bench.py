@@ -66,15 +66,17 @@ from psmc_b200.sharding import lpt_shards  # noqa: E402
 
 
 class ClockSampler:
-    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line).  The sampler is started before the
+    warm-up (nvidia-smi needs a moment to come up); only rows whose timestamp falls inside [t0, t1] count, and if the timed
+    region was too short to catch one, the rows taken while the GPU was under the same load (warm-up .. end) are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -83,9 +85,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,21 +95,29 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smmax, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smmax.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def digest(rows):
+            sm, smmax, reasons, pw = [], [], set(), []
+            for _, r in rows:
+                f = [x.strip() for x in r.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); smmax.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, smmax, reasons, pw
+        inside = [r for r in self.rows if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = self.rows, "warm-up + timed region (the timed region was shorter than one sampling period)"
+        sm, smmax, reasons, pw = digest(inside)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -296,12 +306,13 @@ def run_own(args):
             dt = float(t.item())
         return dt
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     kern_ms.clear(); launches[0] = 0
-    sampler = ClockSampler(local) if rank == 0 else None
+    t_clk0 = time.time()
     dt = timed(args.steps, upload=False)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_clk0, time.time()) if sampler else None
     k_resident = [list(x) for x in kern_ms]
     n_launch = launches[0]
     st = em.state()
@@ -370,7 +381,7 @@ def run_own(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale every contig length (1.0 = the 28.8 M-bin workload)")

@@ -906,19 +906,79 @@ __device__ __forceinline__ void publish_direction(const double (&b)[SPL], double
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4w: the backward warm-up on its own (needs only the observations and the model, so it runs on a second stream
+// concurrently with the forward pass): direction of b at the last bin of every chunk that does not end its sequence,
+// from `warm` bins to the right (or from the previous E-step's saved direction), sum-normalised into bwarm[c].
+template <int SPL, int G>
+__global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__ chunks, int n_chunks,
+                                                       const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0, NP);
+	const int ulast = ch.u0 + ch.len - 1;
+	const bool is_last = (ch.flags & CH_LAST) != 0;
+	double beta[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
+	int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
+	if (bsave_prev && !is_last) {
+		// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin
+		// min(ulast + warm, last bin of the right neighbour) -- see usave in k_backward
+		const Chunk nx = chunks[c + 1];
+		z0 = min(ulast + warm, nx.u0 + nx.len - 1);
+		const double *row = bsave_prev + (size_t)c * NP + s0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) beta[i] = fmax(row[i], 1e-300);
+	}
+	const int trips = warp_trips(id.valid ? z0 - ulast : 0);
+	uint32_t word = 0;
+	ScanMasks<G> mk;
+	mk.init(gl);
+	for (int t = 0; t < trips; ++t) {
+		const int u = z0 - t;
+		const bool act = id.valid && u > ulast;
+		const int uo = act ? u : ulast;
+		if (t == 0 || (uo & 15) == 15) word = __ldg(obs + ch.ow0 + (uo >> 4));
+		const int x = (word >> ((uo & 15) * 2)) & 3;
+		double g[SPL], out[SPL], c0, c1;
+		emis_coef(x, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * beta[i];
+		semisep<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, mk, out);
+		double scl = 1.0;
+		if ((t & 7) == 7) { // exact power-of-two rescale, same factor in every lane of the group
+			double tt = 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) tt += out[i];
+			tt = gsum<G>(tt);
+			if (tt > 1e-290 && tt < 1e290) scl = pow2i(-exponent_of(tt));
+		}
+		if (act) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) beta[i] = out[i] * scl;
+		}
+	}
+	publish_direction<SPL, G>(beta, bwarm + (size_t)c * NP, gl, id.valid && !is_last);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: backward + expected counts.  One lane group per chunk.  Per-chunk partials: part[c][S_COUNT][NP].
-//   warm == 0 : the direction of b at the chunk's last bin comes from the boundary chain (bend).
-//   warm  > 0 : the group first runs the bare backward recursion (direction only) from `warm` bins to the
-//               RIGHT of its chunk, starting from ones, and saves the direction it reached (bwarm[c]);
-//               the chunk to the right publishes the direction it computed for the same bin (bexact[c]).
+// The direction of b at the chunk's last bin is read from `bdir`: the boundary chain's bend (transfer mode) or the
+// warm-up result bwarm (fast path, K4w).  With publish != 0 the direction computed for the last bin of chunk c-1
+// goes to bexact[c-1] for the certificate; usave/bsave_next feed the optional warm start of the next E-step.
 // ------------------------------------------------------------------------------------------------
 template <int SPL, int G>
 __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
                                                   const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                  const double *__restrict__ bend, int warm, const double *__restrict__ fhat,
+                                                  const double *__restrict__ bdir, int publish, const double *__restrict__ fhat,
                                                   const double *__restrict__ sc, double *__restrict__ part,
-                                                  double *__restrict__ bwarm, double *__restrict__ bexact,
-                                                  const double *__restrict__ bsave_prev, double *__restrict__ bsave_next, int warm_next)
+                                                  double *__restrict__ bexact, double *__restrict__ bsave_next, int warm_next)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
@@ -930,51 +990,7 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 	const int ulast = ch.u0 + ch.len - 1;
 	const bool is_last = (ch.flags & CH_LAST) != 0;
 	double beta[SPL], b[SPL];
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
-	if (warm > 0) { // lock-step warm-up of all groups of the warp (groups at a sequence end have nothing to do)
-		int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
-		if (bsave_prev && !is_last) {
-			// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin
-			// min(ulast + warm, last bin of the right neighbour) -- see usave below
-			const Chunk nx = chunks[c + 1];
-			z0 = min(ulast + warm, nx.u0 + nx.len - 1);
-			const double *row = bsave_prev + (size_t)c * NP + s0;
-#pragma unroll
-			for (int i = 0; i < SPL; ++i) beta[i] = fmax(row[i], 1e-300);
-		}
-		const int trips = warp_trips(id.valid ? z0 - ulast : 0);
-		uint32_t word = 0;
-		ScanMasks<G> mk;
-		mk.init(gl);
-		for (int t = 0; t < trips; ++t) {
-			const int u = z0 - t;
-			const bool act = id.valid && u > ulast;
-			const int uo = act ? u : ulast;
-			if (t == 0 || (uo & 15) == 15) word = __ldg(obs + ch.ow0 + (uo >> 4));
-			const int x = (word >> ((uo & 15) * 2)) & 3;
-			double g[SPL], out[SPL], c0, c1;
-			emis_coef(x, c0, c1);
-#pragma unroll
-			for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * beta[i];
-			semisep<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, mk, out);
-			double scl = 1.0;
-			if ((t & 7) == 7) { // exact power-of-two rescale, same factor in every lane of the group
-				double tt = 0.0;
-#pragma unroll
-				for (int i = 0; i < SPL; ++i) tt += out[i];
-				tt = gsum<G>(tt);
-				if (tt > 1e-290 && tt < 1e290) scl = pow2i(-exponent_of(tt));
-			}
-			if (act) {
-#pragma unroll
-				for (int i = 0; i < SPL; ++i) beta[i] = out[i] * scl;
-			}
-		}
-		publish_direction<SPL, G>(beta, bwarm + (size_t)c * NP, gl, id.valid && !is_last);
-	} else if (!is_last) {
-		load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
-	}
+	load_vec<SPL>(bdir + (size_t)c * NP + s0, beta);
 	// (the groups of a warp differ in is_last: everything containing a shuffle runs unconditionally, then selects)
 	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
 	if (is_last) { // khmm.c:226: b_L[k] = 1/s_L
@@ -987,7 +1003,7 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 	backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
 	                       bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
 	// b now belongs to the last bin of chunk c-1: publish its direction for the certificate
-	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && warm > 0 && !(ch.flags & CH_FIRST));
+	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && publish && !(ch.flags & CH_FIRST));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1063,19 +1079,19 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_certify(const Chunk *__restrict__ chunks, int n_chunks, int N,
                                                  const double *__restrict__ fhat, const double *__restrict__ fwarm,
                                                  const double *__restrict__ bwarm, const double *__restrict__ bexact,
-                                                 double eps, unsigned long long *__restrict__ cert)
+                                                 double eps, int dir, unsigned long long *__restrict__ cert)
 {
+	// dir 0: forward boundaries of the forward plan; dir 1: backward boundaries of the backward plan
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31, s0 = gl * SPL;
 	const Chunk ch = chunks[c];
 	if (ch.flags & CH_LAST) return;
-	const double mf = fwd_boundary_mismatch<SPL>(chunks[c + 1], c + 1, fhat, fwarm, s0, N);
-	const double mb = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, s0, N);
+	const double m = dir == 0 ? fwd_boundary_mismatch<SPL>(chunks[c + 1], c + 1, fhat, fwarm, s0, N)
+	                          : bwd_boundary_mismatch<SPL>(c, bwarm, bexact, s0, N);
 	if (gl == 0) {
-		if (!(mf <= eps) || !(mb <= eps)) atomicAdd(&cert[0], 1ull);
-		atomicMax(&cert[1], (unsigned long long)__double_as_longlong(mf));
-		atomicMax(&cert[2], (unsigned long long)__double_as_longlong(mb));
+		if (!(m <= eps)) atomicAdd(&cert[0], 1ull);
+		atomicMax(&cert[1 + dir], (unsigned long long)__double_as_longlong(m));
 	}
 }
 
@@ -1085,7 +1101,7 @@ __global__ void __launch_bounds__(128) k_certify(const Chunk *__restrict__ chunk
 // grid = 1 + S_COUNT*N blocks, block = 256 threads; block 0 reduces LL.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part, const double *__restrict__ llpart,
-                                                int n_chunks, int N, int NP, double *__restrict__ out)
+                                                int n_chunks, int n_part, int N, int NP, double *__restrict__ out)
 {
 	__shared__ double sh[256];
 	const int o = blockIdx.x;
@@ -1095,7 +1111,7 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part,
 	} else {
 		const int row = (o - 1) / N, k = (o - 1) % N;
 		const double *p = part + (size_t)row * NP + k;
-		for (int c = threadIdx.x; c < n_chunks; c += 256) acc += p[(size_t)c * S_COUNT * NP];
+		for (int c = threadIdx.x; c < n_part; c += 256) acc += p[(size_t)c * S_COUNT * NP];
 	}
 	sh[threadIdx.x] = acc;
 	__syncthreads();
@@ -1229,8 +1245,8 @@ struct psmc_b200_ctx {
 	std::vector<int32_t> seq_c0, seq_nc;
 	std::vector<int64_t> seq_gb0;
 	std::vector<Chunk> chunks;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[8] = {};
+	cudaStream_t stream = nullptr, stream2 = nullptr;
+	cudaEvent_t ev[8] = {}, ev_fork = nullptr, ev_join = nullptr;
 	// device buffers
 	uint32_t *d_obs = nullptr;
 	Chunk *d_chunks = nullptr;
@@ -1248,13 +1264,20 @@ struct psmc_b200_ctx {
 	int32_t *d_sub_parent = nullptr, *d_chunk_sub0 = nullptr, *d_Texsub = nullptr;
 	double *d_Tsub = nullptr, *d_vsub = nullptr, *d_bsub = nullptr, *d_llsub = nullptr, *d_partsub = nullptr;
 	int32_t *d_flag = nullptr; // n_chunks + 2 boundary flags of the current repair round (entries -1 and n_chunks are always 0)
+	// The backward pass has its OWN chunk plan in the fast path: its kernel needs about twice the registers of the
+	// forward kernel, so one resident wave holds half as many chunks; tying both passes to one plan would make the
+	// forward chunks twice as long as necessary.  (Transfer mode and decode use the forward plan for both directions.)
+	int n_chunks_b = 0, chunk_len_b = 0, n_sub_b = 0;
+	Chunk *d_chunks_b = nullptr, *d_sub_b = nullptr;
+	int32_t *d_sub_parent_b = nullptr, *d_chunk_sub0_b = nullptr, *d_flag_b = nullptr;
 	unsigned long long *d_cert = nullptr, *h_cert = nullptr;            // [failed boundaries, max fwd mismatch bits, max bwd mismatch bits]
-	int warm_len = 0;          // bins of warm-up overlap (0 = always use the transfer-matrix path)
+	int warm_len = 0;          // bins of forward warm-up overlap (0 = always use the transfer-matrix path)
+	int warm_len_bwd = 0;      // bins of backward warm-up overlap (runs concurrently with the forward kernel, so it can be longer)
 	double cert_eps = 1e-12;
 	bool mode_warm = false, certified = true;
 	int fallbacks = 0, repair_rounds = 3;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
-	int g_fwd = 32, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
+	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
 	double mis_f = 0.0, mis_b = 0.0;
 	// decode scratch (allocated on demand)
@@ -1299,6 +1322,7 @@ static void free_ctx(psmc_b200_ctx *c)
 	cudaFree(c->d_obs); cudaFree(c->d_chunks); cudaFree(c->d_k1); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
 	cudaFree(c->d_Tex); cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_T);
 	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_fwarm); cudaFree(c->d_bwarm); cudaFree(c->d_bexact); cudaFree(c->d_cert); cudaFree(c->d_flag); cudaFree(c->d_bsave[0]); cudaFree(c->d_bsave[1]);
+	cudaFree(c->d_chunks_b); cudaFree(c->d_sub_b); cudaFree(c->d_sub_parent_b); cudaFree(c->d_chunk_sub0_b); cudaFree(c->d_flag_b);
 	cudaFree(c->d_sub); cudaFree(c->d_sub_parent); cudaFree(c->d_chunk_sub0); cudaFree(c->d_Texsub); cudaFree(c->d_Tsub); cudaFree(c->d_vsub); cudaFree(c->d_bsub); cudaFree(c->d_llsub); cudaFree(c->d_partsub);
 	if (c->h_cert) cudaFreeHost(c->h_cert); cudaFree(c->d_part); cudaFree(c->d_llpart); cudaFree(c->d_stats);
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
@@ -1307,6 +1331,9 @@ static void free_ctx(psmc_b200_ctx *c)
 	if (c->h_obs) cudaFreeHost(c->h_obs);
 	for (int i = 0; i < 8; ++i)
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
+	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -1395,6 +1422,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		const char *env = getenv("PSMC_B200_CHUNK");
 		if (env && atoi(env) > 0) chunk_len = atoi(env);
 	}
+	int chunk_len_b = chunk_len;
 	if (chunk_len <= 0) {
 		int sf = 4, sb = 4;
 		switch (c->NP) {
@@ -1402,21 +1430,31 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		case 64: chunk_slots<64>(c, &sf, &sb); break;
 		default: chunk_slots<128>(c, &sf, &sb); break;
 		}
-		int per_sm = std::min(sf, sb);
+		// measured on B200: beyond 16 forward chunks per SM the extra warm-up overlaps cost more than the shorter chunks save
+		if (sf > 16) sf = 16;
 		const char *env = getenv("PSMC_B200_CHUNKS_PER_SM");
-		if (env && atoi(env) > 0) per_sm = atoi(env);
+		if (env && atoi(env) > 0) sf = sb = atoi(env);
+		env = getenv("PSMC_B200_CHUNKS_PER_SM_FWD");
+		if (env && atoi(env) > 0) sf = atoi(env);
 		c->slots_fwd = sf; c->slots_bwd = sb;
-		int64_t target = (int64_t)prop.multiProcessorCount * per_sm - c->n_seqs; // every sequence rounds its chunk count up
-		if (target < 1) target = 1;
-		int64_t cl = (c->total_bins + target - 1) / target;
-		if (cl < 512) cl = 512;
-		chunk_len = (int)std::min<int64_t>(cl, 1 << 24);
+		auto len_for = [&](int per_sm) {
+			int64_t target = (int64_t)prop.multiProcessorCount * per_sm - c->n_seqs; // every sequence rounds its chunk count up
+			if (target < 1) target = 1;
+			int64_t cl = (c->total_bins + target - 1) / target;
+			if (cl < 512) cl = 512;
+			return (int)std::min<int64_t>(cl, 1 << 24);
+		};
+		chunk_len = len_for(sf);
+		chunk_len_b = len_for(sb);
 	}
+	c->chunk_len_b = chunk_len_b;
 	c->chunk_len = chunk_len;
 	{ // warm-up overlap: PSMC_B200_WARM=0 disables the fast path (always transfer matrices)
 		const char *env = getenv("PSMC_B200_WARM");
-		c->warm_len = env ? atoi(env) : 8192;
+		c->warm_len = env ? atoi(env) : 12288;
 		if (c->warm_len < 0) c->warm_len = 0;
+		env = getenv("PSMC_B200_WARM_BWD");
+		c->warm_len_bwd = (env && atoi(env) > 0) ? atoi(env) : 2 * c->warm_len;
 		env = getenv("PSMC_B200_WARM_HOT");
 		if (env && atoi(env) >= 0) c->warm_hot = atoi(env);
 		env = getenv("PSMC_B200_REPAIR_ROUNDS");
@@ -1434,41 +1472,44 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		words += (w + 31) / 32 * 32;
 	}
 	c->words_obs = std::max<int64_t>(words, 32);
-	// chunks
-	int64_t gb = 0;
-	c->seq_c0.resize(c->n_seqs); c->seq_nc.resize(c->n_seqs); c->seq_gb0.resize(c->n_seqs);
-	std::vector<int32_t> k1;
-	for (int i = 0; i < c->n_seqs; ++i) {
-		const int Li = c->L[i];
-		const int nc = (Li + chunk_len - 1) / chunk_len;
-		c->seq_c0[i] = (int)c->chunks.size();
-		c->seq_nc[i] = nc;
-		c->seq_gb0[i] = gb;
-		for (int k = 0; k < nc; ++k) {
-			Chunk ch;
-			const int64_t a = (int64_t)Li * k / nc, b = (int64_t)Li * (k + 1) / nc;
-			ch.seq = i;
-			ch.flags = (k == 0 ? CH_FIRST : 0) | (k == nc - 1 ? CH_LAST : 0);
-			ch.u0 = (int)a;
-			ch.len = (int)(b - a);
-			ch.gb0 = gb + a;
-			ch.ow0 = ow0[i];
-			ch.Lseq = Li;
-			ch.pad_ = 0;
-			if (nc > 1) k1.push_back((int)c->chunks.size());
-			c->chunks.push_back(ch);
-		}
-		gb += Li;
-	}
-	c->n_chunks = (int)c->chunks.size();
-	// sub-chunks (repair granularity): every chunk split into equal pieces of about sub_len bins
-	std::vector<Chunk> subs;
-	std::vector<int32_t> sub_parent, chunk_sub0((size_t)c->n_chunks + 1, 0);
+	// chunk plans (forward plan = the context's main plan; backward plan for the fast path)
 	{
 		const char *env = getenv("PSMC_B200_SUB_LEN");
 		if (env && atoi(env) >= 64) c->sub_len = atoi(env);
-		for (int ci = 0; ci < c->n_chunks; ++ci) {
-			const Chunk &pc = c->chunks[ci];
+	}
+	c->seq_c0.resize(c->n_seqs); c->seq_nc.resize(c->n_seqs); c->seq_gb0.resize(c->n_seqs);
+	std::vector<int32_t> k1;
+	auto build_plan = [&](int clen, bool is_main, std::vector<Chunk> &chunks, std::vector<Chunk> &subs,
+	                      std::vector<int32_t> &sub_parent, std::vector<int32_t> &chunk_sub0) {
+		int64_t gb = 0;
+		for (int i = 0; i < c->n_seqs; ++i) {
+			const int Li = c->L[i];
+			const int nc = (Li + clen - 1) / clen;
+			if (is_main) {
+				c->seq_c0[i] = (int)chunks.size();
+				c->seq_nc[i] = nc;
+				c->seq_gb0[i] = gb;
+			}
+			for (int k = 0; k < nc; ++k) {
+				Chunk ch;
+				const int64_t a = (int64_t)Li * k / nc, b = (int64_t)Li * (k + 1) / nc;
+				ch.seq = i;
+				ch.flags = (k == 0 ? CH_FIRST : 0) | (k == nc - 1 ? CH_LAST : 0);
+				ch.u0 = (int)a;
+				ch.len = (int)(b - a);
+				ch.gb0 = gb + a;
+				ch.ow0 = ow0[i];
+				ch.Lseq = Li;
+				ch.pad_ = 0;
+				if (is_main && nc > 1) k1.push_back((int)chunks.size());
+				chunks.push_back(ch);
+			}
+			gb += Li;
+		}
+		// sub-chunks (repair granularity): every chunk split into equal pieces of about sub_len bins
+		chunk_sub0.assign(chunks.size() + 1, 0);
+		for (size_t ci = 0; ci < chunks.size(); ++ci) {
+			const Chunk &pc = chunks[ci];
 			const int ns = std::max(1, (pc.len + c->sub_len - 1) / c->sub_len);
 			chunk_sub0[ci] = (int32_t)subs.size();
 			for (int k = 0; k < ns; ++k) {
@@ -1479,12 +1520,19 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 				sc_.gb0 = pc.gb0 + a;
 				sc_.flags = ((pc.flags & CH_FIRST) && k == 0 ? CH_FIRST : 0) | ((pc.flags & CH_LAST) && k == ns - 1 ? CH_LAST : 0);
 				subs.push_back(sc_);
-				sub_parent.push_back(ci);
+				sub_parent.push_back((int32_t)ci);
 			}
 		}
-		chunk_sub0[c->n_chunks] = (int32_t)subs.size();
-		c->n_sub = (int)subs.size();
-	}
+		chunk_sub0[chunks.size()] = (int32_t)subs.size();
+	};
+	std::vector<Chunk> subs, chunks_b, subs_b;
+	std::vector<int32_t> sub_parent, chunk_sub0, sub_parent_b, chunk_sub0_b;
+	build_plan(chunk_len, true, c->chunks, subs, sub_parent, chunk_sub0);
+	build_plan(chunk_len_b, false, chunks_b, subs_b, sub_parent_b, chunk_sub0_b);
+	c->n_chunks = (int)c->chunks.size();
+	c->n_sub = (int)subs.size();
+	c->n_chunks_b = (int)chunks_b.size();
+	c->n_sub_b = (int)subs_b.size();
 	c->n_k1 = (int)k1.size();
 	const int NP = c->NP;
 #define ALLOC(ptr, bytes)                                                                         \
@@ -1514,25 +1562,30 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	ALLOC(c->d_Tex, sizeof(int32_t) * (size_t)c->n_chunks * NP);
 	ALLOC(c->d_vstart, sizeof(double) * (size_t)c->n_chunks * NP);
 	ALLOC(c->d_bend, sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_part, sizeof(double) * (size_t)c->n_chunks * S_COUNT * NP);
+	ALLOC(c->d_part, sizeof(double) * (size_t)std::max(c->n_chunks, c->n_chunks_b) * S_COUNT * NP);
 	ALLOC(c->d_llpart, sizeof(double) * (size_t)c->n_chunks);
 	ALLOC(c->d_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1));
 	ALLOC(c->d_fwarm, sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_bwarm, sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_bexact, sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_bsave[0], sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_bsave[1], sizeof(double) * (size_t)c->n_chunks * NP);
+	ALLOC(c->d_bwarm, sizeof(double) * (size_t)std::max(c->n_chunks, c->n_chunks_b) * NP);
+	ALLOC(c->d_bexact, sizeof(double) * (size_t)std::max(c->n_chunks, c->n_chunks_b) * NP);
+	ALLOC(c->d_bsave[0], sizeof(double) * (size_t)c->n_chunks_b * NP);
+	ALLOC(c->d_bsave[1], sizeof(double) * (size_t)c->n_chunks_b * NP);
+	ALLOC(c->d_chunks_b, sizeof(Chunk) * (size_t)c->n_chunks_b);
+	ALLOC(c->d_sub_b, sizeof(Chunk) * (size_t)c->n_sub_b);
+	ALLOC(c->d_sub_parent_b, sizeof(int32_t) * (size_t)c->n_sub_b);
+	ALLOC(c->d_chunk_sub0_b, sizeof(int32_t) * (size_t)(c->n_chunks_b + 1));
+	ALLOC(c->d_flag_b, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2));
 	ALLOC(c->d_cert, sizeof(unsigned long long) * 8);
 	ALLOC(c->d_flag, sizeof(int32_t) * (size_t)(c->n_chunks + 2));
 	ALLOC(c->d_sub, sizeof(Chunk) * (size_t)c->n_sub);
 	ALLOC(c->d_sub_parent, sizeof(int32_t) * (size_t)c->n_sub);
 	ALLOC(c->d_chunk_sub0, sizeof(int32_t) * (size_t)(c->n_chunks + 1));
-	ALLOC(c->d_Tsub, sizeof(double) * (size_t)c->n_sub * NP * NP);
-	ALLOC(c->d_Texsub, sizeof(int32_t) * (size_t)c->n_sub * NP);
+	ALLOC(c->d_Tsub, sizeof(double) * (size_t)std::max(c->n_sub, c->n_sub_b) * NP * NP);
+	ALLOC(c->d_Texsub, sizeof(int32_t) * (size_t)std::max(c->n_sub, c->n_sub_b) * NP);
 	ALLOC(c->d_vsub, sizeof(double) * (size_t)c->n_sub * NP);
-	ALLOC(c->d_bsub, sizeof(double) * (size_t)c->n_sub * NP);
+	ALLOC(c->d_bsub, sizeof(double) * (size_t)c->n_sub_b * NP);
 	ALLOC(c->d_llsub, sizeof(double) * (size_t)c->n_sub);
-	ALLOC(c->d_partsub, sizeof(double) * (size_t)c->n_sub * S_COUNT * NP);
+	ALLOC(c->d_partsub, sizeof(double) * (size_t)c->n_sub_b * S_COUNT * NP);
 #undef ALLOC
 #define CTRY(call)                                                                                \
 	do {                                                                                          \
@@ -1544,6 +1597,9 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		}                                                                                         \
 	} while (0)
 	CTRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CTRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	CTRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	CTRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	for (int i = 0; i < 8; ++i) CTRY(cudaEventCreate(&c->ev[i]));
 	CTRY(cudaMallocHost((void **)&c->h_model, sizeof(double) * M_COUNT * NP));
 	CTRY(cudaMallocHost((void **)&c->h_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1)));
@@ -1557,6 +1613,13 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		CTRY(cudaMemcpyAsync(c->d_sub_parent, sub_parent.data(), sizeof(int32_t) * (size_t)c->n_sub, cudaMemcpyHostToDevice, c->stream));
 	}
 	CTRY(cudaMemcpyAsync(c->d_chunk_sub0, chunk_sub0.data(), sizeof(int32_t) * (size_t)(c->n_chunks + 1), cudaMemcpyHostToDevice, c->stream));
+	if (c->n_chunks_b) CTRY(cudaMemcpyAsync(c->d_chunks_b, chunks_b.data(), sizeof(Chunk) * (size_t)c->n_chunks_b, cudaMemcpyHostToDevice, c->stream));
+	if (c->n_sub_b) {
+		CTRY(cudaMemcpyAsync(c->d_sub_b, subs_b.data(), sizeof(Chunk) * (size_t)c->n_sub_b, cudaMemcpyHostToDevice, c->stream));
+		CTRY(cudaMemcpyAsync(c->d_sub_parent_b, sub_parent_b.data(), sizeof(int32_t) * (size_t)c->n_sub_b, cudaMemcpyHostToDevice, c->stream));
+	}
+	CTRY(cudaMemcpyAsync(c->d_chunk_sub0_b, chunk_sub0_b.data(), sizeof(int32_t) * (size_t)(c->n_chunks_b + 1), cudaMemcpyHostToDevice, c->stream));
+	CTRY(cudaMemsetAsync(c->d_flag_b, 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), c->stream));
 	if (c->n_k1) CTRY(cudaMemcpyAsync(c->d_k1, k1.data(), sizeof(int32_t) * (size_t)c->n_k1, cudaMemcpyHostToDevice, c->stream));
 	if (c->n_seqs) {
 		CTRY(cudaMemcpyAsync(c->d_seq_c0, c->seq_c0.data(), sizeof(int32_t) * (size_t)c->n_seqs, cudaMemcpyHostToDevice, c->stream));
@@ -1669,20 +1732,29 @@ static void run_forward_repair(psmc_b200_ctx *c)
 #undef FWR
 }
 template <int NP>
-static void run_backward(psmc_b200_ctx *c, int warm, int use_prev)
+static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const double *bdir, int publish, double *bsave_next)
 {
 	cudaStream_t st = c->stream;
-#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_bend, warm, c->d_fhat, c->d_sc, c->d_part, c->d_bwarm, c->d_bexact, use_prev ? c->d_bsave[c->bsave_cur] : nullptr, c->d_bsave[c->bsave_cur ^ 1], c->warm_hot)
+#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(n, G_), 128, 0, st>>>(chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
 	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8);
 	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16);
 	else BWD(32);
 #undef BWD
 }
 template <int NP>
+static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
+{
+#define BWW(G_) k_backward_warm<NP / G_, G_><<<blocks_for(c->n_chunks_b, G_), 128, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
+	if (c->g_bwd == 8 && NP / 8 <= 8) BWW(8);
+	else if (c->g_bwd <= 16 && NP / 16 <= 8) BWW(16);
+	else BWW(32);
+#undef BWW
+}
+template <int NP>
 static void run_backward_repair(psmc_b200_ctx *c)
 {
 	cudaStream_t st = c->stream;
-#define BWR(G_) k_backward_repair<NP / G_, G_><<<blocks_for(c->n_sub, G_), 128, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_chunks, c->d_obs, c->d_model, c->d_flag + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
+#define BWR(G_) k_backward_repair<NP / G_, G_><<<blocks_for(c->n_sub_b, G_), 128, 0, st>>>(c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
 	if (c->g_bwd == 8 && NP / 8 <= 4) BWR(8);
 	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWR(16);
 	else BWR(32);
@@ -1732,19 +1804,18 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	cudaEventRecord(c->ev[3], st);
 	if (with_counts) {
 		if (c->n_chunks > 0) {
-			run_backward<NP>(c, 0, 0);
+			run_backward<NP>(c, c->d_chunks, c->n_chunks, c->d_bend, 0, nullptr);
 			++c->launches;
-			c->bsave_cur ^= 1; // this pass saved the warm-start directions of the next one
 		}
 		cudaEventRecord(c->ev[4], st);
-		k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->N, NP, c->d_stats);
+		k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks, c->N, NP, c->d_stats);
 		++c->launches;
 		cudaEventRecord(c->ev[5], st);
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 	c->fwd_valid = true;
-	if (with_counts) c->have_prev = true;
+	if (with_counts) c->have_prev = false; // the transfer-mode backward pass saves no warm-start directions
 	return 0;
 }
 
@@ -1762,6 +1833,11 @@ static int launch_warm(psmc_b200_ctx *c)
 	const int wpb = 4, nblk = (c->n_chunks + wpb - 1) / wpb;
 	const int hot = (c->have_prev && c->warm_hot > 0) ? 1 : 0;
 	const int wl = hot ? c->warm_hot : c->warm_len;
+	// the backward warm-up needs only observations + model: run it on the side stream, concurrently with the forward pass
+	cudaEventRecord(c->ev_fork, st);
+	cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
+	run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : c->warm_len_bwd, hot);
+	cudaEventRecord(c->ev_join, c->stream2);
 	run_forward<NP>(c, wl, hot);
 	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 	const dim3 gridT((unsigned)c->n_sub, NP / COLS);
@@ -1773,20 +1849,24 @@ static int launch_warm(psmc_b200_ctx *c)
 		k_fold<<<c->n_chunks, 128, 0, st>>>(c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[3], st);
-	run_backward<NP>(c, wl, hot);
+	cudaStreamWaitEvent(st, c->ev_join, 0);
+	run_backward<NP>(c, c->d_chunks_b, c->n_chunks_b, c->d_bwarm, 1, c->d_bsave[c->bsave_cur ^ 1]);
 	c->bsave_cur ^= 1;
+	const int nblk_b = (c->n_chunks_b + wpb - 1) / wpb;
+	const dim3 gridTb((unsigned)c->n_sub_b, NP / COLS);
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		k_mark_bwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag + 1, c->d_cert + 4);
-		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3);
-		k_chain_subs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 1, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
+		k_mark_bwd<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4);
+		k_transfer<SPL1, G1, COLS><<<gridTb, COLS * G1, 0, st>>>(c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag_b + 1, 3);
+		k_chain_subs<NP><<<c->n_chunks_b, NP, 0, st>>>(c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
-		k_fold<<<c->n_chunks, 128, 0, st>>>(c->d_chunk_sub0, c->d_flag + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
+		k_fold<<<c->n_chunks_b, 128, 0, st>>>(c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[4], st);
-	k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->N, NP, c->d_stats);
-	k_certify<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, c->d_cert);
+	k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats);
+	k_certify<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
+	k_certify<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 4 + 10 * c->repair_rounds;
+	c->launches = 6 + 10 * c->repair_rounds;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 	c->fwd_valid = false; // bend[] is not filled in this mode; decode runs its own forward pass
@@ -2045,7 +2125,7 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
 extern "C" int psmc_b200_set_warm(psmc_b200_ctx *c, int32_t warm_len, double eps)
 {
 	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
-	if (warm_len >= 0) c->warm_len = warm_len;
+	if (warm_len >= 0) { c->warm_len = warm_len; c->warm_len_bwd = 2 * warm_len; }
 	if (eps > 0) c->cert_eps = eps;
 	return 0;
 }
