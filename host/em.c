@@ -35,9 +35,10 @@ static double objective(int n, double *x, void *data)
 	return -psmch_Q_fast(&em->model, &em->counts);
 }
 
-int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void))
+/* parameter space, initial parameters (core.c:32-49) and the first model; sq gives sum_n / sum_L only */
+static int init_model(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void))
 {
-	int k, g, i, rc;
+	int k;
 	const char *pattern = o->pattern ? o->pattern : "4+5*3+4";
 	memset(em, 0, sizeof(*em));
 	if (psmch_space_init(&em->sp, pattern, (o->flag & PSMCH_F_DIVERG) ? 1 : 0, o->alpha0) < 0) {
@@ -65,10 +66,28 @@ int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq,
 		if (em->sp.diverg) em->model.params[em->sp.n_params - 1] = o->dt0;
 	}
 	psmch_model_update(&em->sp, em->model.params, &em->model);
-	/* shard whole sequences over the GPUs: longest-processing-time first (SURVEY.md 8e) */
-	em->n_gpus = o->n_gpus;
 	em->exact_mstep = getenv("PSMC_B200_EXACT_MSTEP") != 0; /* scalar libm in every trial evaluation */
 	em->n_seqs = sq->n_seqs;
+	return 0;
+}
+
+/* EM on a context that already holds the sequences (bootstrap replicates: the multiplicities are set by the
+ * caller; sq carries the replicate's n_seqs / sum_L / sum_n).  The context is borrowed, not destroyed. */
+int psmch_em_init_shared(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, psmc_b200_ctx *ctx, double (*rnd)(void))
+{
+	if (init_model(em, o, sq, rnd) != 0) return -1;
+	em->n_gpus = 1;
+	em->ctx[0] = ctx;
+	em->borrowed = 1;
+	return 0;
+}
+
+int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void))
+{
+	int g, i, rc;
+	if (init_model(em, o, sq, rnd) != 0) return -1;
+	/* shard whole sequences over the GPUs: longest-processing-time first (SURVEY.md 8e) */
+	em->n_gpus = o->n_gpus;
 	em->seq_owner = (int*)calloc(sq->n_seqs > 0 ? sq->n_seqs : 1, sizeof(int));
 	{
 		int *order = (int*)malloc(sizeof(int) * (sq->n_seqs > 0 ? sq->n_seqs : 1)), j;
@@ -106,7 +125,7 @@ int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq,
 void psmch_em_free(psmch_em_t *em)
 {
 	int g;
-	for (g = 0; g < em->n_gpus; ++g) psmc_b200_destroy(em->ctx[g]);
+	for (g = 0; g < em->n_gpus && !em->borrowed; ++g) psmc_b200_destroy(em->ctx[g]);
 	psmch_counts_free(&em->counts);
 	psmch_model_free(&em->model);
 	psmch_space_free(&em->sp);

@@ -17,17 +17,24 @@ int main(int argc, char *argv[])
 	int i, rc;
 	if (psmch_parse_cli(argc, argv, &o) != 0) return 1;
 	srand48(o.seed >= 0 ? o.seed : (long)(time(0) ^ getpid())); /* main.c:11 */
-	psmch_print_header(&o, 0, 0, 0);
+	if (o.n_replicates == 0) psmch_print_header(&o, 0, 0, 0);
 	if (o.pre_fn && psmch_read_param(&o, 0) != 0) return 1;
 	if (psmch_space_init(&hdr, o.pattern ? o.pattern : "4+5*3+4", 0, o.alpha0) != 0) {
 		fprintf(stderr, "psmc: bad pattern '%s'\n", o.pattern);
 		return 1;
 	}
-	psmch_print_header(&o, &hdr, 0, 1);
+	if (o.n_replicates == 0) psmch_print_header(&o, &hdr, 0, 1);
 	psmch_space_free(&hdr);
 	if (psmch_read_psmcfa(o.in_fn, &sq) != 0) {
 		fprintf(stderr, "psmc: cannot read '%s'\n", o.in_fn);
 		return 1;
+	}
+	if (o.split_len > 0 && psmch_split(&sq, o.split_len) != 0) return 1;
+	if (o.n_replicates > 0) { /* README:57-62 in one process: every replicate prints its own complete .psmc text */
+		rc = psmch_bootstrap_run(&o, &sq, o.n_replicates, o.slots);
+		psmch_free_seqs(&sq);
+		if (o.fpout != stdout) fclose(o.fpout);
+		return rc != 0;
 	}
 	if (o.is_bootstrap) psmch_resample(&sq, rnd48);
 	psmch_print_header(&o, 0, &sq, 2);

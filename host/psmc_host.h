@@ -9,7 +9,7 @@
  *   Hooke-Jeeves                 kmin.c:48-107        -> hj.c
  *   EM iteration                 em.c:15-78           -> em.c      (E-step = psmc_b200_estep on the GPU)
  *   round printer, -i reader     aux.c:49-113         -> output.c
- *   bootstrap resampling         aux.c:8-47           -> resamp.c  (seedable)
+ *   bootstrap resampling         aux.c:8-47           -> resamp.c  (seedable); bootstrap.c (R replicates, one process)
  *   decode printer               aux.c:129-232        -> decode.c  (posteriors from psmc_b200_decode)
  */
 #ifndef PSMC_HOST_H
@@ -52,6 +52,8 @@ typedef struct {
 int  psmch_read_psmcfa(const char *fn, psmch_seqs_t *out); /* "-" = stdin; gz or plain */
 void psmch_free_seqs(psmch_seqs_t *s);
 void psmch_resample(psmch_seqs_t *s, double (*rnd)(void)); /* aux.c:8-47; rnd() in [0,1) */
+int  psmch_split(psmch_seqs_t *s, int trunk);               /* utils/splitfa.c:20-31 in memory */
+void psmch_draw(const psmch_seqs_t *s, double (*rnd)(void), int32_t *mult, psmch_seqs_t *view); /* aux.c:14-32 as multiplicities; view: n_seqs, sum_L, sum_n of the replicate */
 
 /* ---- parameter space and model ----------------------------------------------------------------- */
 typedef struct {
@@ -128,6 +130,9 @@ typedef struct {
 	long seed;           /* --seed S   [-1 = time^pid as the reference, main.c:11] */
 	int chunk_len;       /* --chunk L  [0 = auto] */
 	int verbose;         /* --verbose  timing lines on stderr */
+	int n_replicates;    /* --replicates R  R bootstrap replicates in this process (implies -b) [0] */
+	int split_len;       /* --split[=T]  apply the splitfa rule with trunk size T bins first [off; 500000] */
+	int slots;           /* --slots K  concurrent replicates per GPU [2] */
 } psmch_opts_t;
 
 typedef struct {
@@ -141,6 +146,7 @@ typedef struct {
 	int *seq_owner; /* per sequence: which context holds it */
 	int64_t n_seqs;
 	int hj_calls;
+	int borrowed;    /* ctx[0] belongs to the caller (bootstrap replicates share one context per GPU slot) */
 	int exact_mstep; /* PSMC_B200_EXACT_MSTEP: trial evaluations with scalar libm instead of libmvec */
 	double t_estep_ms, t_mstep_ms; /* wall time of the last iteration */
 } psmch_em_t;
@@ -149,6 +155,7 @@ int  psmch_parse_cli(int argc, char *argv[], psmch_opts_t *o);
 void psmch_print_header(const psmch_opts_t *o, const psmch_space_t *sp, const psmch_seqs_t *sq, int stage);
 int  psmch_read_param(psmch_opts_t *o, psmch_space_t *sp); /* aux.c:84-113 */
 int  psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, double (*rnd)(void));
+int  psmch_em_init_shared(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, psmc_b200_ctx *ctx, double (*rnd)(void));
 int  psmch_em_iterate(psmch_em_t *em, FILE *fpout); /* one psmc_em (em.c:27-78); prints the IT line */
 int  psmch_em_estep(psmch_em_t *em);                 /* em.c:33-55 on the GPU(s) */
 int  psmch_em_set_raw(psmch_em_t *em, const double *raw, int64_t n_seqs_total);
@@ -156,6 +163,7 @@ int  psmch_em_mstep(psmch_em_t *em, FILE *fpout);    /* em.c:56-74 */
 void psmch_em_free(psmch_em_t *em);
 void psmch_print_round(const psmch_opts_t *o, const psmch_em_t *em, const psmch_seqs_t *sq, FILE *fp); /* aux.c:49-82 */
 int  psmch_decode(const psmch_opts_t *o, psmch_em_t *em, const psmch_seqs_t *sq, FILE *fp);          /* aux.c:129-232 */
+int  psmch_bootstrap_run(const psmch_opts_t *o, const psmch_seqs_t *sq, int n_rep, int slots);     /* README:57-62 in one process */
 
 #ifdef __cplusplus
 }

@@ -247,3 +247,63 @@ int psmch_py_em_upload(void *h, int n_seqs, const int32_t *L, const signed char 
 	free(all); free(ptr); free(len);
 	return rc;
 }
+
+/* ---- bootstrap helpers (tests): the splitfa rule and the replicate draw --------------------------- */
+static void seqs_from_lengths(psmch_seqs_t *sq, int n, const int32_t *L)
+{
+	int i;
+	memset(sq, 0, sizeof(*sq));
+	sq->n_seqs = n;
+	sq->seqs = (psmch_seq_t*)calloc(n > 0 ? n : 1, sizeof(psmch_seq_t));
+	for (i = 0; i < n; ++i) {
+		char nm[32];
+		int32_t u;
+		psmch_seq_t *s = sq->seqs + i;
+		s->L = L[i];
+		s->seq = (signed char*)malloc(L[i] > 0 ? L[i] : 1);
+		for (u = 0; u < L[i]; ++u) s->seq[u] = (signed char)((u * 7 + i) % 23 == 0 ? 1 : ((u + i) % 41 == 0 ? 2 : 0));
+		for (u = 0; u < L[i]; ++u) { if (s->seq[u] < 2) ++s->L_e; if (s->seq[u] == 1) ++s->n_e; }
+		sprintf(nm, "r%d", i);
+		s->name = strdup(nm);
+		sq->sum_L += s->L_e; sq->sum_n += s->n_e;
+	}
+}
+
+/* piece lengths of the splitfa rule; rec[i] = source record, idx[i] = 1-based piece number; returns the count */
+int psmch_py_split(int n, const int32_t *L, int trunk, int32_t *out_L, int32_t *rec, int32_t *idx, int cap)
+{
+	psmch_seqs_t sq;
+	int i, m;
+	seqs_from_lengths(&sq, n, L);
+	if (psmch_split(&sq, trunk) != 0) { psmch_free_seqs(&sq); return -1; }
+	m = sq.n_seqs;
+	for (i = 0; i < m && i < cap; ++i) {
+		out_L[i] = sq.seqs[i].L;
+		sscanf(sq.seqs[i].name, "r%d_%d", &rec[i], &idx[i]);
+	}
+	psmch_free_seqs(&sq);
+	return m;
+}
+
+static unsigned short py_x[3];
+static double py_rnd(void) { return erand48(py_x); }
+
+/* multiplicities of one replicate drawn with srand48(seed) semantics; view = {n_seqs, sum_L, sum_n};
+ * also runs psmch_resample (the copying path of `psmc -b`) from the same seed and returns in mult_copy the
+ * multiplicities it produced (matched by record name), so that a test can require them to agree */
+int psmch_py_draw(int n, const int32_t *L, long seed, int32_t *mult, int64_t *view, int32_t *mult_copy)
+{
+	psmch_seqs_t sq, v;
+	int i;
+	seqs_from_lengths(&sq, n, L);
+	py_x[0] = 0x330E; py_x[1] = (unsigned short)(seed & 0xffff); py_x[2] = (unsigned short)((seed >> 16) & 0xffff);
+	psmch_draw(&sq, py_rnd, mult, &v);
+	view[0] = v.n_seqs; view[1] = v.sum_L; view[2] = v.sum_n;
+	srand48(seed);
+	psmch_resample(&sq, rnd48);
+	for (i = 0; i < n; ++i) mult_copy[i] = 0;
+	for (i = 0; i < sq.n_seqs; ++i) ++mult_copy[atoi(sq.seqs[i].name + 1)];
+	view[3] = sq.n_seqs; view[4] = sq.sum_L; view[5] = sq.sum_n;
+	psmch_free_seqs(&sq);
+	return 0;
+}

@@ -75,6 +75,8 @@ typedef struct {
 	double fwd_mismatch, bwd_mismatch;
 	/* last run: boundary failures seen by the repair rounds (summed over rounds) and chunks they recomputed */
 	int32_t failed_fwd, repaired_fwd, failed_bwd, repaired_bwd;
+	/* psmc_b200_set_multiplicity: bins of the sequences with multiplicity > 0, and the sum of multiplicities */
+	int64_t active_bins, n_seqs_effective;
 } psmc_b200_info;
 
 int  psmc_b200_version(void);
@@ -98,6 +100,15 @@ void psmc_b200_destroy(psmc_b200_ctx *ctx);
  * the per-call input transfer of a psmc_em-style call that owns only host buffers (em.c:42-44). */
 int  psmc_b200_upload(psmc_b200_ctx *ctx, int32_t n_seqs, const int32_t *L, const signed char *const *seqs);
 int  psmc_b200_upload_cat(psmc_b200_ctx *ctx, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat);
+
+/* Bootstrap replicates without re-uploading anything.  psmc_resamp (aux.c:8-47) draws WHOLE records with
+ * replacement, so a replicate is a multiset of the resident sequences: mult[i] (i indexes the n_seqs records given
+ * to create) says how often record i occurs.  The following E-steps return sum_i mult[i] * (LL_i, counts_i) - exactly
+ * what em.c:33-55 computes on the resampled copy (khmm.c:346-359 adds the per-record counts), including one HMM_TINY
+ * term per drawn record - and records with mult[i] == 0 are skipped: the chunk plans are rebuilt over the drawn
+ * records only (host-side planning + a few hundred KB of tables; observations and work buffers stay in place).
+ * mult == NULL restores multiplicity 1 for every record.  psmc_b200_decode refuses records with multiplicity 0. */
+int  psmc_b200_set_multiplicity(psmc_b200_ctx *ctx, const int32_t *mult);
 
 /* One E-step: forward, backward, log-likelihood and expected counts over every sequence.
  * Replaces em.c:33-55 (hmm_pre_backward + the loop over hmm_forward / hmm_backward / hmm_lk /

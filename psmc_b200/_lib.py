@@ -35,7 +35,8 @@ class CInfo(C.Structure):
                 ("bytes_transfer", C.c_int64), ("bytes_total", C.c_int64),
                 ("ms", C.c_float * 8), ("launches", C.c_int32),
                 ("warm_len", C.c_int32), ("fallbacks", C.c_int32), ("fwd_mismatch", C.c_double), ("bwd_mismatch", C.c_double),
-                ("failed_fwd", C.c_int32), ("repaired_fwd", C.c_int32), ("failed_bwd", C.c_int32), ("repaired_bwd", C.c_int32)]
+                ("failed_fwd", C.c_int32), ("repaired_fwd", C.c_int32), ("failed_bwd", C.c_int32), ("repaired_bwd", C.c_int32),
+                ("active_bins", C.c_int64), ("n_seqs_effective", C.c_int64)]
 
 
 # every symbol include/psmc_b200.h declares: name -> (restype, argtypes)
@@ -48,6 +49,7 @@ SYMBOLS = {
     "psmc_b200_destroy": (None, [C.c_void_p]),
     "psmc_b200_upload": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.POINTER(C.c_void_p)]),
     "psmc_b200_upload_cat": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.c_void_p]),
+    "psmc_b200_set_multiplicity": (C.c_int, [C.c_void_p, _ip]),
     "psmc_b200_estep": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.POINTER(CStats)]),
     "psmc_b200_estep_dense": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_double, C.POINTER(CStats)]),
     "psmc_b200_factorize": (C.c_int, [C.c_int32, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp]),

@@ -1101,17 +1101,22 @@ __global__ void __launch_bounds__(128) k_certify(const Chunk *__restrict__ chunk
 // grid = 1 + S_COUNT*N blocks, block = 256 threads; block 0 reduces LL.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part, const double *__restrict__ llpart,
-                                                int n_chunks, int n_part, int N, int NP, double *__restrict__ out)
+                                                int n_chunks, int n_part, int N, int NP, double *__restrict__ out,
+                                                const double *__restrict__ w_ll, const double *__restrict__ w_part)
 {
+	// w_ll / w_part: multiplicity of the sequence every chunk belongs to (bootstrap replicates, aux.c:8-47); NULL = 1
 	__shared__ double sh[256];
 	const int o = blockIdx.x;
 	double acc = 0.0;
 	if (o == 0) {
-		for (int c = threadIdx.x; c < n_chunks; c += 256) acc += llpart[c];
+		for (int c = threadIdx.x; c < n_chunks; c += 256) acc += w_ll ? w_ll[c] * llpart[c] : llpart[c];
 	} else {
 		const int row = (o - 1) / N, k = (o - 1) % N;
 		const double *p = part + (size_t)row * NP + k;
-		for (int c = threadIdx.x; c < n_part; c += 256) acc += p[(size_t)c * S_COUNT * NP];
+		for (int c = threadIdx.x; c < n_part; c += 256) {
+			const double v = p[(size_t)c * S_COUNT * NP];
+			acc += w_part ? w_part[c] * v : v;
+		}
 	}
 	sh[threadIdx.x] = acc;
 	__syncthreads();
@@ -1294,6 +1299,19 @@ struct psmc_b200_ctx {
 	int launches = 0;
 	bool launched = false;
 	bool fwd_valid = false; // fhat/sc/bend hold a complete forward pass + boundary chains
+	// multiplicities (bootstrap replicates): the chunk plans cover the sequences with mult > 0 only
+	int n_seqs_given = 0;            // as passed to create (including empty records)
+	std::vector<int32_t> kept_of;    // given index -> kept index or -1
+	std::vector<int32_t> mult;       // per kept sequence
+	bool weighted = false;           // some multiplicity differs from 1
+	int64_t n_seq_eff = 0;           // sum of multiplicities (the HMM_TINY terms, khmm.c:305-308)
+	int64_t active_bins = 0;
+	int chunk_len_req = 0;           // chunk length the caller / environment asked for (0 = one resident wave)
+	int sm_count = 0;
+	double *d_cw = nullptr, *d_cw_b = nullptr; // per-chunk multiplicity, forward / backward plan
+	int cap_chunks = 0, cap_chunks_b = 0, cap_sub = 0, cap_sub_b = 0, cap_k1 = 0; // allocated capacities of the plan buffers
+	int64_t bytes_plan = 0;
+	int replans = 0;
 };
 
 template <int NP>
@@ -1315,16 +1333,29 @@ static int pad_states(int N)
 	return 128;
 }
 
+static void free_plan(psmc_b200_ctx *c)
+{
+	void **p[] = {(void **)&c->d_chunks, (void **)&c->d_k1, (void **)&c->d_Tex, (void **)&c->d_T, (void **)&c->d_vstart, (void **)&c->d_bend,
+	              (void **)&c->d_part, (void **)&c->d_llpart, (void **)&c->d_fwarm, (void **)&c->d_bwarm, (void **)&c->d_bexact,
+	              (void **)&c->d_bsave[0], (void **)&c->d_bsave[1], (void **)&c->d_chunks_b, (void **)&c->d_sub_b, (void **)&c->d_sub_parent_b,
+	              (void **)&c->d_chunk_sub0_b, (void **)&c->d_flag_b, (void **)&c->d_flag, (void **)&c->d_sub, (void **)&c->d_sub_parent,
+	              (void **)&c->d_chunk_sub0, (void **)&c->d_Tsub, (void **)&c->d_Texsub, (void **)&c->d_vsub, (void **)&c->d_bsub,
+	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b};
+	for (auto q : p) { cudaFree(*q); *q = nullptr; }
+	c->bytes_total -= c->bytes_plan;
+	c->bytes_plan = 0;
+	c->cap_chunks = c->cap_chunks_b = c->cap_sub = c->cap_sub_b = c->cap_k1 = 0;
+}
+
 static void free_ctx(psmc_b200_ctx *c)
 {
 	if (!c) return;
 	cudaSetDevice(c->device);
-	cudaFree(c->d_obs); cudaFree(c->d_chunks); cudaFree(c->d_k1); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
-	cudaFree(c->d_Tex); cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_T);
-	cudaFree(c->d_vstart); cudaFree(c->d_bend); cudaFree(c->d_fwarm); cudaFree(c->d_bwarm); cudaFree(c->d_bexact); cudaFree(c->d_cert); cudaFree(c->d_flag); cudaFree(c->d_bsave[0]); cudaFree(c->d_bsave[1]);
-	cudaFree(c->d_chunks_b); cudaFree(c->d_sub_b); cudaFree(c->d_sub_parent_b); cudaFree(c->d_chunk_sub0_b); cudaFree(c->d_flag_b);
-	cudaFree(c->d_sub); cudaFree(c->d_sub_parent); cudaFree(c->d_chunk_sub0); cudaFree(c->d_Texsub); cudaFree(c->d_Tsub); cudaFree(c->d_vsub); cudaFree(c->d_bsub); cudaFree(c->d_llsub); cudaFree(c->d_partsub);
-	if (c->h_cert) cudaFreeHost(c->h_cert); cudaFree(c->d_part); cudaFree(c->d_llpart); cudaFree(c->d_stats);
+	free_plan(c);
+	cudaFree(c->d_obs); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
+	cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_cert);
+	if (c->h_cert) cudaFreeHost(c->h_cert);
+	cudaFree(c->d_stats);
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
 	if (c->h_model) cudaFreeHost(c->h_model);
 	if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -1378,113 +1409,42 @@ static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 	}
 }
 
-extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *const *seqs,
-                                int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags)
+// (Re)build both chunk plans over the sequences with multiplicity > 0 and upload them.  The packed observations,
+// the forward spill (indexed by bin) and everything else that does not depend on the plan stay where they are.
+static int replan(psmc_b200_ctx *c)
 {
-	(void)flags;
-	if (!out) return set_err(PSMC_B200_EINVAL, "out is NULL");
-	*out = nullptr;
-	if (n_seqs < 0 || (n_seqs > 0 && (!L || !seqs))) return set_err(PSMC_B200_EINVAL, "bad sequence arguments");
-	if (n_states < 1 || n_states > 128) return set_err(PSMC_B200_EINVAL, "n_states=%d unsupported on the GPU path (1..128)", n_states);
-	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
-		return set_err(PSMC_B200_ENODEV, "no CUDA device available (there is no CPU fallback)");
-	if (device < 0 || device >= ndev) return set_err(PSMC_B200_ENODEV, "device %d out of range (have %d)", device, ndev);
-	CUDA_TRY(cudaSetDevice(device), PSMC_B200_ENODEV);
-
-	psmc_b200_ctx *c = new psmc_b200_ctx();
-	c->device = device;
-	c->N = n_states;
-	c->NP = pad_states(n_states);
-	c->SPL = c->NP / 32;
-	// keep non-empty sequences only (the reference reads uninitialised memory for L == 0; nothing to count there)
-	std::vector<const signed char *> sp;
-	for (int i = 0; i < n_seqs; ++i) {
-		if (L[i] < 0) { free_ctx(c); return set_err(PSMC_B200_EINVAL, "negative sequence length"); }
-		if (L[i] == 0) continue;
-		c->L.push_back(L[i]);
-		sp.push_back(seqs[i]);
-		c->total_bins += L[i];
+	const int NP = c->NP;
+	c->active_bins = 0; c->n_seq_eff = 0; c->weighted = false;
+	int n_active = 0;
+	for (int i = 0; i < c->n_seqs; ++i) {
+		if (c->mult[i] > 0) { c->active_bins += c->L[i]; ++n_active; }
+		if (c->mult[i] != 1) c->weighted = true;
+		c->n_seq_eff += c->mult[i];
 	}
-	c->n_seqs = (int)c->L.size();
-	cudaDeviceProp prop;
-	CUDA_TRY(cudaGetDeviceProperties(&prop, device), PSMC_B200_ENODEV);
-	// chunk plan.  The chunk kernels are latency-bound and every block lives as long as the kernel, so the plan
-	// must fit in ONE resident wave: chunks <= SMs x resident chunk slots of the tighter of the two kernels
-	// (one block too many doubles the kernel time; more chunks than that only add warm-up work).
-	{
-		const char *env = getenv("PSMC_B200_G_FWD");
-		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_fwd = atoi(env);
-		env = getenv("PSMC_B200_G_BWD");
-		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bwd = atoi(env);
-	}
+	// The chunk kernels are latency-bound and every block lives as long as the kernel, so a plan must fit in ONE
+	// resident wave of its kernel (one block too many doubles the kernel time; more chunks only add warm-up work).
+	int chunk_len = c->chunk_len_req, chunk_len_b = c->chunk_len_req;
 	if (chunk_len <= 0) {
-		const char *env = getenv("PSMC_B200_CHUNK");
-		if (env && atoi(env) > 0) chunk_len = atoi(env);
-	}
-	int chunk_len_b = chunk_len;
-	if (chunk_len <= 0) {
-		int sf = 4, sb = 4;
-		switch (c->NP) {
-		case 32: chunk_slots<32>(c, &sf, &sb); break;
-		case 64: chunk_slots<64>(c, &sf, &sb); break;
-		default: chunk_slots<128>(c, &sf, &sb); break;
-		}
-		// measured on B200: beyond 16 forward chunks per SM the extra warm-up overlaps cost more than the shorter chunks save
-		if (sf > 16) sf = 16;
-		const char *env = getenv("PSMC_B200_CHUNKS_PER_SM");
-		if (env && atoi(env) > 0) sf = sb = atoi(env);
-		env = getenv("PSMC_B200_CHUNKS_PER_SM_FWD");
-		if (env && atoi(env) > 0) sf = atoi(env);
-		c->slots_fwd = sf; c->slots_bwd = sb;
 		auto len_for = [&](int per_sm) {
-			int64_t target = (int64_t)prop.multiProcessorCount * per_sm - c->n_seqs; // every sequence rounds its chunk count up
+			int64_t target = (int64_t)c->sm_count * per_sm - n_active; // every sequence rounds its chunk count up
 			if (target < 1) target = 1;
-			int64_t cl = (c->total_bins + target - 1) / target;
+			int64_t cl = (c->active_bins + target - 1) / target;
 			if (cl < 512) cl = 512;
 			return (int)std::min<int64_t>(cl, 1 << 24);
 		};
-		chunk_len = len_for(sf);
-		chunk_len_b = len_for(sb);
+		chunk_len = len_for(c->slots_fwd);
+		chunk_len_b = len_for(c->slots_bwd);
 	}
-	c->chunk_len_b = chunk_len_b;
 	c->chunk_len = chunk_len;
-	{ // warm-up overlap: PSMC_B200_WARM=0 disables the fast path (always transfer matrices)
-		const char *env = getenv("PSMC_B200_WARM");
-		c->warm_len = env ? atoi(env) : 12288;
-		if (c->warm_len < 0) c->warm_len = 0;
-		env = getenv("PSMC_B200_WARM_BWD");
-		c->warm_len_bwd = (env && atoi(env) > 0) ? atoi(env) : 2 * c->warm_len;
-		env = getenv("PSMC_B200_WARM_HOT");
-		if (env && atoi(env) >= 0) c->warm_hot = atoi(env);
-		env = getenv("PSMC_B200_REPAIR_ROUNDS");
-		if (env && atoi(env) >= 0) c->repair_rounds = atoi(env);
-		env = getenv("PSMC_B200_CERT_EPS");
-		if (env && atof(env) > 0) c->cert_eps = atof(env);
-	}
-	// packed observations: every sequence starts on a 128-byte boundary (512 bins)
-	std::vector<int64_t> &ow0 = c->seq_ow0;
-	ow0.resize(c->n_seqs);
-	int64_t words = 0;
-	for (int i = 0; i < c->n_seqs; ++i) {
-		ow0[i] = words;
-		int64_t w = ((int64_t)c->L[i] + 15) / 16;
-		words += (w + 31) / 32 * 32;
-	}
-	c->words_obs = std::max<int64_t>(words, 32);
-	// chunk plans (forward plan = the context's main plan; backward plan for the fast path)
-	{
-		const char *env = getenv("PSMC_B200_SUB_LEN");
-		if (env && atoi(env) >= 64) c->sub_len = atoi(env);
-	}
-	c->seq_c0.resize(c->n_seqs); c->seq_nc.resize(c->n_seqs); c->seq_gb0.resize(c->n_seqs);
+	c->chunk_len_b = chunk_len_b;
 	std::vector<int32_t> k1;
+	std::vector<double> cw, cw_b;
 	auto build_plan = [&](int clen, bool is_main, std::vector<Chunk> &chunks, std::vector<Chunk> &subs,
-	                      std::vector<int32_t> &sub_parent, std::vector<int32_t> &chunk_sub0) {
+	                      std::vector<int32_t> &sub_parent, std::vector<int32_t> &chunk_sub0, std::vector<double> &w) {
 		int64_t gb = 0;
 		for (int i = 0; i < c->n_seqs; ++i) {
 			const int Li = c->L[i];
-			const int nc = (Li + clen - 1) / clen;
+			const int nc = c->mult[i] > 0 ? (Li + clen - 1) / clen : 0;
 			if (is_main) {
 				c->seq_c0[i] = (int)chunks.size();
 				c->seq_nc[i] = nc;
@@ -1498,11 +1458,12 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 				ch.u0 = (int)a;
 				ch.len = (int)(b - a);
 				ch.gb0 = gb + a;
-				ch.ow0 = ow0[i];
+				ch.ow0 = c->seq_ow0[i];
 				ch.Lseq = Li;
 				ch.pad_ = 0;
 				if (is_main && nc > 1) k1.push_back((int)chunks.size());
 				chunks.push_back(ch);
+				w.push_back((double)c->mult[i]);
 			}
 			gb += Li;
 		}
@@ -1527,13 +1488,176 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	};
 	std::vector<Chunk> subs, chunks_b, subs_b;
 	std::vector<int32_t> sub_parent, chunk_sub0, sub_parent_b, chunk_sub0_b;
-	build_plan(chunk_len, true, c->chunks, subs, sub_parent, chunk_sub0);
-	build_plan(chunk_len_b, false, chunks_b, subs_b, sub_parent_b, chunk_sub0_b);
+	c->chunks.clear();
+	build_plan(chunk_len, true, c->chunks, subs, sub_parent, chunk_sub0, cw);
+	build_plan(chunk_len_b, false, chunks_b, subs_b, sub_parent_b, chunk_sub0_b, cw_b);
 	c->n_chunks = (int)c->chunks.size();
 	c->n_sub = (int)subs.size();
 	c->n_chunks_b = (int)chunks_b.size();
 	c->n_sub_b = (int)subs_b.size();
 	c->n_k1 = (int)k1.size();
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream2), PSMC_B200_ECUDA);
+	if (!c->d_chunks || c->n_chunks > c->cap_chunks || c->n_chunks_b > c->cap_chunks_b || c->n_sub > c->cap_sub || c->n_sub_b > c->cap_sub_b || c->n_k1 > c->cap_k1) {
+		// grow-only, with head room: a replicate never needs much more than the all-sequences plan
+		free_plan(c);
+		auto room = [](int n) { return n + n / 8 + 16; };
+		const int cc = room(c->n_chunks), cb = room(c->n_chunks_b), cs = room(c->n_sub), csb = room(c->n_sub_b), ck = room(c->n_k1);
+		bool ok = true;
+		auto alloc = [&](void **ptr, size_t bytes) {
+			if (!ok) return;
+			if (bytes == 0) bytes = 256;
+			cudaError_t e_ = cudaMalloc(ptr, bytes);
+			if (e_ != cudaSuccess) { set_err(PSMC_B200_ECUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e_)); *ptr = nullptr; ok = false; return; }
+			c->bytes_plan += (int64_t)bytes;
+		};
+		const size_t cm = (size_t)std::max(cc, cb), sm = (size_t)std::max(cs, csb);
+		alloc((void **)&c->d_chunks, sizeof(Chunk) * (size_t)cc);
+		alloc((void **)&c->d_k1, sizeof(int32_t) * (size_t)ck);
+		alloc((void **)&c->d_T, sizeof(double) * (size_t)cc * NP * NP);
+		alloc((void **)&c->d_Tex, sizeof(int32_t) * (size_t)cc * NP);
+		alloc((void **)&c->d_vstart, sizeof(double) * (size_t)cc * NP);
+		alloc((void **)&c->d_bend, sizeof(double) * (size_t)cc * NP);
+		alloc((void **)&c->d_part, sizeof(double) * cm * S_COUNT * NP);
+		alloc((void **)&c->d_llpart, sizeof(double) * (size_t)cc);
+		alloc((void **)&c->d_fwarm, sizeof(double) * (size_t)cc * NP);
+		alloc((void **)&c->d_bwarm, sizeof(double) * cm * NP);
+		alloc((void **)&c->d_bexact, sizeof(double) * cm * NP);
+		alloc((void **)&c->d_bsave[0], sizeof(double) * (size_t)cb * NP);
+		alloc((void **)&c->d_bsave[1], sizeof(double) * (size_t)cb * NP);
+		alloc((void **)&c->d_chunks_b, sizeof(Chunk) * (size_t)cb);
+		alloc((void **)&c->d_sub_b, sizeof(Chunk) * (size_t)csb);
+		alloc((void **)&c->d_sub_parent_b, sizeof(int32_t) * (size_t)csb);
+		alloc((void **)&c->d_chunk_sub0_b, sizeof(int32_t) * (size_t)(cb + 1));
+		alloc((void **)&c->d_flag_b, sizeof(int32_t) * (size_t)(cb + 2));
+		alloc((void **)&c->d_flag, sizeof(int32_t) * (size_t)(cc + 2));
+		alloc((void **)&c->d_sub, sizeof(Chunk) * (size_t)cs);
+		alloc((void **)&c->d_sub_parent, sizeof(int32_t) * (size_t)cs);
+		alloc((void **)&c->d_chunk_sub0, sizeof(int32_t) * (size_t)(cc + 1));
+		alloc((void **)&c->d_Tsub, sizeof(double) * sm * NP * NP);
+		alloc((void **)&c->d_Texsub, sizeof(int32_t) * sm * NP);
+		alloc((void **)&c->d_vsub, sizeof(double) * (size_t)cs * NP);
+		alloc((void **)&c->d_bsub, sizeof(double) * (size_t)csb * NP);
+		alloc((void **)&c->d_llsub, sizeof(double) * (size_t)cs);
+		alloc((void **)&c->d_partsub, sizeof(double) * (size_t)csb * S_COUNT * NP);
+		alloc((void **)&c->d_cw, sizeof(double) * (size_t)cc);
+		alloc((void **)&c->d_cw_b, sizeof(double) * (size_t)cb);
+		c->bytes_total += c->bytes_plan;
+		if (!ok) { free_plan(c); return PSMC_B200_ECUDA; }
+		c->cap_chunks = cc; c->cap_chunks_b = cb; c->cap_sub = cs; c->cap_sub_b = csb; c->cap_k1 = ck;
+	}
+	c->bytes_transfer = (int64_t)c->n_chunks * NP * NP * 8;
+	cudaStream_t st = c->stream;
+#define UP(dst, vec)                                                                                                  \
+	do {                                                                                                              \
+		if (!(vec).empty())                                                                                           \
+			CUDA_TRY(cudaMemcpyAsync(dst, (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice, st), PSMC_B200_ECUDA); \
+	} while (0)
+	UP(c->d_chunks, c->chunks); UP(c->d_sub, subs); UP(c->d_sub_parent, sub_parent); UP(c->d_chunk_sub0, chunk_sub0);
+	UP(c->d_chunks_b, chunks_b); UP(c->d_sub_b, subs_b); UP(c->d_sub_parent_b, sub_parent_b); UP(c->d_chunk_sub0_b, chunk_sub0_b);
+	UP(c->d_k1, k1); UP(c->d_cw, cw); UP(c->d_cw_b, cw_b);
+	UP(c->d_seq_c0, c->seq_c0); UP(c->d_seq_nc, c->seq_nc);
+#undef UP
+	CUDA_TRY(cudaMemsetAsync(c->d_flag_b, 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), st), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemsetAsync(c->d_flag, 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), st), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(st), PSMC_B200_ECUDA); // the host vectors above go out of scope
+	c->have_prev = false;
+	c->fwd_valid = false;
+	c->launched = false;
+	++c->replans;
+	return 0;
+}
+
+extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *const *seqs,
+                                int32_t n_states, int32_t device, int32_t chunk_len, uint32_t flags)
+{
+	(void)flags;
+	if (!out) return set_err(PSMC_B200_EINVAL, "out is NULL");
+	*out = nullptr;
+	if (n_seqs < 0 || (n_seqs > 0 && (!L || !seqs))) return set_err(PSMC_B200_EINVAL, "bad sequence arguments");
+	if (n_states < 1 || n_states > 128) return set_err(PSMC_B200_EINVAL, "n_states=%d unsupported on the GPU path (1..128)", n_states);
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+		return set_err(PSMC_B200_ENODEV, "no CUDA device available (there is no CPU fallback)");
+	if (device < 0 || device >= ndev) return set_err(PSMC_B200_ENODEV, "device %d out of range (have %d)", device, ndev);
+	CUDA_TRY(cudaSetDevice(device), PSMC_B200_ENODEV);
+
+	psmc_b200_ctx *c = new psmc_b200_ctx();
+	c->device = device;
+	c->N = n_states;
+	c->NP = pad_states(n_states);
+	c->SPL = c->NP / 32;
+	// keep non-empty sequences only (the reference reads uninitialised memory for L == 0; nothing to count there)
+	std::vector<const signed char *> sp;
+	c->n_seqs_given = n_seqs;
+	c->kept_of.assign((size_t)std::max(n_seqs, 1), -1);
+	for (int i = 0; i < n_seqs; ++i) {
+		if (L[i] < 0) { free_ctx(c); return set_err(PSMC_B200_EINVAL, "negative sequence length"); }
+		if (L[i] == 0) continue;
+		c->kept_of[i] = (int32_t)c->L.size();
+		c->L.push_back(L[i]);
+		sp.push_back(seqs[i]);
+		c->total_bins += L[i];
+	}
+	c->n_seqs = (int)c->L.size();
+	c->mult.assign((size_t)c->n_seqs, 1);
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device), PSMC_B200_ENODEV);
+	c->sm_count = prop.multiProcessorCount;
+	{
+		const char *env = getenv("PSMC_B200_G_FWD");
+		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_fwd = atoi(env);
+		env = getenv("PSMC_B200_G_BWD");
+		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bwd = atoi(env);
+	}
+	if (chunk_len <= 0) {
+		const char *env = getenv("PSMC_B200_CHUNK");
+		if (env && atoi(env) > 0) chunk_len = atoi(env);
+	}
+	c->chunk_len_req = chunk_len > 0 ? chunk_len : 0;
+	{ // resident chunk slots per SM of the forward / backward kernels (one wave each)
+		int sf = 4, sb = 4;
+		switch (c->NP) {
+		case 32: chunk_slots<32>(c, &sf, &sb); break;
+		case 64: chunk_slots<64>(c, &sf, &sb); break;
+		default: chunk_slots<128>(c, &sf, &sb); break;
+		}
+		// measured on B200: beyond 16 forward chunks per SM the extra warm-up overlaps cost more than the shorter chunks save
+		if (sf > 16) sf = 16;
+		const char *env = getenv("PSMC_B200_CHUNKS_PER_SM");
+		if (env && atoi(env) > 0) sf = sb = atoi(env);
+		env = getenv("PSMC_B200_CHUNKS_PER_SM_FWD");
+		if (env && atoi(env) > 0) sf = atoi(env);
+		c->slots_fwd = sf; c->slots_bwd = sb;
+	}
+	{ // warm-up overlap: PSMC_B200_WARM=0 disables the fast path (always transfer matrices)
+		const char *env = getenv("PSMC_B200_WARM");
+		c->warm_len = env ? atoi(env) : 12288;
+		if (c->warm_len < 0) c->warm_len = 0;
+		env = getenv("PSMC_B200_WARM_BWD");
+		c->warm_len_bwd = (env && atoi(env) > 0) ? atoi(env) : 2 * c->warm_len;
+		env = getenv("PSMC_B200_WARM_HOT");
+		if (env && atoi(env) >= 0) c->warm_hot = atoi(env);
+		env = getenv("PSMC_B200_REPAIR_ROUNDS");
+		if (env && atoi(env) >= 0) c->repair_rounds = atoi(env);
+		env = getenv("PSMC_B200_CERT_EPS");
+		if (env && atof(env) > 0) c->cert_eps = atof(env);
+		env = getenv("PSMC_B200_SUB_LEN");
+		if (env && atoi(env) >= 64) c->sub_len = atoi(env);
+	}
+	// packed observations: every sequence starts on a 128-byte boundary (512 bins)
+	std::vector<int64_t> &ow0 = c->seq_ow0;
+	ow0.resize(c->n_seqs);
+	int64_t words = 0;
+	for (int i = 0; i < c->n_seqs; ++i) {
+		ow0[i] = words;
+		int64_t w = ((int64_t)c->L[i] + 15) / 16;
+		words += (w + 31) / 32 * 32;
+	}
+	c->words_obs = std::max<int64_t>(words, 32);
+	c->seq_c0.resize(c->n_seqs); c->seq_nc.resize(c->n_seqs); c->seq_gb0.resize(c->n_seqs);
 	const int NP = c->NP;
 #define ALLOC(ptr, bytes)                                                                         \
 	do {                                                                                          \
@@ -1549,43 +1673,14 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	} while (0)
 	c->bytes_obs = c->words_obs * 4;
 	c->bytes_forward = c->total_bins * NP * 8 + c->total_bins * 8;
-	c->bytes_transfer = (int64_t)c->n_chunks * NP * NP * 8;
 	ALLOC(c->d_obs, c->bytes_obs);
-	ALLOC(c->d_chunks, sizeof(Chunk) * (size_t)c->n_chunks);
-	ALLOC(c->d_k1, sizeof(int32_t) * (size_t)c->n_k1);
 	ALLOC(c->d_seq_c0, sizeof(int32_t) * (size_t)c->n_seqs);
 	ALLOC(c->d_seq_nc, sizeof(int32_t) * (size_t)c->n_seqs);
 	ALLOC(c->d_model, sizeof(double) * M_COUNT * NP);
 	ALLOC(c->d_fhat, (size_t)c->total_bins * NP * 8);
 	ALLOC(c->d_sc, (size_t)c->total_bins * 8);
-	ALLOC(c->d_T, (size_t)c->bytes_transfer);
-	ALLOC(c->d_Tex, sizeof(int32_t) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_vstart, sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_bend, sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_part, sizeof(double) * (size_t)std::max(c->n_chunks, c->n_chunks_b) * S_COUNT * NP);
-	ALLOC(c->d_llpart, sizeof(double) * (size_t)c->n_chunks);
 	ALLOC(c->d_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1));
-	ALLOC(c->d_fwarm, sizeof(double) * (size_t)c->n_chunks * NP);
-	ALLOC(c->d_bwarm, sizeof(double) * (size_t)std::max(c->n_chunks, c->n_chunks_b) * NP);
-	ALLOC(c->d_bexact, sizeof(double) * (size_t)std::max(c->n_chunks, c->n_chunks_b) * NP);
-	ALLOC(c->d_bsave[0], sizeof(double) * (size_t)c->n_chunks_b * NP);
-	ALLOC(c->d_bsave[1], sizeof(double) * (size_t)c->n_chunks_b * NP);
-	ALLOC(c->d_chunks_b, sizeof(Chunk) * (size_t)c->n_chunks_b);
-	ALLOC(c->d_sub_b, sizeof(Chunk) * (size_t)c->n_sub_b);
-	ALLOC(c->d_sub_parent_b, sizeof(int32_t) * (size_t)c->n_sub_b);
-	ALLOC(c->d_chunk_sub0_b, sizeof(int32_t) * (size_t)(c->n_chunks_b + 1));
-	ALLOC(c->d_flag_b, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2));
 	ALLOC(c->d_cert, sizeof(unsigned long long) * 8);
-	ALLOC(c->d_flag, sizeof(int32_t) * (size_t)(c->n_chunks + 2));
-	ALLOC(c->d_sub, sizeof(Chunk) * (size_t)c->n_sub);
-	ALLOC(c->d_sub_parent, sizeof(int32_t) * (size_t)c->n_sub);
-	ALLOC(c->d_chunk_sub0, sizeof(int32_t) * (size_t)(c->n_chunks + 1));
-	ALLOC(c->d_Tsub, sizeof(double) * (size_t)std::max(c->n_sub, c->n_sub_b) * NP * NP);
-	ALLOC(c->d_Texsub, sizeof(int32_t) * (size_t)std::max(c->n_sub, c->n_sub_b) * NP);
-	ALLOC(c->d_vsub, sizeof(double) * (size_t)c->n_sub * NP);
-	ALLOC(c->d_bsub, sizeof(double) * (size_t)c->n_sub_b * NP);
-	ALLOC(c->d_llsub, sizeof(double) * (size_t)c->n_sub);
-	ALLOC(c->d_partsub, sizeof(double) * (size_t)c->n_sub_b * S_COUNT * NP);
 #undef ALLOC
 #define CTRY(call)                                                                                \
 	do {                                                                                          \
@@ -1607,31 +1702,30 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	CTRY(cudaMallocHost((void **)&c->h_obs, (size_t)c->bytes_obs));
 	pack_all(c, sp.data());
 	CTRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
-	if (c->n_chunks) CTRY(cudaMemcpyAsync(c->d_chunks, c->chunks.data(), sizeof(Chunk) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream));
-	if (c->n_sub) {
-		CTRY(cudaMemcpyAsync(c->d_sub, subs.data(), sizeof(Chunk) * (size_t)c->n_sub, cudaMemcpyHostToDevice, c->stream));
-		CTRY(cudaMemcpyAsync(c->d_sub_parent, sub_parent.data(), sizeof(int32_t) * (size_t)c->n_sub, cudaMemcpyHostToDevice, c->stream));
-	}
-	CTRY(cudaMemcpyAsync(c->d_chunk_sub0, chunk_sub0.data(), sizeof(int32_t) * (size_t)(c->n_chunks + 1), cudaMemcpyHostToDevice, c->stream));
-	if (c->n_chunks_b) CTRY(cudaMemcpyAsync(c->d_chunks_b, chunks_b.data(), sizeof(Chunk) * (size_t)c->n_chunks_b, cudaMemcpyHostToDevice, c->stream));
-	if (c->n_sub_b) {
-		CTRY(cudaMemcpyAsync(c->d_sub_b, subs_b.data(), sizeof(Chunk) * (size_t)c->n_sub_b, cudaMemcpyHostToDevice, c->stream));
-		CTRY(cudaMemcpyAsync(c->d_sub_parent_b, sub_parent_b.data(), sizeof(int32_t) * (size_t)c->n_sub_b, cudaMemcpyHostToDevice, c->stream));
-	}
-	CTRY(cudaMemcpyAsync(c->d_chunk_sub0_b, chunk_sub0_b.data(), sizeof(int32_t) * (size_t)(c->n_chunks_b + 1), cudaMemcpyHostToDevice, c->stream));
-	CTRY(cudaMemsetAsync(c->d_flag_b, 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), c->stream));
-	if (c->n_k1) CTRY(cudaMemcpyAsync(c->d_k1, k1.data(), sizeof(int32_t) * (size_t)c->n_k1, cudaMemcpyHostToDevice, c->stream));
-	if (c->n_seqs) {
-		CTRY(cudaMemcpyAsync(c->d_seq_c0, c->seq_c0.data(), sizeof(int32_t) * (size_t)c->n_seqs, cudaMemcpyHostToDevice, c->stream));
-		CTRY(cudaMemcpyAsync(c->d_seq_nc, c->seq_nc.data(), sizeof(int32_t) * (size_t)c->n_seqs, cudaMemcpyHostToDevice, c->stream));
-	}
-	CTRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, c->stream));
-	CTRY(cudaMemsetAsync(c->d_flag, 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), c->stream));
-	CTRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, c->stream));
 	CTRY(cudaStreamSynchronize(c->stream));
 #undef CTRY
+	{
+		int rc = replan(c);
+		if (rc != 0) { free_ctx(c); return rc; }
+	}
 	*out = c;
 	return 0;
+}
+
+// Multiplicities of the resident sequences for the following E-steps (bootstrap replicates, aux.c:8-47).
+extern "C" int psmc_b200_set_multiplicity(psmc_b200_ctx *c, const int32_t *mult)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	std::vector<int32_t> m((size_t)c->n_seqs, 1);
+	if (mult)
+		for (int i = 0; i < c->n_seqs_given; ++i) {
+			if (mult[i] < 0) return set_err(PSMC_B200_EINVAL, "negative multiplicity");
+			if (c->kept_of[i] >= 0) m[c->kept_of[i]] = mult[i];
+		}
+	if (m == c->mult) return 0;
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	c->mult.swap(m);
+	return replan(c);
 }
 
 extern "C" int psmc_b200_create_cat(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat,
@@ -1808,7 +1902,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 			++c->launches;
 		}
 		cudaEventRecord(c->ev[4], st);
-		k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks, c->N, NP, c->d_stats);
+		k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw : nullptr);
 		++c->launches;
 		cudaEventRecord(c->ev[5], st);
 	}
@@ -1862,7 +1956,7 @@ static int launch_warm(psmc_b200_ctx *c)
 		k_fold<<<c->n_chunks_b, 128, 0, st>>>(c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[4], st);
-	k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats);
+	k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
 	k_certify<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
 	k_certify<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
 	cudaEventRecord(c->ev[5], st);
@@ -2000,7 +2094,7 @@ extern "C" int psmc_b200_estep_finish(psmc_b200_ctx *c, int64_t n_seqs_total, ps
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	collect_times(c, true);
 	c->launched = false;
-	if (n_seqs_total < 0) n_seqs_total = c->n_seqs;
+	if (n_seqs_total < 0) n_seqs_total = c->n_seq_eff;
 	return psmc_b200_unpack_stats(c->N, c->h_stats, n_seqs_total, out);
 }
 
@@ -2024,7 +2118,7 @@ extern "C" int psmc_b200_estep(psmc_b200_ctx *c, const psmc_b200_model *model, p
 {
 	int rc = psmc_b200_estep_launch(c, model);
 	if (rc) return rc;
-	return psmc_b200_estep_finish(c, c->n_seqs, out);
+	return psmc_b200_estep_finish(c, c->n_seq_eff, out);
 }
 
 extern "C" int psmc_b200_factorize(int32_t N, const double *a, double tol, double *U, double *V, double *W, double *Z, double *D)
@@ -2070,6 +2164,7 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
 	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
 	if (seq_id < 0 || seq_id >= c->n_seqs) return set_err(PSMC_B200_EINVAL, "seq_id out of range");
 	if (!best_k || !best_p) return set_err(PSMC_B200_EINVAL, "best_k/best_p are NULL");
+	if (c->mult[seq_id] <= 0) return set_err(PSMC_B200_EINVAL, "sequence %d has multiplicity 0 (psmc_b200_set_multiplicity)", seq_id);
 	int rc = 0;
 	if (model) {
 		rc = check_model(c, model);
@@ -2155,5 +2250,7 @@ extern "C" int psmc_b200_get_info(const psmc_b200_ctx *c, psmc_b200_info *info)
 	info->repaired_bwd = (int32_t)c->rep_bwd_chunks;
 	info->failed_fwd = (int32_t)c->rep_fwd_fail;
 	info->failed_bwd = (int32_t)c->rep_bwd_fail;
+	info->active_bins = c->active_bins;
+	info->n_seqs_effective = c->n_seq_eff;
 	return 0;
 }

@@ -157,6 +157,16 @@ class EStep:
                                                   _d(s) if want_s else None))
         return dict(best_k=bk, best_p=bp, post=post, p_recomb=pr, s=s)
 
+    def set_multiplicity(self, mult=None):
+        """bootstrap replicate = multiplicity of every resident record (aux.c:8-47); None restores 1 everywhere"""
+        if mult is None:
+            check(self.lib, self.lib.psmc_b200_set_multiplicity(self.h, None))
+            return
+        m = np.ascontiguousarray(mult, dtype=np.int32)
+        if m.shape != (self.n_seqs,):
+            raise ValueError("mult must have one entry per record given at construction (%d)" % self.n_seqs)
+        check(self.lib, self.lib.psmc_b200_set_multiplicity(self.h, m.ctypes.data_as(C.POINTER(C.c_int32))))
+
     def set_warm(self, warm_len=-1, eps=0.0):
         """warm-up overlap in bins (0 = exact transfer-matrix path only) and certificate tolerance"""
         check(self.lib, self.lib.psmc_b200_set_warm(self.h, warm_len, eps))

@@ -219,3 +219,29 @@ def read_psmcfa(path):
         return names, seqs, L.psmch_py_read_sum(h, 0), L.psmch_py_read_sum(h, 1)
     finally:
         L.psmch_py_read_free(h)
+
+
+def split_lengths(lengths, trunk):
+    """the splitfa rule (utils/splitfa.c:20-31) as applied by `psmc --split`: [(record, piece number, length)]"""
+    L = load_host()
+    lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+    cap = int(sum(int(x) // max(trunk, 1) + 2 for x in lengths)) + 4
+    oL = np.zeros(cap, dtype=np.int32); rec = np.zeros(cap, dtype=np.int32); idx = np.zeros(cap, dtype=np.int32)
+    m = L.psmch_py_split(len(lengths), lengths.ctypes.data_as(_ip), int(trunk), oL.ctypes.data_as(_ip),
+                         rec.ctypes.data_as(_ip), idx.ctypes.data_as(_ip), cap)
+    if m < 0:
+        raise ValueError("bad trunk size")
+    return [(int(rec[i]), int(idx[i]), int(oL[i])) for i in range(m)]
+
+
+def draw_replicate(lengths, seed):
+    """one bootstrap replicate as multiplicities (host/bootstrap.c psmch_draw, srand48(seed) stream) and, for
+    cross-checking, the multiplicities the copying path of `psmc -b --seed` (host/resamp.c) produces"""
+    L = load_host()
+    lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+    mult = np.zeros(len(lengths), dtype=np.int32); mult2 = np.zeros(len(lengths), dtype=np.int32)
+    view = np.zeros(6, dtype=np.int64)
+    L.psmch_py_draw.argtypes = [C.c_int, _ip, C.c_long, _ip, C.POINTER(C.c_int64), _ip]
+    L.psmch_py_draw(len(lengths), lengths.ctypes.data_as(_ip), int(seed), mult.ctypes.data_as(_ip),
+                    view.ctypes.data_as(C.POINTER(C.c_int64)), mult2.ctypes.data_as(_ip))
+    return mult, mult2, view
