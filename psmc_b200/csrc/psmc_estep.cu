@@ -973,8 +973,8 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 // warm-up result bwarm (fast path, K4w).  With publish != 0 the direction computed for the last bin of chunk c-1
 // goes to bexact[c-1] for the certificate; usave/bsave_next feed the optional warm start of the next E-step.
 // ------------------------------------------------------------------------------------------------
-template <int SPL, int G>
-__global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
+template <int SPL, int G, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
                                                   const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                   const double *__restrict__ bdir, int publish, const double *__restrict__ fhat,
                                                   const double *__restrict__ sc, double *__restrict__ part,
@@ -1282,6 +1282,8 @@ struct psmc_b200_ctx {
 	bool mode_warm = false, certified = true;
 	int fallbacks = 0, repair_rounds = 3;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
+	int k4_minb = 1;            // PSMC_B200_K4_MINB=4: backward kernel compiled for 4 resident blocks per SM (128 registers, a few spills)
+	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
 	double mis_f = 0.0, mis_b = 0.0;
@@ -1373,12 +1375,29 @@ extern "C" void psmc_b200_destroy(psmc_b200_ctx *ctx) { free_ctx(ctx); }
 
 // 2 bits per bin, 16 bins per word, little end first; every sequence starts on a 128-byte boundary.
 // Symbols: 0 hom, 1 het, everything else missing (cli.c:15-32 maps to {0,1,2}).
+static inline uint32_t squeeze8(uint64_t x) // eight bytes holding 0..2 -> sixteen bits, byte k -> bits 2k..2k+1
+{
+	x = (x | (x >> 6)) & 0x000F000F000F000Full;
+	x = (x | (x >> 12)) & 0x000000FF000000FFull;
+	return (uint32_t)((x | (x >> 24)) & 0xFFFFull);
+}
 static void pack_range(const signed char *s, int64_t u0, int64_t u1, uint32_t *dst)
 {
-	for (int64_t w = u0 >> 4; w < (u1 + 15) >> 4; ++w) {
-		const int64_t b0 = w << 4, b1 = std::min<int64_t>(b0 + 16, u1);
-		uint32_t v = 0xaaaaaaaau; // padding = missing
-		for (int64_t u = b0; u < b1; ++u) {
+	int64_t w = u0 >> 4;
+	const int64_t w_full = u1 >> 4; // words [w, w_full) are complete
+	for (; w < w_full; ++w) {
+		uint8_t t[16];
+		const uint8_t *src = (const uint8_t *)s + (w << 4);
+		for (int i = 0; i < 16; ++i) t[i] = src[i] > 1u ? 2u : src[i]; // vectorised by the host compiler (pminub)
+		uint64_t lo, hi;
+		memcpy(&lo, t, 8);
+		memcpy(&hi, t + 8, 8);
+		dst[w] = squeeze8(lo) | (squeeze8(hi) << 16);
+	}
+	if (w < (u1 + 15) >> 4) { // ragged last word, padding = missing
+		const int64_t b0 = w << 4;
+		uint32_t v = 0xaaaaaaaau;
+		for (int64_t u = b0; u < u1; ++u) {
 			const uint32_t x = (uint8_t)s[u];
 			const int sh = (int)(u - b0) * 2;
 			v = (v & ~(3u << sh)) | ((x > 1u ? 2u : x) << sh);
@@ -1388,14 +1407,21 @@ static void pack_range(const signed char *s, int64_t u0, int64_t u1, uint32_t *d
 }
 static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 {
-	for (int64_t w = 0; w < c->words_obs; ++w) c->h_obs[w] = 0xaaaaaaaau;
+	// only the alignment padding behind every sequence needs the 'missing' fill; the rest is overwritten below
+	for (int i = 0; i < c->n_seqs; ++i) {
+		const int64_t w0 = c->seq_ow0[i] + ((int64_t)c->L[i] + 15) / 16;
+		const int64_t w1 = (i + 1 < c->n_seqs) ? c->seq_ow0[i + 1] : c->words_obs;
+		for (int64_t w = w0; w < w1; ++w) c->h_obs[w] = 0xaaaaaaaau;
+	}
+	if (c->n_seqs == 0)
+		for (int64_t w = 0; w < c->words_obs; ++w) c->h_obs[w] = 0xaaaaaaaau;
 	struct Job { const signed char *s; int64_t u0, u1; uint32_t *dst; };
 	std::vector<Job> jobs;
 	const int64_t step = 1 << 20; // multiple of 16
 	for (int i = 0; i < c->n_seqs; ++i)
 		for (int64_t u = 0; u < c->L[i]; u += step)
 			jobs.push_back({sp[i], u, std::min<int64_t>(u + step, c->L[i]), c->h_obs + c->seq_ow0[i]});
-	unsigned nt = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+	unsigned nt = std::min<unsigned>(16, std::max<unsigned>(1, std::thread::hardware_concurrency()));
 	if (jobs.size() < 4) nt = 1;
 	if (nt == 1) {
 		for (auto &j : jobs) pack_range(j.s, j.u0, j.u1, j.dst);
@@ -1611,6 +1637,11 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_fwd = atoi(env);
 		env = getenv("PSMC_B200_G_BWD");
 		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bwd = atoi(env);
+		c->g_bww = 8; // measured on B200: the narrow warm-up kernel leaves the most issue slots to the concurrent forward kernel
+		env = getenv("PSMC_B200_K4_MINB");
+		if (env && atoi(env) >= 4) c->k4_minb = 4;
+		env = getenv("PSMC_B200_G_BWW");
+		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bww = atoi(env);
 	}
 	if (chunk_len <= 0) {
 		const char *env = getenv("PSMC_B200_CHUNK");
@@ -1829,18 +1860,19 @@ template <int NP>
 static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const double *bdir, int publish, double *bsave_next)
 {
 	cudaStream_t st = c->stream;
-#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(n, G_), 128, 0, st>>>(chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
-	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8);
-	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16);
-	else BWD(32);
+#define BWD(G_, MB_) k_backward<NP / G_, G_, MB_><<<blocks_for(n, G_), 128, 0, st>>>(chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
+	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8, 1);
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16, 1);
+	else if (c->k4_minb >= 4) BWD(32, 4);
+	else BWD(32, 1);
 #undef BWD
 }
 template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
 #define BWW(G_) k_backward_warm<NP / G_, G_><<<blocks_for(c->n_chunks_b, G_), 128, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
-	if (c->g_bwd == 8 && NP / 8 <= 8) BWW(8);
-	else if (c->g_bwd <= 16 && NP / 16 <= 8) BWW(16);
+	if (c->g_bww == 8 && NP / 8 <= 8) BWW(8);
+	else if (c->g_bww <= 16 && NP / 16 <= 8) BWW(16);
 	else BWW(32);
 #undef BWW
 }
@@ -1861,13 +1893,16 @@ static void chunk_slots(const psmc_b200_ctx *c, int *slots_fwd, int *slots_bwd)
 {
 	int bf = 1, bb = 1, gf = 32, gb = 32;
 #define OCC(K_, G_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, K_<NP / G_, G_>, 128, 0)
+#define OCCB(G_, MB_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, k_backward<NP / G_, G_, MB_>, 128, 0)
 	if (c->g_fwd == 8 && NP / 8 <= 8) { gf = 8; OCC(k_forward, 8, bf); }
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) { gf = 16; OCC(k_forward, 16, bf); }
 	else OCC(k_forward, 32, bf);
-	if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCC(k_backward, 8, bb); }
-	else if (c->g_bwd <= 16 && NP / 16 <= 4) { gb = 16; OCC(k_backward, 16, bb); }
-	else OCC(k_backward, 32, bb);
+	if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCCB(8, 1, bb); }
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) { gb = 16; OCCB(16, 1, bb); }
+	else if (c->k4_minb >= 4) OCCB(32, 4, bb);
+	else OCCB(32, 1, bb);
 #undef OCC
+#undef OCCB
 	*slots_fwd = bf * 4 * (32 / gf);
 	*slots_bwd = bb * 4 * (32 / gb);
 }
