@@ -29,6 +29,7 @@ int psmch_model_alloc(psmch_model_t *m, const psmch_space_t *sp)
 	m->U = blk; blk += N; m->V = blk; blk += N; m->W = blk; blk += N; m->Z = blk; blk += N; m->D = blk; blk += N;
 	m->lam = blk; blk += N; m->alp = blk; blk += N + 1; m->bet = blk; blk += N; m->qax = blk; blk += N; m->tau = blk; blk += N + 1;
 	m->vw = blk; /* 4*(N+2) + 21*N doubles of scratch for the vectorised trial evaluations */
+	m->t_max_t = NAN;
 	return 0;
 }
 
@@ -45,6 +46,7 @@ void psmch_model_update(const psmch_space_t *sp, const double *params, psmch_mod
 	double theta, rho, max_t, dt = 0.0, sum_t, C_pi, C_sigma;
 	double *lam = m->lam, *alp = m->alp, *bet = m->bet, *qax = m->qax, *tau = m->tau, *t = m->t;
 	if (params != m->params) memcpy(m->params, params, sizeof(double) * sp->n_params);
+	m->fast_valid = 0; m->t_max_t = NAN; /* t[] and e[] below come from scalar libm: the fast path's caches do not apply */
 	theta = params[0]; rho = params[1]; max_t = params[2];
 	for (k = 0; k < N; ++k) lam[k] = params[sp->par_map[k] + PSMCH_N_PARAMS];
 	if (sp->inp_ti == 0) {                               /* core.c:9-14 */
@@ -111,11 +113,14 @@ void psmch_model_update_fast(const psmch_space_t *sp, const double *params, psmc
 	theta = params[0]; rho = params[1]; max_t = params[2];
 	for (k = 0; k < N; ++k) lam[k] = params[sp->par_map[k] + PSMCH_N_PARAMS];
 	if (sp->inp_ti == 0) {
-		const double beta = log(1.0 + max_t / sp->alpha0) / n;
-		for (k = 0; k < n; ++k) w0[k] = beta * k;
-		psmch_vexp(n, w0, w1);
-		for (k = 0; k < n; ++k) t[k] = sp->alpha0 * (w1[k] - 1);
-		t[n] = max_t; t[n + 1] = PSMCH_T_INF;
+		if (!(max_t == m->t_max_t)) { /* most trial points move one lambda or theta/rho: the boundaries stay */
+			const double beta = log(1.0 + max_t / sp->alpha0) / n;
+			for (k = 0; k < n; ++k) w0[k] = beta * k;
+			psmch_vexp(n, w0, w1);
+			for (k = 0; k < n; ++k) t[k] = sp->alpha0 * (w1[k] - 1);
+			t[n] = max_t; t[n + 1] = PSMCH_T_INF;
+			m->t_max_t = max_t;
+		}
 	} else {
 		memcpy(t, sp->inp_ti, sizeof(double) * (n + 1));
 		t[n + 1] = PSMCH_T_INF;
@@ -148,6 +153,7 @@ void psmch_model_update_fast(const psmch_space_t *sp, const double *params, psmc
 	}
 	psmch_vexp(N, w3, m->e);
 	for (k = 0; k < N; ++k) m->e[N + k] = 1.0 - m->e[k];
+	m->fast_valid = 1; /* w3 = log e[0][.] for psmch_Q_fast */
 }
 
 /* dense view (tests, diagnostics) */

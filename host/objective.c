@@ -118,7 +118,13 @@ double psmch_Q_fast(const psmch_model_t *m, const psmch_counts_t *c)
 		if (k > 0 && (m->U[k] * m->V[0] <= 0.0 || m->U[N - 1] * m->V[k - 1] <= 0.0)) return -PSMCH_INF;
 		if (k < N - 1 && (m->W[k] * m->Z[N - 1] <= 0.0 || m->W[0] * m->Z[k + 1] <= 0.0)) return -PSMCH_INF;
 	}
-	for (k = 0; k < 2 * N; ++k) { x[n] = m->e[k]; w[n] = c->E[k]; ++n; }
+	double q_e0 = 0.0;
+	if (m->fast_valid) { /* log e[0][k] = -theta (avg_t_k + dt) is what the model update exponentiated: no logarithm needed */
+		q_e0 = psmch_vdot(N, c->E, m->vw + 3 * (N + 2));
+		for (k = N; k < 2 * N; ++k) { x[n] = m->e[k]; w[n] = c->E[k]; ++n; }
+	} else {
+		for (k = 0; k < 2 * N; ++k) { x[n] = m->e[k]; w[n] = c->E[k]; ++n; }
+	}
 	for (k = 0; k < N; ++k) { x[n] = m->D[k]; w[n] = c->AD[k]; ++n; }
 	for (k = 1; k < N; ++k) {
 		x[n] = fabs(m->U[k]); w[n] = c->RL[k]; ++n;
@@ -129,5 +135,5 @@ double psmch_Q_fast(const psmch_model_t *m, const psmch_counts_t *c)
 		x[n] = fabs(m->V[k]); w[n] = c->CL[k]; ++n;
 	}
 	psmch_vlog(n, x, lg);
-	return psmch_vdot(n, w, lg) - c->Q0;
+	return q_e0 + psmch_vdot(n, w, lg) - c->Q0;
 }

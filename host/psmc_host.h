@@ -81,6 +81,8 @@ typedef struct {
 	double C_pi, C_sigma;
 	double *lam, *alp, *bet, *qax, *tau; /* scratch */
 	double *vw;                          /* scratch of the vectorised trial evaluations */
+	int fast_valid;                      /* vw holds log e[0][k] = -theta (avg_t_k + dt) of the current point (set by psmch_model_update_fast) */
+	double t_max_t;                      /* max_t the boundaries t[] were last computed for by the fast path (NaN = none) */
 } psmch_model_t;
 
 int  psmch_model_alloc(psmch_model_t *m, const psmch_space_t *sp);

@@ -1,22 +1,25 @@
-/* vmath.c -- the only translation unit built with -O3 -ffast-math -mavx2 -mfma: plain loops over exp/log that gcc
- * turns into glibc libmvec calls (_ZGVdN4v_exp / _ZGVdN4v_log, 4 doubles per call, <= 4 ulp).  Used ONLY inside the
+/* vmath.c -- the only translation unit built with -O3 -ffast-math: plain loops over exp/log that gcc turns into glibc
+ * libmvec calls (<= 4 ulp).  Every function is compiled three times (AVX-512: _ZGVeN8v_*, 8 doubles per call; AVX2+FMA:
+ * _ZGVdN4v_*; baseline) and the loader picks the best the host CPU supports (ifunc).  Used ONLY inside the
  * Hooke-Jeeves trial evaluations (psmch_model_update_fast / psmch_Q_fast); the model that is printed and sent to
  * the GPU is always recomputed with the scalar, bit-reproducible path. */
 #include <math.h>
 
-void psmch_vexp(int n, const double *x, double *y)
+#define VCLONES __attribute__((target_clones("avx512f", "avx2,fma", "default")))
+
+VCLONES void psmch_vexp(int n, const double *x, double *y)
 {
 	int i;
 	for (i = 0; i < n; ++i) y[i] = exp(x[i]);
 }
 
-void psmch_vlog(int n, const double *x, double *y)
+VCLONES void psmch_vlog(int n, const double *x, double *y)
 {
 	int i;
 	for (i = 0; i < n; ++i) y[i] = log(x[i]);
 }
 
-double psmch_vdot(int n, const double *a, const double *b)
+VCLONES double psmch_vdot(int n, const double *a, const double *b)
 {
 	double s = 0.0;
 	int i;
@@ -26,7 +29,7 @@ double psmch_vdot(int n, const double *a, const double *b)
 
 /* dependency-free per-interval arithmetic of the model update (core.c:100-122 regrouped), vectorised by gcc;
  * sum_t[k] = t_k - t_0 is passed in.  Outputs sigma, the five factor arrays and the argument of the avg_t logarithm. */
-void psmch_vmodel_phase1(int N, const double *alp, const double *lam, const double *tau, const double *bet,
+VCLONES void psmch_vmodel_phase1(int N, const double *alp, const double *lam, const double *tau, const double *bet,
                          const double *qax, const double *sumt, double C_pi, double rho, double C_sigma,
                          double *sigma, double *U, double *V, double *W, double *Z, double *D, double *logarg)
 {
@@ -50,13 +53,13 @@ void psmch_vmodel_phase1(int N, const double *alp, const double *lam, const doub
 }
 
 /* q_aux (core.c:93-94) and 1/alpha, vectorised */
-void psmch_vmodel_qaux(int n, const double *alp, const double *lam, const double *tau, const double *bet, double *qax)
+VCLONES void psmch_vmodel_qaux(int n, const double *alp, const double *lam, const double *tau, const double *bet, double *qax)
 {
 	int l;
 	for (l = 0; l < n; ++l) qax[l] = (alp[l] - alp[l + 1]) * (bet[l] - lam[l] / alp[l]) + tau[l];
 }
 
-void psmch_vinv(int n, const double *x, double *y)
+VCLONES void psmch_vinv(int n, const double *x, double *y)
 {
 	int i;
 	for (i = 0; i < n; ++i) y[i] = 1.0 / x[i];

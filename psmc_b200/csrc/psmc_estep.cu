@@ -109,6 +109,16 @@ struct ScanMasks {
 		}
 		up[STEPS] = dn[STEPS] = 0.0;
 	}
+	// keep the masks in registers: without this ptxas re-derives every mask from a predicate in every iteration
+	// (ISETP + FSEL + MOV per scan stage); only for kernels with registers to spare
+	__device__ __forceinline__ void pin()
+	{
+#pragma unroll
+		for (int k = 0; k < STEPS; ++k) {
+			asm volatile("" : "+d"(up[k]));
+			asm volatile("" : "+d"(dn[k]));
+		}
+	}
 };
 template <int G>
 __device__ __forceinline__ double gscan_up(double t, const ScanMasks<G> &m) // exclusive prefix over the lanes of a group
@@ -135,15 +145,13 @@ __device__ __forceinline__ double gsum(double t) // all-reduce over the lanes of
 	for (int d = G >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULLMASK, t, d, G);
 	return t;
 }
-// reciprocal of a positive normal double: hardware seed + two Newton steps (~1 ulp; the IEEE division drags a
-// slow path and a range check into the loop)
+// reciprocal of a positive normal double: hardware seed (20 bits) + two Newton steps (2^-80 before rounding, ~1 ulp;
+// the IEEE division drags a slow path and a range check into the loop)
 __device__ __forceinline__ double fast_rcp(double s)
 {
 	double r;
 	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
 	double e = fma(-s, r, 1.0);
-	r = fma(r, e, r);
-	e = fma(-s, r, 1.0);
 	r = fma(r, e, r);
 	e = fma(-s, r, 1.0);
 	return fma(r, e, r);
@@ -264,13 +272,15 @@ template <int SPL, int G, int COLS>
 __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ chunks, const int32_t *__restrict__ k1_list,
                                                       const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                       double *__restrict__ T, int32_t *__restrict__ Tex, int N,
-                                                      const int32_t *__restrict__ flag, int sel)
+                                                      const int32_t *__restrict__ flag, int sel, const int32_t *__restrict__ skip)
 {
 	constexpr int NP = SPL * G;
 	// sel 0: chunk list (transfer mode).  sel 3: repair rounds of the warm-up mode: `chunks` is the SUB-chunk table,
 	// one block row per sub-chunk, only those whose parent chunk is flagged (flag has guard entries at -1 and n).
 	const int c = sel == 0 ? k1_list[blockIdx.x] : (int)blockIdx.x;
-	if (sel == 3 && !flag[k1_list[c]]) return; // k1_list = parent chunk of every sub-chunk in this mode
+	// k1_list = parent chunk of every sub-chunk in this mode; `skip` marks parents whose operators are already there
+	// (computed ahead of time from the previous E-step's failures, see launch_warm)
+	if (sel == 3 && (!flag[k1_list[c]] || (skip && skip[k1_list[c]]))) return;
 	const Chunk ch = chunks[c];
 	const int gl = threadIdx.x % G;
 	const int col = blockIdx.y * COLS + threadIdx.x / G;
@@ -607,6 +617,7 @@ __device__ __forceinline__ double forward_chunk(const Chunk &ch, bool valid, int
 	for (int i = 0; i < SPL; ++i) g[i] = f[i];
 	ScanMasks<G> mk;
 	mk.init(gl);
+	mk.pin();
 	for (int t = 0; t < trips; ++t) {
 		const int u = ubeg + t;
 		const bool act = valid && u < uend;
@@ -720,7 +731,8 @@ __device__ __forceinline__ double fwd_boundary_mismatch(const Chunk &ch, int c, 
 template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ fhat, const double *__restrict__ fwarm,
-                                                  int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat)
+                                                  int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat,
+                                                  int32_t *__restrict__ pred_next)
 {
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
@@ -730,6 +742,7 @@ __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chun
 	if (!(ch.flags & CH_FIRST)) fl = fwd_boundary_mismatch<SPL>(ch, c, fhat, fwarm, gl * SPL, N) > eps ? 1 : 0;
 	if (gl == 0) {
 		flag_f[c] = fl;
+		if (pred_next) pred_next[c] = fl;
 		if (fl) atomicAdd(&stat[0], 1ull);
 	}
 }
@@ -940,6 +953,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 	uint32_t word = 0;
 	ScanMasks<G> mk;
 	mk.init(gl);
+	mk.pin();
 	for (int t = 0; t < trips; ++t) {
 		const int u = z0 - t;
 		const bool act = id.valid && u > ulast;
@@ -973,8 +987,8 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 // warm-up result bwarm (fast path, K4w).  With publish != 0 the direction computed for the last bin of chunk c-1
 // goes to bexact[c-1] for the certificate; usave/bsave_next feed the optional warm start of the next E-step.
 // ------------------------------------------------------------------------------------------------
-template <int SPL, int G, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
+template <int SPL, int G>
+__global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
                                                   const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                   const double *__restrict__ bdir, int publish, const double *__restrict__ fhat,
                                                   const double *__restrict__ sc, double *__restrict__ part,
@@ -1025,7 +1039,8 @@ __device__ __forceinline__ double bwd_boundary_mismatch(int c, const double *__r
 template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ bwarm, const double *__restrict__ bexact,
-                                                  int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat)
+                                                  int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat,
+                                                  int32_t *__restrict__ pred_next)
 {
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
@@ -1034,6 +1049,7 @@ __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chun
 	if (!(chunks[c].flags & CH_LAST)) fl = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, gl * SPL, N) > eps ? 1 : 0;
 	if (gl == 0) {
 		flag_b[c] = fl;
+		if (pred_next) pred_next[c] = fl;
 		if (fl) atomicAdd(&stat[2], 1ull);
 	}
 }
@@ -1277,12 +1293,12 @@ struct psmc_b200_ctx {
 	int32_t *d_sub_parent_b = nullptr, *d_chunk_sub0_b = nullptr, *d_flag_b = nullptr;
 	unsigned long long *d_cert = nullptr, *h_cert = nullptr;            // [failed boundaries, max fwd mismatch bits, max bwd mismatch bits]
 	int warm_len = 0;          // bins of forward warm-up overlap (0 = always use the transfer-matrix path)
+	bool warm_bwd_fixed = false; // PSMC_B200_WARM_BWD given: no adaptive cap
 	int warm_len_bwd = 0;      // bins of backward warm-up overlap (runs concurrently with the forward kernel, so it can be longer)
 	double cert_eps = 1e-12;
 	bool mode_warm = false, certified = true;
 	int fallbacks = 0, repair_rounds = 3;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
-	int k4_minb = 1;            // PSMC_B200_K4_MINB=4: backward kernel compiled for 4 resident blocks per SM (128 registers, a few spills)
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
@@ -1311,6 +1327,16 @@ struct psmc_b200_ctx {
 	int chunk_len_req = 0;           // chunk length the caller / environment asked for (0 = one resident wave)
 	int sm_count = 0;
 	double *d_cw = nullptr, *d_cw_b = nullptr; // per-chunk multiplicity, forward / backward plan
+	// Slow-mixing boundaries are a property of the data (het-poor, low-TMRCA tracts): the chunks that needed a repair in
+	// one E-step almost always need it in the next.  Their transfer operators depend on model + observations only, so they
+	// are computed AHEAD of time on the side stream, hidden behind the forward kernel (d_pred*: round-1 failures of the
+	// previous E-step, double-buffered; the backward plan has its own operator buffer so both can be in flight).
+	int32_t *d_pred[2] = {nullptr, nullptr}, *d_pred_b[2] = {nullptr, nullptr};
+	int pred_cur = 0;
+	double *d_Tsub_b = nullptr;
+	int32_t *d_Texsub_b = nullptr;
+	cudaEvent_t ev_k1f = nullptr, ev_k1b = nullptr;
+	bool predict = true; // PSMC_B200_PREDICT=0 disables
 	int cap_chunks = 0, cap_chunks_b = 0, cap_sub = 0, cap_sub_b = 0, cap_k1 = 0; // allocated capacities of the plan buffers
 	int64_t bytes_plan = 0;
 	int replans = 0;
@@ -1342,7 +1368,9 @@ static void free_plan(psmc_b200_ctx *c)
 	              (void **)&c->d_bsave[0], (void **)&c->d_bsave[1], (void **)&c->d_chunks_b, (void **)&c->d_sub_b, (void **)&c->d_sub_parent_b,
 	              (void **)&c->d_chunk_sub0_b, (void **)&c->d_flag_b, (void **)&c->d_flag, (void **)&c->d_sub, (void **)&c->d_sub_parent,
 	              (void **)&c->d_chunk_sub0, (void **)&c->d_Tsub, (void **)&c->d_Texsub, (void **)&c->d_vsub, (void **)&c->d_bsub,
-	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b};
+	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b,
+	              (void **)&c->d_pred[0], (void **)&c->d_pred[1], (void **)&c->d_pred_b[0], (void **)&c->d_pred_b[1],
+	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b};
 	for (auto q : p) { cudaFree(*q); *q = nullptr; }
 	c->bytes_total -= c->bytes_plan;
 	c->bytes_plan = 0;
@@ -1366,6 +1394,8 @@ static void free_ctx(psmc_b200_ctx *c)
 		if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->ev_join) cudaEventDestroy(c->ev_join);
+	if (c->ev_k1f) cudaEventDestroy(c->ev_k1f);
+	if (c->ev_k1b) cudaEventDestroy(c->ev_k1b);
 	if (c->stream2) cudaStreamDestroy(c->stream2);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -1537,7 +1567,7 @@ static int replan(psmc_b200_ctx *c)
 			if (e_ != cudaSuccess) { set_err(PSMC_B200_ECUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e_)); *ptr = nullptr; ok = false; return; }
 			c->bytes_plan += (int64_t)bytes;
 		};
-		const size_t cm = (size_t)std::max(cc, cb), sm = (size_t)std::max(cs, csb);
+		const size_t cm = (size_t)std::max(cc, cb);
 		alloc((void **)&c->d_chunks, sizeof(Chunk) * (size_t)cc);
 		alloc((void **)&c->d_k1, sizeof(int32_t) * (size_t)ck);
 		alloc((void **)&c->d_T, sizeof(double) * (size_t)cc * NP * NP);
@@ -1560,8 +1590,14 @@ static int replan(psmc_b200_ctx *c)
 		alloc((void **)&c->d_sub, sizeof(Chunk) * (size_t)cs);
 		alloc((void **)&c->d_sub_parent, sizeof(int32_t) * (size_t)cs);
 		alloc((void **)&c->d_chunk_sub0, sizeof(int32_t) * (size_t)(cc + 1));
-		alloc((void **)&c->d_Tsub, sizeof(double) * sm * NP * NP);
-		alloc((void **)&c->d_Texsub, sizeof(int32_t) * sm * NP);
+		alloc((void **)&c->d_Tsub, sizeof(double) * (size_t)cs * NP * NP);
+		alloc((void **)&c->d_Texsub, sizeof(int32_t) * (size_t)cs * NP);
+		alloc((void **)&c->d_Tsub_b, sizeof(double) * (size_t)csb * NP * NP);
+		alloc((void **)&c->d_Texsub_b, sizeof(int32_t) * (size_t)csb * NP);
+		for (int q = 0; q < 2; ++q) {
+			alloc((void **)&c->d_pred[q], sizeof(int32_t) * (size_t)(cc + 2));
+			alloc((void **)&c->d_pred_b[q], sizeof(int32_t) * (size_t)(cb + 2));
+		}
 		alloc((void **)&c->d_vsub, sizeof(double) * (size_t)cs * NP);
 		alloc((void **)&c->d_bsub, sizeof(double) * (size_t)csb * NP);
 		alloc((void **)&c->d_llsub, sizeof(double) * (size_t)cs);
@@ -1586,6 +1622,10 @@ static int replan(psmc_b200_ctx *c)
 #undef UP
 	CUDA_TRY(cudaMemsetAsync(c->d_flag_b, 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaMemsetAsync(c->d_flag, 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), st), PSMC_B200_ECUDA);
+	for (int q = 0; q < 2; ++q) { // no prediction for a new plan
+		CUDA_TRY(cudaMemsetAsync(c->d_pred[q], 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), st), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMemsetAsync(c->d_pred_b[q], 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), st), PSMC_B200_ECUDA);
+	}
 	CUDA_TRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(st), PSMC_B200_ECUDA); // the host vectors above go out of scope
@@ -1638,8 +1678,6 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		env = getenv("PSMC_B200_G_BWD");
 		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bwd = atoi(env);
 		c->g_bww = 8; // measured on B200: the narrow warm-up kernel leaves the most issue slots to the concurrent forward kernel
-		env = getenv("PSMC_B200_K4_MINB");
-		if (env && atoi(env) >= 4) c->k4_minb = 4;
 		env = getenv("PSMC_B200_G_BWW");
 		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bww = atoi(env);
 	}
@@ -1669,6 +1707,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		if (c->warm_len < 0) c->warm_len = 0;
 		env = getenv("PSMC_B200_WARM_BWD");
 		c->warm_len_bwd = (env && atoi(env) > 0) ? atoi(env) : 2 * c->warm_len;
+		c->warm_bwd_fixed = (env && atoi(env) > 0);
 		env = getenv("PSMC_B200_WARM_HOT");
 		if (env && atoi(env) >= 0) c->warm_hot = atoi(env);
 		env = getenv("PSMC_B200_REPAIR_ROUNDS");
@@ -1726,6 +1765,12 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	CTRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 	CTRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CTRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+	CTRY(cudaEventCreateWithFlags(&c->ev_k1f, cudaEventDisableTiming));
+	CTRY(cudaEventCreateWithFlags(&c->ev_k1b, cudaEventDisableTiming));
+	{
+		const char *env = getenv("PSMC_B200_PREDICT");
+		if (env && atoi(env) == 0) c->predict = false;
+	}
 	for (int i = 0; i < 8; ++i) CTRY(cudaEventCreate(&c->ev[i]));
 	CTRY(cudaMallocHost((void **)&c->h_model, sizeof(double) * M_COUNT * NP));
 	CTRY(cudaMallocHost((void **)&c->h_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1)));
@@ -1860,11 +1905,11 @@ template <int NP>
 static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const double *bdir, int publish, double *bsave_next)
 {
 	cudaStream_t st = c->stream;
-#define BWD(G_, MB_) k_backward<NP / G_, G_, MB_><<<blocks_for(n, G_), 128, 0, st>>>(chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
-	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8, 1);
-	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16, 1);
-	else if (c->k4_minb >= 4) BWD(32, 4);
-	else BWD(32, 1);
+#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(n, G_), 128, 0, st>>>(chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
+	// (forcing 4 resident blocks per SM with __launch_bounds__(128, 4) was measured: the spills cost more than the occupancy gives)
+	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8);
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16);
+	else BWD(32);
 #undef BWD
 }
 template <int NP>
@@ -1893,16 +1938,13 @@ static void chunk_slots(const psmc_b200_ctx *c, int *slots_fwd, int *slots_bwd)
 {
 	int bf = 1, bb = 1, gf = 32, gb = 32;
 #define OCC(K_, G_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, K_<NP / G_, G_>, 128, 0)
-#define OCCB(G_, MB_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, k_backward<NP / G_, G_, MB_>, 128, 0)
 	if (c->g_fwd == 8 && NP / 8 <= 8) { gf = 8; OCC(k_forward, 8, bf); }
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) { gf = 16; OCC(k_forward, 16, bf); }
 	else OCC(k_forward, 32, bf);
-	if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCCB(8, 1, bb); }
-	else if (c->g_bwd <= 16 && NP / 16 <= 4) { gb = 16; OCCB(16, 1, bb); }
-	else if (c->k4_minb >= 4) OCCB(32, 4, bb);
-	else OCCB(32, 1, bb);
+	if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCC(k_backward, 8, bb); }
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) { gb = 16; OCC(k_backward, 16, bb); }
+	else OCC(k_backward, 32, bb);
 #undef OCC
-#undef OCCB
 	*slots_fwd = bf * 4 * (32 / gf);
 	*slots_bwd = bb * 4 * (32 / gb);
 }
@@ -1917,7 +1959,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	if (c->n_k1 > 0) {
 		constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 		dim3 grid((unsigned)c->n_k1, NP / COLS);
-		k_transfer<SPL1, G1, COLS><<<grid, COLS * G1, 0, st>>>(c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0);
+		k_transfer<SPL1, G1, COLS><<<grid, COLS * G1, 0, st>>>(c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[1], st);
@@ -1965,14 +2007,29 @@ static int launch_warm(psmc_b200_ctx *c)
 	// the backward warm-up needs only observations + model: run it on the side stream, concurrently with the forward pass
 	cudaEventRecord(c->ev_fork, st);
 	cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
-	run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : c->warm_len_bwd, hot);
+	// the backward warm-up hides behind the forward kernel (warm_len + chunk_len steps per chunk): on small shards
+	// (multi-GPU) a longer one would become the critical path, so it is capped at the forward kernel's length
+	const int wl_b = (c->warm_bwd_fixed || c->warm_len_bwd <= c->warm_len + c->chunk_len) ? c->warm_len_bwd : std::max(c->warm_len, c->warm_len + c->chunk_len);
+	run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : wl_b, hot);
 	cudaEventRecord(c->ev_join, c->stream2);
 	run_forward<NP>(c, wl, hot);
 	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 	const dim3 gridT((unsigned)c->n_sub, NP / COLS);
+	const int nblk_b = (c->n_chunks_b + wpb - 1) / wpb;
+	const dim3 gridTb((unsigned)c->n_sub_b, NP / COLS);
+	// operators of the chunks that failed in the previous E-step, ahead of time on the side stream (behind the backward warm-up)
+	const int32_t *pred = c->predict ? c->d_pred[c->pred_cur] + 1 : nullptr, *pred_b = c->predict ? c->d_pred_b[c->pred_cur] + 1 : nullptr;
+	int32_t *pred_next = c->d_pred[c->pred_cur ^ 1] + 1, *pred_next_b = c->d_pred_b[c->pred_cur ^ 1] + 1;
+	if (c->predict) {
+		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, c->stream2>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr);
+		cudaEventRecord(c->ev_k1f, c->stream2);
+		k_transfer<SPL1, G1, COLS><<<gridTb, COLS * G1, 0, c->stream2>>>(c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr);
+		cudaEventRecord(c->ev_k1b, c->stream2);
+		cudaStreamWaitEvent(st, c->ev_k1f, 0);
+	}
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		k_mark_fwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4);
-		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3);
+		k_mark_fwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr);
+		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr);
 		k_chain_subs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_forward_repair<NP>(c);
 		k_fold<<<c->n_chunks, 128, 0, st>>>(c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
@@ -1981,12 +2038,11 @@ static int launch_warm(psmc_b200_ctx *c)
 	cudaStreamWaitEvent(st, c->ev_join, 0);
 	run_backward<NP>(c, c->d_chunks_b, c->n_chunks_b, c->d_bwarm, 1, c->d_bsave[c->bsave_cur ^ 1]);
 	c->bsave_cur ^= 1;
-	const int nblk_b = (c->n_chunks_b + wpb - 1) / wpb;
-	const dim3 gridTb((unsigned)c->n_sub_b, NP / COLS);
+	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		k_mark_bwd<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4);
-		k_transfer<SPL1, G1, COLS><<<gridTb, COLS * G1, 0, st>>>(c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag_b + 1, 3);
-		k_chain_subs<NP><<<c->n_chunks_b, NP, 0, st>>>(c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
+		k_mark_bwd<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr);
+		k_transfer<SPL1, G1, COLS><<<gridTb, COLS * G1, 0, st>>>(c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr);
+		k_chain_subs<NP><<<c->n_chunks_b, NP, 0, st>>>(c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
 		k_fold<<<c->n_chunks_b, 128, 0, st>>>(c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
@@ -1995,7 +2051,8 @@ static int launch_warm(psmc_b200_ctx *c)
 	k_certify<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
 	k_certify<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 6 + 10 * c->repair_rounds;
+	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0);
+	c->pred_cur ^= 1;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 	c->fwd_valid = false; // bend[] is not filled in this mode; decode runs its own forward pass
