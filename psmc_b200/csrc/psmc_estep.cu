@@ -32,7 +32,9 @@
 //
 // All arithmetic is FP64.  No tensor cores: there is no dense contraction on this path.
 
+#ifndef PSMC_SIMT_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -47,6 +49,25 @@
 #include "psmc_b200.h"
 
 #define FULLMASK 0xffffffffu
+
+// Every kernel launch goes through LAUNCH so that tests/emu can compile this very file for the host (a SIMT emulation
+// used by the CPU test-suite only: it runs the kernels' source with one host thread per CUDA thread; never shipped).
+#define PSMC_UNPAREN(...) __VA_ARGS__
+#ifndef PSMC_SIMT_EMU
+#define LAUNCH(kern, grid, block, stream, ...)                        \
+	do {                                                              \
+		auto kfn_ = PSMC_UNPAREN kern;                                \
+		kfn_<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);          \
+	} while (0)
+#define PIN_REG(x) asm volatile("" : "+d"(x))
+#else
+#define LAUNCH(kern, grid, block, stream, ...)                        \
+	do {                                                              \
+		auto kfn_ = PSMC_UNPAREN kern;                                \
+		simt_emu::launch((grid), (block), [&]() { kfn_(__VA_ARGS__); }); \
+	} while (0)
+#define PIN_REG(x) ((void)(x))
+#endif
 #define HMM_TINY_ 1e-25 /* khmm.h:28 */
 
 // ------------------------------------------------------------------------------------------------
@@ -115,8 +136,8 @@ struct ScanMasks {
 	{
 #pragma unroll
 		for (int k = 0; k < STEPS; ++k) {
-			asm volatile("" : "+d"(up[k]));
-			asm volatile("" : "+d"(dn[k]));
+			PIN_REG(up[k]);
+			PIN_REG(dn[k]);
 		}
 	}
 };
@@ -150,7 +171,11 @@ __device__ __forceinline__ double gsum(double t) // all-reduce over the lanes of
 __device__ __forceinline__ double fast_rcp(double s)
 {
 	double r;
+#ifndef PSMC_SIMT_EMU
 	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+#else
+	r = simt_emu::rcp_seed(s);
+#endif
 	double e = fma(-s, r, 1.0);
 	r = fma(r, e, r);
 	e = fma(-s, r, 1.0);
@@ -1885,7 +1910,7 @@ template <int NP>
 static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
-#define FWD(G_) k_forward<NP / G_, G_><<<blocks_for(c->n_chunks, G_), 128, 0, st>>>(c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
+#define FWD(G_) LAUNCH((k_forward<NP / G_, G_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
 	if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8);
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWD(16);
 	else FWD(32);
@@ -1895,7 +1920,7 @@ template <int NP>
 static void run_forward_repair(psmc_b200_ctx *c)
 {
 	cudaStream_t st = c->stream;
-#define FWR(G_) k_forward_repair<NP / G_, G_><<<blocks_for(c->n_sub, G_), 128, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4)
+#define FWR(G_) LAUNCH((k_forward_repair<NP / G_, G_>), blocks_for(c->n_sub, G_), 128, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4)
 	if (c->g_fwd == 8 && NP / 8 <= 8) FWR(8);
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWR(16);
 	else FWR(32);
@@ -1905,7 +1930,7 @@ template <int NP>
 static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const double *bdir, int publish, double *bsave_next)
 {
 	cudaStream_t st = c->stream;
-#define BWD(G_) k_backward<NP / G_, G_><<<blocks_for(n, G_), 128, 0, st>>>(chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
+#define BWD(G_) LAUNCH((k_backward<NP / G_, G_>), blocks_for(n, G_), 128, st, chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
 	// (forcing 4 resident blocks per SM with __launch_bounds__(128, 4) was measured: the spills cost more than the occupancy gives)
 	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8);
 	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16);
@@ -1915,7 +1940,7 @@ static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const dou
 template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
-#define BWW(G_) k_backward_warm<NP / G_, G_><<<blocks_for(c->n_chunks_b, G_), 128, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
+#define BWW(G_) LAUNCH((k_backward_warm<NP / G_, G_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
 	if (c->g_bww == 8 && NP / 8 <= 8) BWW(8);
 	else if (c->g_bww <= 16 && NP / 16 <= 8) BWW(16);
 	else BWW(32);
@@ -1925,7 +1950,7 @@ template <int NP>
 static void run_backward_repair(psmc_b200_ctx *c)
 {
 	cudaStream_t st = c->stream;
-#define BWR(G_) k_backward_repair<NP / G_, G_><<<blocks_for(c->n_sub_b, G_), 128, 0, st>>>(c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
+#define BWR(G_) LAUNCH((k_backward_repair<NP / G_, G_>), blocks_for(c->n_sub_b, G_), 128, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
 	if (c->g_bwd == 8 && NP / 8 <= 4) BWR(8);
 	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWR(16);
 	else BWR(32);
@@ -1959,12 +1984,12 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	if (c->n_k1 > 0) {
 		constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 		dim3 grid((unsigned)c->n_k1, NP / COLS);
-		k_transfer<SPL1, G1, COLS><<<grid, COLS * G1, 0, st>>>(c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), grid, COLS * G1, st, c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[1], st);
 	if (c->n_k1 > 0) {
-		k_chain<NP><<<2 * c->n_seqs, NP, 0, st>>>(c->d_seq_c0, c->d_seq_nc, c->d_T, c->d_Tex, c->d_model, c->d_vstart, c->d_bend, c->n_seqs);
+		LAUNCH((k_chain<NP>), 2 * c->n_seqs, NP, st, c->d_seq_c0, c->d_seq_nc, c->d_T, c->d_Tex, c->d_model, c->d_vstart, c->d_bend, c->n_seqs);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[2], st);
@@ -1979,7 +2004,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 			++c->launches;
 		}
 		cudaEventRecord(c->ev[4], st);
-		k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw : nullptr);
+		LAUNCH((k_reduce), 1 + S_COUNT * c->N, 256, st, c->d_part, c->d_llpart, c->n_chunks, c->n_chunks, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw : nullptr);
 		++c->launches;
 		cudaEventRecord(c->ev[5], st);
 	}
@@ -2021,18 +2046,18 @@ static int launch_warm(psmc_b200_ctx *c)
 	const int32_t *pred = c->predict ? c->d_pred[c->pred_cur] + 1 : nullptr, *pred_b = c->predict ? c->d_pred_b[c->pred_cur] + 1 : nullptr;
 	int32_t *pred_next = c->d_pred[c->pred_cur ^ 1] + 1, *pred_next_b = c->d_pred_b[c->pred_cur ^ 1] + 1;
 	if (c->predict) {
-		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, c->stream2>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, c->stream2, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr);
 		cudaEventRecord(c->ev_k1f, c->stream2);
-		k_transfer<SPL1, G1, COLS><<<gridTb, COLS * G1, 0, c->stream2>>>(c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr);
 		cudaEventRecord(c->ev_k1b, c->stream2);
 		cudaStreamWaitEvent(st, c->ev_k1f, 0);
 	}
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		k_mark_fwd<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr);
-		k_transfer<SPL1, G1, COLS><<<gridT, COLS * G1, 0, st>>>(c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr);
-		k_chain_subs<NP><<<c->n_chunks, NP, 0, st>>>(c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
+		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr);
+		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_forward_repair<NP>(c);
-		k_fold<<<c->n_chunks, 128, 0, st>>>(c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
+		LAUNCH((k_fold), c->n_chunks, 128, st, c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[3], st);
 	cudaStreamWaitEvent(st, c->ev_join, 0);
@@ -2040,16 +2065,16 @@ static int launch_warm(psmc_b200_ctx *c)
 	c->bsave_cur ^= 1;
 	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		k_mark_bwd<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr);
-		k_transfer<SPL1, G1, COLS><<<gridTb, COLS * G1, 0, st>>>(c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr);
-		k_chain_subs<NP><<<c->n_chunks_b, NP, 0, st>>>(c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
+		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr);
+		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
-		k_fold<<<c->n_chunks_b, 128, 0, st>>>(c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
+		LAUNCH((k_fold), c->n_chunks_b, 128, st, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[4], st);
-	k_reduce<<<1 + S_COUNT * c->N, 256, 0, st>>>(c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
-	k_certify<SPL><<<nblk, wpb * 32, 0, st>>>(c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
-	k_certify<SPL><<<nblk_b, wpb * 32, 0, st>>>(c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
+	LAUNCH((k_reduce), 1 + S_COUNT * c->N, 256, st, c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
+	LAUNCH((k_certify<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
+	LAUNCH((k_certify<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
 	cudaEventRecord(c->ev[5], st);
 	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0);
 	c->pred_cur ^= 1;
@@ -2293,9 +2318,9 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
 	const double *fh = c->d_fhat;
 	const double *scp = c->d_sc;
 	switch (c->SPL) {
-	case 1: k_decode<1><<<nblk, wpb * 32, 0, c->stream>>>(c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
-	case 2: k_decode<2><<<nblk, wpb * 32, 0, c->stream>>>(c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
-	case 4: k_decode<4><<<nblk, wpb * 32, 0, c->stream>>>(c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
+	case 1: LAUNCH((k_decode<1>), nblk, wpb * 32, c->stream, c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
+	case 2: LAUNCH((k_decode<2>), nblk, wpb * 32, c->stream, c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
+	case 4: LAUNCH((k_decode<4>), nblk, wpb * 32, c->stream, c->d_chunks, c0, nc, c->d_obs, c->d_model, c->d_bend, fh, scp, c->N, c->d_bestk, c->d_bestp, post ? c->d_post : nullptr, p_recomb ? c->d_prec : nullptr); break;
 	}
 	++c->launches;
 	CUDA_TRY(cudaGetLastError(), PSMC_B200_ECUDA);
