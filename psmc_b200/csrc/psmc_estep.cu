@@ -287,6 +287,172 @@ __device__ __forceinline__ Chunk uniform_chunk(Chunk ch)
 __device__ __forceinline__ int exponent_of(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
 __device__ __forceinline__ double pow2i(int k) { return __hiloint2double((1023 + k) << 20, 0); } // |k| < 1022
 
+// ================================================================================================
+// Second-generation lane-group primitives (the chunk kernels are bound by the LATENCY of the per-bin dependency
+// chain at one or two warps per scheduler, not by issue slots or bandwidth; measured with ncu on B200):
+//   * DualScan<G>: exclusive prefix of one value AND exclusive suffix of another over the G lanes of a group in ONE
+//     (G = 8) or TWO (G = 16) shuffle rounds instead of 1 + log2 G Kogge-Stone rounds.  With xor-partners, the lane
+//     pair (l, l ^ m) needs exactly one value from each other: the lower lane's prefix term goes up, the upper lane's
+//     suffix term goes down, so one 64-bit shuffle serves both scans.
+//   * local prefix/suffix sums as trees, and everything that does not depend on the shuffled values moved in front
+//     of them: after the shuffles a state costs two FMAs.
+// ================================================================================================
+template <int G>
+struct DualScan;
+
+template <>
+struct DualScan<8> {
+	bool h0, h1, h2;
+	double u0, u1, u2, d0, d1, d2; // u_b = 1 iff bit b of my lane is set: the partners that differ first in bit b are BELOW me
+	__device__ __forceinline__ void init(int gl)
+	{
+		h0 = (gl & 1) != 0; h1 = (gl & 2) != 0; h2 = (gl & 4) != 0;
+		u0 = h0 ? 1.0 : 0.0; u1 = h1 ? 1.0 : 0.0; u2 = h2 ? 1.0 : 0.0;
+		d0 = 1.0 - u0; d1 = 1.0 - u1; d2 = 1.0 - u2;
+		PIN_REG(u0); PIN_REG(u1); PIN_REG(u2); PIN_REG(d0); PIN_REG(d1); PIN_REG(d2);
+	}
+	// P = sum_{j<gl} tp_j,  S = sum_{j>gl} ts_j
+	__device__ __forceinline__ void run(double tp, double ts, double &P, double &S) const
+	{
+		// a partner above me needs my prefix term and sends its suffix term; a partner below me the other way round
+		const double s0 = h0 ? ts : tp, s1 = h1 ? ts : tp, s2 = h2 ? ts : tp;
+		const double r1 = __shfl_xor_sync(FULLMASK, s0, 1, 8);
+		const double r2 = __shfl_xor_sync(FULLMASK, s1, 2, 8), r3 = __shfl_xor_sync(FULLMASK, s1, 3, 8);
+		const double r4 = __shfl_xor_sync(FULLMASK, s2, 4, 8), r5 = __shfl_xor_sync(FULLMASK, s2, 5, 8);
+		const double r6 = __shfl_xor_sync(FULLMASK, s2, 6, 8), r7 = __shfl_xor_sync(FULLMASK, s2, 7, 8);
+		const double q1 = r2 + r3, q2 = (r4 + r5) + (r6 + r7);
+		P = fma(u2, q2, fma(u1, q1, u0 * r1));
+		S = fma(d2, q2, fma(d1, q1, d0 * r1));
+	}
+};
+
+template <>
+struct DualScan<16> {
+	bool h2, h3;
+	double u0, u1, u2, u3, d0, d1, d2, d3;
+	__device__ __forceinline__ void init(int gl)
+	{
+		h2 = (gl & 4) != 0; h3 = (gl & 8) != 0;
+		u0 = (gl & 1) ? 1.0 : 0.0; u1 = (gl & 2) ? 1.0 : 0.0; u2 = h2 ? 1.0 : 0.0; u3 = h3 ? 1.0 : 0.0;
+		d0 = 1.0 - u0; d1 = 1.0 - u1; d2 = 1.0 - u2; d3 = 1.0 - u3;
+		PIN_REG(u0); PIN_REG(u1); PIN_REG(u2); PIN_REG(u3); PIN_REG(d0); PIN_REG(d1); PIN_REG(d2); PIN_REG(d3);
+	}
+	__device__ __forceinline__ void run(double tp, double ts, double &P, double &S) const
+	{
+		// round 1, inside quads of lanes: both terms travel, because the quad totals are needed as well
+		const double p1 = __shfl_xor_sync(FULLMASK, tp, 1, 16), s1 = __shfl_xor_sync(FULLMASK, ts, 1, 16);
+		const double p2 = __shfl_xor_sync(FULLMASK, tp, 2, 16), s2 = __shfl_xor_sync(FULLMASK, ts, 2, 16);
+		const double p3 = __shfl_xor_sync(FULLMASK, tp, 3, 16), s3 = __shfl_xor_sync(FULLMASK, ts, 3, 16);
+		const double qp = p2 + p3, qs = s2 + s3;
+		const double Pq = fma(u1, qp, u0 * p1), Sq = fma(d1, qs, d0 * s1);
+		const double Tp = (tp + p1) + qp, Ts = (ts + s1) + qs;
+		// round 2, between quads: one value per partner quad, as in DualScan<8>
+		const double t2 = h2 ? Ts : Tp, t3 = h3 ? Ts : Tp;
+		const double r4 = __shfl_xor_sync(FULLMASK, t2, 4, 16);
+		const double r8 = __shfl_xor_sync(FULLMASK, t3, 8, 16), r12 = __shfl_xor_sync(FULLMASK, t3, 12, 16);
+		const double q3 = r8 + r12;
+		P = fma(u3, q3, fma(u2, r4, Pq));
+		S = fma(d3, q3, fma(d2, r4, Sq));
+	}
+};
+
+// exclusive prefix sums of a[0..SPL) inside a lane (lp[i] = a[0] + .. + a[i-1]) and the total, as a tree: the total
+// is log2 SPL additions deep
+template <int SPL>
+__device__ __forceinline__ void local_prefix(const double (&a)[SPL], double (&lp)[SPL], double &tot)
+{
+	if (SPL == 1) {
+		lp[0] = 0.0;
+		tot = a[0];
+	} else if (SPL == 2) {
+		lp[0] = 0.0;
+		lp[1] = a[0];
+		tot = a[0] + a[1];
+	} else if (SPL == 4) {
+		const double p01 = a[0] + a[1], p23 = a[2] + a[3];
+		lp[0] = 0.0; lp[1] = a[0]; lp[2] = p01; lp[3] = p01 + a[2];
+		tot = p01 + p23;
+	} else if (SPL == 8) {
+		const double p01 = a[0] + a[1], p23 = a[2] + a[3], p45 = a[4] + a[5], p67 = a[6] + a[7];
+		const double q03 = p01 + p23, q47 = p45 + p67, q05 = q03 + p45;
+		lp[0] = 0.0; lp[1] = a[0]; lp[2] = p01; lp[3] = p01 + a[2];
+		lp[4] = q03; lp[5] = q03 + a[4]; lp[6] = q05; lp[7] = q05 + a[6];
+		tot = q03 + q47;
+	} else {
+		double t = 0.0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			lp[i] = t;
+			t += a[i];
+		}
+		tot = t;
+	}
+}
+template <int SPL>
+__device__ __forceinline__ void local_suffix(const double (&c)[SPL], double (&ls)[SPL], double &tot)
+{
+	double r[SPL], lr[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) r[i] = c[SPL - 1 - i];
+	local_prefix<SPL>(r, lr, tot);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) ls[i] = lr[SPL - 1 - i];
+}
+template <int SPL>
+__device__ __forceinline__ double local_sum(const double (&a)[SPL])
+{
+	if (SPL == 4) return (a[0] + a[1]) + (a[2] + a[3]);
+	if (SPL == 8) return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+	double t = 0.0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) t += a[i];
+	return t;
+}
+
+// out[i] = D[i] x[i] + pc[i] * sum_{j<i} pm[j] x[j] + sc[i] * sum_{j>i} sm[j] x[j]  (same contract as semisep)
+template <int SPL, int G>
+__device__ __forceinline__ void semisep2(const double (&x)[SPL], const double (&pm)[SPL], const double (&pc)[SPL],
+                                         const double (&sm)[SPL], const double (&sc)[SPL], const double (&D)[SPL],
+                                         const DualScan<G> &ds, double (&out)[SPL])
+{
+	double a[SPL], c[SPL], lp[SPL], ls[SPL], tp, ts, P, S;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		a[i] = x[i] * pm[i];
+		c[i] = x[i] * sm[i];
+	}
+	local_prefix<SPL>(a, lp, tp);
+	local_suffix<SPL>(c, ls, ts);
+	ds.run(tp, ts, P, S);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		double base = D[i] * x[i]; // independent of the shuffles (lp[0] and ls[SPL-1] are zero)
+		if (i > 0) base = fma(pc[i], lp[i], base);
+		if (i < SPL - 1) base = fma(sc[i], ls[i], base);
+		out[i] = fma(sc[i], S, fma(pc[i], P, base));
+	}
+}
+// full exclusive prefix P[i] = sum_{j<i} pm[j] x[j] and suffix S[i] = sum_{j>i} sm[j] x[j] (same contract as prefsuf)
+template <int SPL, int G>
+__device__ __forceinline__ void prefsuf2(const double (&x)[SPL], const double (&pm)[SPL], const double (&sm)[SPL],
+                                         const DualScan<G> &ds, double (&P)[SPL], double (&S)[SPL])
+{
+	double a[SPL], c[SPL], lp[SPL], ls[SPL], tp, ts, p, s;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		a[i] = x[i] * pm[i];
+		c[i] = x[i] * sm[i];
+	}
+	local_prefix<SPL>(a, lp, tp);
+	local_suffix<SPL>(c, ls, ts);
+	ds.run(tp, ts, p, s);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		P[i] = p + lp[i];
+		S[i] = s + ls[i];
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: transfer operators.  grid = (n_k1_chunks, NP / COLS), block = COLS * G threads; the lane group
 // of column j pushes the unit vector e_j through every bin of the chunk.
@@ -324,8 +490,8 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
 	int ex = 0;
 	const int uend = ch.u0 + ch.len;
 	uint32_t word = 0;
-	ScanMasks<G> mk;
-	mk.init(gl);
+	DualScan<G> ds;
+	ds.init(gl);
 	for (int u = ch.u0; u < uend; ++u) {
 		if (u == ch.u0 || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
 		const int x = (word >> ((u & 15) * 2)) & 3;
@@ -334,7 +500,7 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) out[i] = f[i];
 		} else {
-			semisep<SPL, G>(f, cW, cZ, cU, cV, cD, mk, out);
+			semisep2<SPL, G>(f, cW, cZ, cU, cV, cD, ds, out);
 		}
 		if (x == 0) {
 #pragma unroll
@@ -691,13 +857,193 @@ __device__ __forceinline__ double forward_chunk(const Chunk &ch, bool valid, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Second-generation forward over a chunk (same contract as forward_chunk).  Differences, all about latency:
+//   * the recursion carries an UNNORMALISED vector g_u = q_u * diag(e_{x_u}) A^T g_{u-1}; q_u is 1 or an exact power
+//     of two that is switched on when the sum has dropped below 2^-200 -- nothing on the per-bin dependency chain
+//     depends on a reduction any more.  With S_u = sum(g_u): s_u = S_u / (q_u S_{u-1}) (the reference's scale factor,
+//     khmm.c:183-184), f_u = g_u / S_u, and sum_u log s_u telescopes to log S_last - log S_before - log2(prod q) ln 2.
+//   * during the warm-up overlap nothing else is computed; in the store phase the reduction, the reciprocal and the
+//     stores of bin u-1 are issued together with the scan of bin u (software pipelining by one bin), so that their
+//     shuffle latency hides behind the scan's.
+//   * the lane groups of a warp are aligned at the END of their chunks, so that all of them are in the same phase.
+// ------------------------------------------------------------------------------------------------
+#ifndef PSMC_BOOST_BITS
+#define PSMC_BOOST_BITS 200 /* the emulation tests also build with a small value so that boosts happen every few bins */
+#endif
+#define PSMC_BOOST_LOW pow2i(-PSMC_BOOST_BITS)
+#define PSMC_BOOST_UP pow2i(PSMC_BOOST_BITS)
+__device__ __forceinline__ int warp_min_i(int n)
+{
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) n = min(n, __shfl_xor_sync(FULLMASK, n, d));
+	return n;
+}
+template <int SPL, int G>
+struct ForwardRun {
+	static constexpr int NP = SPL * G;
+	const Chunk &ch;
+	const LaneModel<SPL> &M;
+	const bool valid;
+	const int gl, s0, u0, uend;
+	const uint32_t *__restrict__ obs;
+	double *__restrict__ fhat, *__restrict__ sc, *__restrict__ fwarm_c;
+	DualScan<G> ds;
+	double g[SPL], ps, inv_prev, qc, rq_cur, Sstart;
+	int kq, ubase, ubeg, wlast, tpend, mystart;
+	bool warmed;
+	uint32_t word, wnext;
+
+	__device__ __forceinline__ ForwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_,
+	                                      const uint32_t *__restrict__ obs_, double *__restrict__ fhat_, double *__restrict__ sc_,
+	                                      double *__restrict__ fwarm_c_)
+	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), u0(ch_.u0), uend(ch_.u0 + ch_.len), obs(obs_),
+	      fhat(fhat_), sc(sc_), fwarm_c(fwarm_c_)
+	{
+	}
+
+	// A group whose chunk needs fewer steps than the longest one of its warp starts late: until then it computes on
+	// whatever its registers hold (no per-step select keeps it idle) and picks up its real start vector here.
+	__device__ __forceinline__ void start_if_due(int t, const double (&f)[SPL], double inv_before)
+	{
+		if (t == tpend) { // warp-uniform, rare
+			if (mystart == t) {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) g[i] = f[i];
+				ps = local_sum<SPL>(g);
+				inv_prev = inv_before;
+				rq_cur = 1.0;
+				qc = 1.0;
+			}
+			tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
+		}
+	}
+
+	// bin u = ubase + t is formed from the current vector (bin u-1); BOOK: finish bin u-1 (sum, reciprocal, stores) alongside
+	template <bool BOOK>
+	__device__ __forceinline__ void step(int t)
+	{
+		const int u = ubase + t;
+		if (valid && u > ubeg && (u & 15) == 0) {
+			word = wnext;
+			wnext = __ldg(obs + ch.ow0 + min((u >> 4) + 1, wlast));
+		}
+		const int x = (word >> ((u & 15) * 2)) & 3;
+		double inv1 = inv_prev, qn = 1.0;
+		if (BOOK) {
+			const double S1 = gsum<G>(ps); // = S_{u-1}
+			inv1 = fast_rcp(S1);
+			const bool st_f = valid && u - 1 >= u0;               // (implies that the group has started)
+			const bool st_w = valid && u == u0 && warmed && fwarm_c != nullptr;
+			if (st_f || st_w) {
+				double fn[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) fn[i] = g[i] * inv1;
+				store_vec<SPL>(st_f ? fhat + ((size_t)ch.gb0 + (u - 1 - u0)) * NP + s0 : fwarm_c + s0, fn);
+			}
+			if (st_f && gl == 0) sc[ch.gb0 + (u - 1 - u0)] = S1 * inv_prev * rq_cur;
+			if (u == u0 && u >= ubeg) Sstart = S1;             // (u >= ubeg: the group has started)
+			qn = (S1 < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+		} else if ((t & 15) == 0) {
+			qn = (gsum<G>(ps) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+		}
+		double c0, c1;
+		emis_coef(x, c0, c1);
+		c0 *= qc;
+		c1 *= qc;
+		double out[SPL];
+		semisep2<SPL, G>(g, M.W, M.Z, M.U, M.V, M.D, ds, out);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = out[i] * fma(c1, M.e0[i], c0);
+		ps = local_sum<SPL>(g);
+		inv_prev = inv1;
+		const bool boosted = qc != 1.0;
+		rq_cur = boosted ? PSMC_BOOST_LOW : 1.0;
+		if (boosted && u >= u0 && u >= ubeg) kq += PSMC_BOOST_BITS;
+		qc = qn;
+	}
+
+	__device__ __forceinline__ double run(int ubeg_in, double (&f)[SPL])
+	{
+		ubeg = ubeg_in;
+		warmed = ubeg_in < u0;
+		wlast = (ch.Lseq - 1) >> 4;
+		ds.init(gl);
+		Sstart = 1.0;
+		kq = 0;
+		double inv_before = 1.0; // 1 / S of the bin before the start vector's bin (only the first bin of a sequence needs it)
+		const double S_init = gsum<G>(local_sum<SPL>(f)); // (every lane of the warp takes part)
+		if (ubeg_in == 0) {
+			// first bin of a sequence: emission only, no transition (khmm.c:171-174); f is a0 here.  Done in front of the loop
+			// so that the loop body has no special case: the start vector becomes bin 0 (unnormalised) and bin 1 is formed first.
+			const int x = __ldg(obs + ch.ow0) & 3;
+			double c0, c1;
+			emis_coef(x, c0, c1);
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] *= fma(c1, M.e0[i], c0);
+			inv_before = fast_rcp(S_init);
+			if (u0 == 0) Sstart = S_init;
+			ubeg = 1;
+		}
+		// from here on: f = vector of bin ubeg-1, the group forms bins ubeg .. uend-1 and is aligned with the other groups at the END
+		const int mytrips = valid ? uend - ubeg : 0;
+		const int trips = warp_trips(mytrips);
+		const int tB = warp_min_i(valid ? trips - (uend - max(u0, ubeg)) : trips); // first step in which some group forms a bin it stores
+		ubase = uend - trips;
+		mystart = valid ? trips - mytrips : INT_MAX;
+		word = __ldg(obs + ch.ow0 + (ubeg >> 4));
+		wnext = __ldg(obs + ch.ow0 + min((ubeg >> 4) + 1, wlast));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = f[i];
+		ps = local_sum<SPL>(g);
+		inv_prev = inv_before;
+		rq_cur = 1.0;
+		qc = 1.0;
+		tpend = warp_min_i(mystart);
+		int t = 0;
+		for (; t < tB; ++t) {
+			start_if_due(t, f, inv_before);
+			step<false>(t);
+		}
+		for (; t < trips; ++t) {
+			start_if_due(t, f, inv_before);
+			step<true>(t);
+		}
+		if (mytrips == 0) { // nothing formed in the loop (a one-bin chunk at the start of a sequence): the start vector is the last bin
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) g[i] = f[i];
+			ps = local_sum<SPL>(g);
+			inv_prev = inv_before;
+			rq_cur = 1.0;
+		}
+		// finish the last bin
+		const double S1 = gsum<G>(ps), inv1 = fast_rcp(S1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) f[i] = g[i] * inv1;
+		if (valid) {
+			store_vec<SPL>(fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + s0, f);
+			if (gl == 0) sc[ch.gb0 + (ch.len - 1)] = S1 * inv_prev * rq_cur;
+		}
+		return (log(S1) - log(Sstart)) - (double)kq * 0.69314718055994530942;
+	}
+};
+
+template <int SPL, int G>
+__device__ __forceinline__ double forward_chunk2(const Chunk &ch, bool valid, int ubeg, const LaneModel<SPL> &M, double (&f)[SPL],
+                                                 int gl, const uint32_t *__restrict__ obs, double *__restrict__ fhat,
+                                                 double *__restrict__ sc, double *__restrict__ fwarm_c)
+{
+	ForwardRun<SPL, G> r(ch, valid, M, gl, obs, fhat, sc, fwarm_c);
+	return r.run(ubeg, f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: forward.  One lane group per chunk.
 //   warm == 0 : the exact start vector comes from the boundary chain (vstart, transfer mode).
 //   warm  > 0 : the group starts `warm` bins to the LEFT of its chunk from the stationary vector, runs
 //               the same recursion without storing (the HMM forgets its start geometrically) and saves
 //               the vector it reached at the bin before its chunk (fwarm[c]) for the certificate.
 // ------------------------------------------------------------------------------------------------
-template <int SPL, int G>
+template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                  const double *__restrict__ vstart, int warm, int use_prev, double *__restrict__ fhat,
@@ -727,7 +1073,9 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	} else {
 		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
 	}
-	const double ll = forward_chunk<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
+	double ll;
+	if constexpr (VER == 2) ll = forward_chunk2<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
+	else ll = forward_chunk<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	if (gl == 0 && id.valid) llpart[c] = ll;
 }
 
@@ -772,7 +1120,7 @@ __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chun
 	}
 }
 
-template <int SPL, int G>
+template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
                                                         const int32_t *__restrict__ chunk_sub0,
                                                         const uint32_t *__restrict__ obs, const double *__restrict__ model,
@@ -793,7 +1141,9 @@ __global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict_
 	double f[SPL];
 	load_vec<SPL>(vsub + (size_t)s * NP + s0, f);                                              // exact vector of the bin before the sub-chunk (k_chain_subs)
 	if (valid && chunk_sub0[pc] == s) store_vec<SPL>(fwarm + (size_t)pc * NP + s0, f);        // the chunk boundary agrees by construction from now on
-	const double ll = forward_chunk<SPL, G>(ch, valid, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
+	double ll;
+	if constexpr (VER == 2) ll = forward_chunk2<SPL, G>(ch, valid, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
+	else ll = forward_chunk<SPL, G>(ch, valid, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
 	if (gl == 0 && valid) {
 		llsub[s] = ll;
 		atomicAdd(&stat[1], 1ull);
@@ -913,6 +1263,143 @@ __device__ __forceinline__ void backward_chunk(const Chunk &ch, bool valid, cons
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second-generation backward over a chunk (same contract as backward_chunk, except for which chunk owns which
+// emission count: gamma_{u-1} = f_{u-1} (A diag(e_{x_u}) b_u) is accumulated with the TRANSITION u-1 -> u, which the
+// chunk of bin u owns -- this covers bins 0..L-2 exactly once, as khmm.c:310-318 does, and needs neither f_u nor s_u).
+// The f rows come from a ring of PF prefetched rows with static slots (the loop is unrolled PF times), the four scans
+// of a bin are two DualScans, and the scans of f_{u-1} do not depend on b, so they overlap the chain through b.
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G>
+struct BackwardRun {
+	static constexpr int NP = SPL * G, PF = 4;
+	const Chunk &ch;
+	const LaneModel<SPL> &M;
+	const bool valid;
+	const int gl, s0, ulast;
+	const uint32_t *__restrict__ obs;
+	const double *__restrict__ frow, *__restrict__ srow; // row of bin ulast
+	double *__restrict__ bsave_c;
+	const int usave;
+	DualScan<G> ds;
+	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
+	double nf[PF][SPL], ns[PF];
+	uint32_t word, wprev;
+	int xu;
+
+	__device__ __forceinline__ BackwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_, const uint32_t *__restrict__ obs_,
+	                                       const double *__restrict__ fhat, const double *__restrict__ sc, double *__restrict__ bsave_c_, int usave_)
+	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), ulast(ch_.u0 + ch_.len - 1), obs(obs_),
+	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_), usave(usave_)
+	{
+	}
+
+	template <int J>
+	__device__ __forceinline__ void step(int t, double (&b)[SPL])
+	{
+		const int u = ulast - t;
+		const bool act = valid && u >= ch.u0;
+		const bool trans = act && u > 0; // no transition into the first bin of a sequence
+		if (act && u == usave && bsave_c) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
+		// row u-1 from the ring, then refill the slot with row u-1-PF
+		double fm[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) fm[i] = nf[J][i];
+		const double sm = ns[J];
+		if (act && u - 1 - PF >= 0) {
+			const size_t back = (size_t)(t + 1 + PF);
+			load_vec<SPL>(frow - back * NP, nf[J]);
+			ns[J] = __ldg(srow - back);
+		}
+		// symbol of bin u-1 (the emission counts of this transition belong to it)
+		const int v = u - 1;
+		int xm = 2;
+		if (trans) {
+			if (t > 0 && (v & 15) == 15) {
+				word = wprev;
+				wprev = __ldg(obs + ch.ow0 + max((v >> 4) - 1, 0));
+			}
+			xm = (word >> ((v & 15) * 2)) & 3;
+		}
+		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
+		emis_coef(xu, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
+		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
+		prefsuf2<SPL, G>(fm, M.W, M.U, ds, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
+		if (trans) {
+			const double inv = fast_rcp(sm);
+			const double w0 = (xm == 0) ? 1.0 : 0.0, w1 = (xm == 1) ? 1.0 : 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				aRL[i] = fma(fm[i], Pg[i], aRL[i]);
+				aRU[i] = fma(fm[i], Sg[i], aRU[i]);
+				aAD[i] = fma(fm[i], g[i], aAD[i]);
+				aCL[i] = fma(g[i], Sf[i], aCL[i]);
+				aCU[i] = fma(g[i], Pf[i], aCU[i]);
+				const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i])); // = b_{u-1} s_{u-1} (khmm.c:230-234)
+				const double gam = fm[i] * bb;                                         // posterior of bin u-1 (khmm.c:317)
+				aE0[i] = fma(gam, w0, aE0[i]);
+				aE1[i] = fma(gam, w1, aE1[i]);
+				b[i] = bb * inv;
+			}
+			xu = xm;
+		}
+	}
+
+	__device__ __forceinline__ void run(double (&b)[SPL], double *__restrict__ part_c)
+	{
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
+#pragma unroll
+		for (int j = 0; j < PF; ++j) {
+			if (ulast - 1 - j >= 0) {
+				load_vec<SPL>(frow - (size_t)(1 + j) * NP, nf[j]);
+				ns[j] = __ldg(srow - (1 + j));
+			} else {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) nf[j][i] = 0.0;
+				ns[j] = 1.0;
+			}
+		}
+		ds.init(gl);
+		xu = (__ldg(obs + ch.ow0 + (ulast >> 4)) >> ((ulast & 15) * 2)) & 3;
+		const int v0 = max(ulast - 1, 0);
+		word = __ldg(obs + ch.ow0 + (v0 >> 4));
+		wprev = __ldg(obs + ch.ow0 + max((v0 >> 4) - 1, 0));
+		const int trips = (warp_trips(valid ? ch.len : 0) + PF - 1) / PF * PF;
+		for (int t = 0; t < trips; t += PF) {
+			step<0>(t, b);
+			step<1>(t + 1, b);
+			step<2>(t + 2, b);
+			step<3>(t + 3, b);
+		}
+		if (valid) {
+			double *po = part_c + s0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				po[S_E0 * NP + i] = aE0[i];
+				po[S_E1 * NP + i] = aE1[i];
+				po[S_RL * NP + i] = aRL[i] * M.U[i];
+				po[S_CL * NP + i] = aCL[i] * M.V[i];
+				po[S_RU * NP + i] = aRU[i] * M.W[i];
+				po[S_CU * NP + i] = aCU[i] * M.Z[i];
+				po[S_AD * NP + i] = aAD[i] * M.D[i];
+			}
+		}
+	}
+};
+
+template <int SPL, int G>
+__device__ __forceinline__ void backward_chunk2(const Chunk &ch, bool valid, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
+                                                const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
+                                                const double *__restrict__ sc, double *__restrict__ part_c,
+                                                double *__restrict__ bsave_c = nullptr, int usave = -1)
+{
+	BackwardRun<SPL, G> r(ch, valid, M, gl, obs, fhat, sc, bsave_c, usave);
+	r.run(b, part_c);
+}
+
 // b_{ulast} in the reference's scaling from a direction beta: sum_k f[k] b[k] s = 1 (khmm.c:237 sanity identity)
 template <int SPL, int G>
 __device__ __forceinline__ void scale_boundary(const Chunk &ch, const double (&beta)[SPL], double (&b)[SPL], int gl,
@@ -947,7 +1434,7 @@ __device__ __forceinline__ void publish_direction(const double (&b)[SPL], double
 // K4w: the backward warm-up on its own (needs only the observations and the model, so it runs on a second stream
 // concurrently with the forward pass): direction of b at the last bin of every chunk that does not end its sequence,
 // from `warm` bins to the right (or from the previous E-step's saved direction), sum-normalised into bwarm[c].
-template <int SPL, int G>
+template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__ chunks, int n_chunks,
                                                        const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                        int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev)
@@ -975,6 +1462,52 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 		for (int i = 0; i < SPL; ++i) beta[i] = fmax(row[i], 1e-300);
 	}
 	const int trips = warp_trips(id.valid ? z0 - ulast : 0);
+	if constexpr (VER == 2) {
+		// Unnormalised recursion with a power-of-two boost when the vector has shrunk (only the direction matters); the sum
+		// that decides it is taken every 16th bin and acts on the NEXT bin, off the dependency chain.  The groups of a warp
+		// are aligned at the END (bin ulast + 1); a group with a shorter overlap starts late and until then computes on
+		// whatever its registers hold -- no per-step select.
+		DualScan<G> ds;
+		ds.init(gl);
+		const int mytrips = id.valid ? z0 - ulast : 0;
+		const int mystart = mytrips > 0 ? trips - mytrips : INT_MAX;
+		int tpend = warp_min_i(mystart);
+		uint32_t word = __ldg(obs + ch.ow0 + (z0 >> 4)), wprev = __ldg(obs + ch.ow0 + max((z0 >> 4) - 1, 0));
+		double q = 1.0, bc[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
+		for (int t = 0; t < trips; ++t) {
+			const int u = ulast + trips - t; // bin whose emission enters; the step yields the direction of bin u-1
+			if (t == tpend) {                // warp-uniform, rare
+				if (mystart == t) {
+#pragma unroll
+					for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
+					q = 1.0;
+				}
+				tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
+			}
+			if (id.valid && u < z0 && (u & 15) == 15) {
+				word = wprev;
+				wprev = __ldg(obs + ch.ow0 + max((u >> 4) - 1, 0));
+			}
+			const int x = (word >> ((u & 15) * 2)) & 3;
+			double g[SPL], c0, c1;
+			emis_coef(x, c0, c1);
+			c0 *= q;
+			c1 *= q;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * bc[i];
+			semisep2<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, ds, bc);
+			q = 1.0;
+			if ((t & 15) == 15) q = (gsum<G>(local_sum<SPL>(bc)) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+		}
+		if (mytrips > 0) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) beta[i] = bc[i];
+		}
+		publish_direction<SPL, G>(beta, bwarm + (size_t)c * NP, gl, id.valid && !is_last);
+		return;
+	}
 	uint32_t word = 0;
 	ScanMasks<G> mk;
 	mk.init(gl);
@@ -1012,7 +1545,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 // warm-up result bwarm (fast path, K4w).  With publish != 0 the direction computed for the last bin of chunk c-1
 // goes to bexact[c-1] for the certificate; usave/bsave_next feed the optional warm start of the next E-step.
 // ------------------------------------------------------------------------------------------------
-template <int SPL, int G>
+template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
                                                   const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                   const double *__restrict__ bdir, int publish, const double *__restrict__ fhat,
@@ -1039,8 +1572,12 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 	}
 	// the bin whose b the left neighbour will start its next overlap from (inside this chunk)
 	const int usave = (ch.flags & CH_FIRST) ? -1 : min(ch.u0 - 1 + warm_next, ulast);
-	backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
-	                       bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
+	if constexpr (VER == 2)
+		backward_chunk2<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
+		                        bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
+	else
+		backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
+		                       bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
 	// b now belongs to the last bin of chunk c-1: publish its direction for the certificate
 	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && publish && !(ch.flags & CH_FIRST));
 }
@@ -1079,7 +1616,7 @@ __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chun
 	}
 }
 
-template <int SPL, int G>
+template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
                                                          const int32_t *__restrict__ chunk_sub0, const Chunk *__restrict__ chunks,
                                                          const uint32_t *__restrict__ obs, const double *__restrict__ model,
@@ -1101,7 +1638,8 @@ __global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict
 	load_vec<SPL>(bsub + (size_t)s * NP + s0, beta);                                                           // exact direction at the sub-chunk's last bin (k_chain_subs)
 	publish_direction<SPL, G>(beta, bwarm + (size_t)pc * NP, gl, valid && chunk_sub0[pc + 1] - 1 == s);       // the chunk boundary agrees by construction from now on
 	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
-	backward_chunk<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP);
+	if constexpr (VER == 2) backward_chunk2<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP);
+	else backward_chunk<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP);
 	if (gl == 0 && valid) atomicAdd(&stat[3], 1ull);
 	// the first sub-chunk of a chunk ends at the boundary to chunk pc-1: publish the direction computed here
 	publish_direction<SPL, G>(b, bexact + (size_t)(pc > 0 ? pc - 1 : 0) * NP, gl,
@@ -1325,6 +1863,7 @@ struct psmc_b200_ctx {
 	int fallbacks = 0, repair_rounds = 3;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
+	int gen = 2;                // kernel generation (PSMC_B200_GEN=1: the Kogge-Stone kernels)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
 	double mis_f = 0.0, mis_b = 0.0;
@@ -1698,7 +2237,9 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device), PSMC_B200_ENODEV);
 	c->sm_count = prop.multiProcessorCount;
 	{
-		const char *env = getenv("PSMC_B200_G_FWD");
+		const char *env = getenv("PSMC_B200_GEN");
+		if (env && atoi(env) == 1) c->gen = 1;
+		env = getenv("PSMC_B200_G_FWD");
 		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_fwd = atoi(env);
 		env = getenv("PSMC_B200_G_BWD");
 		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_bwd = atoi(env);
@@ -1906,54 +2447,80 @@ static void stage_model(psmc_b200_ctx *c, const psmc_b200_model *m)
 // forward kernels are instantiated for SPL <= 8, backward kernels (7*SPL accumulators per lane) for SPL <= 4.
 static inline int blocks_for(int n_chunks, int G) { const int per_block = 4 * (32 / G); return (n_chunks + per_block - 1) / per_block; }
 
+// Kernel generation 2 (DualScan, see above) exists for G = 8 and 16.  Which (G, generation) a context uses:
+//   forward / forward repair / backward warm-up: gen 2 with G = 8 (NP <= 64) or 16 (NP = 128)
+//   backward / backward repair (7 accumulators per state): gen 2 with G = 8 (NP = 32) or 16 (NP = 64); NP = 128 keeps gen 1, G = 32
+// PSMC_B200_GEN=1 selects generation 1 everywhere (then PSMC_B200_G_FWD / _BWD / _BWW choose the group widths as before).
+template <int NP>
+struct Gen2 {
+	static constexpr int G_FWD = (NP > 64) ? 16 : 8;
+	static constexpr int G_BWD = (NP == 32) ? 8 : 16;
+	static constexpr bool BWD_OK = NP <= 64;
+};
+
 template <int NP>
 static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
-#define FWD(G_) LAUNCH((k_forward<NP / G_, G_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
-	if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8);
-	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWD(16);
-	else FWD(32);
+#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
+	if (c->gen == 2) FWD(Gen2<NP>::G_FWD, 2);
+	else if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8, 1);
+	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWD(16, 1);
+	else FWD(32, 1);
 #undef FWD
 }
 template <int NP>
 static void run_forward_repair(psmc_b200_ctx *c)
 {
 	cudaStream_t st = c->stream;
-#define FWR(G_) LAUNCH((k_forward_repair<NP / G_, G_>), blocks_for(c->n_sub, G_), 128, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4)
-	if (c->g_fwd == 8 && NP / 8 <= 8) FWR(8);
-	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWR(16);
-	else FWR(32);
+#define FWR(G_, V_) LAUNCH((k_forward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub, G_), 128, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4)
+	if (c->gen == 2) FWR(Gen2<NP>::G_FWD, 2);
+	else if (c->g_fwd == 8 && NP / 8 <= 8) FWR(8, 1);
+	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWR(16, 1);
+	else FWR(32, 1);
 #undef FWR
 }
 template <int NP>
 static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const double *bdir, int publish, double *bsave_next)
 {
 	cudaStream_t st = c->stream;
-#define BWD(G_) LAUNCH((k_backward<NP / G_, G_>), blocks_for(n, G_), 128, st, chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
+#define BWD(G_, V_) LAUNCH((k_backward<NP / G_, G_, V_>), blocks_for(n, G_), 128, st, chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
 	// (forcing 4 resident blocks per SM with __launch_bounds__(128, 4) was measured: the spills cost more than the occupancy gives)
-	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8);
-	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16);
-	else BWD(32);
+	if constexpr (Gen2<NP>::BWD_OK) {
+		if (c->gen == 2) {
+			BWD(Gen2<NP>::G_BWD, 2);
+			return;
+		}
+	}
+	if (c->g_bwd == 8 && NP / 8 <= 4) BWD(8, 1);
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWD(16, 1);
+	else BWD(32, 1);
 #undef BWD
 }
 template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
-#define BWW(G_) LAUNCH((k_backward_warm<NP / G_, G_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
-	if (c->g_bww == 8 && NP / 8 <= 8) BWW(8);
-	else if (c->g_bww <= 16 && NP / 16 <= 8) BWW(16);
-	else BWW(32);
+#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
+	if (c->gen == 2) BWW(Gen2<NP>::G_FWD, 2);
+	else if (c->g_bww == 8 && NP / 8 <= 8) BWW(8, 1);
+	else if (c->g_bww <= 16 && NP / 16 <= 8) BWW(16, 1);
+	else BWW(32, 1);
 #undef BWW
 }
 template <int NP>
 static void run_backward_repair(psmc_b200_ctx *c)
 {
 	cudaStream_t st = c->stream;
-#define BWR(G_) LAUNCH((k_backward_repair<NP / G_, G_>), blocks_for(c->n_sub_b, G_), 128, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
-	if (c->g_bwd == 8 && NP / 8 <= 4) BWR(8);
-	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWR(16);
-	else BWR(32);
+#define BWR(G_, V_) LAUNCH((k_backward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub_b, G_), 128, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
+	if constexpr (Gen2<NP>::BWD_OK) {
+		if (c->gen == 2) {
+			BWR(Gen2<NP>::G_BWD, 2);
+			return;
+		}
+	}
+	if (c->g_bwd == 8 && NP / 8 <= 4) BWR(8, 1);
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) BWR(16, 1);
+	else BWR(32, 1);
 #undef BWR
 }
 
@@ -1962,13 +2529,19 @@ template <int NP>
 static void chunk_slots(const psmc_b200_ctx *c, int *slots_fwd, int *slots_bwd)
 {
 	int bf = 1, bb = 1, gf = 32, gb = 32;
-#define OCC(K_, G_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, K_<NP / G_, G_>, 128, 0)
-	if (c->g_fwd == 8 && NP / 8 <= 8) { gf = 8; OCC(k_forward, 8, bf); }
-	else if (c->g_fwd <= 16 && NP / 16 <= 8) { gf = 16; OCC(k_forward, 16, bf); }
-	else OCC(k_forward, 32, bf);
-	if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCC(k_backward, 8, bb); }
-	else if (c->g_bwd <= 16 && NP / 16 <= 4) { gb = 16; OCC(k_backward, 16, bb); }
-	else OCC(k_backward, 32, bb);
+#define OCC(K_, G_, V_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, K_<NP / G_, G_, V_>, 128, 0)
+	if (c->gen == 2) { gf = Gen2<NP>::G_FWD; OCC(k_forward, Gen2<NP>::G_FWD, 2, bf); }
+	else if (c->g_fwd == 8 && NP / 8 <= 8) { gf = 8; OCC(k_forward, 8, 1, bf); }
+	else if (c->g_fwd <= 16 && NP / 16 <= 8) { gf = 16; OCC(k_forward, 16, 1, bf); }
+	else OCC(k_forward, 32, 1, bf);
+	bool done = false;
+	if constexpr (Gen2<NP>::BWD_OK) {
+		if (c->gen == 2) { gb = Gen2<NP>::G_BWD; OCC(k_backward, Gen2<NP>::G_BWD, 2, bb); done = true; }
+	}
+	if (done) {}
+	else if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCC(k_backward, 8, 1, bb); }
+	else if (c->g_bwd <= 16 && NP / 16 <= 4) { gb = 16; OCC(k_backward, 16, 1, bb); }
+	else OCC(k_backward, 32, 1, bb);
 #undef OCC
 	*slots_fwd = bf * 4 * (32 / gf);
 	*slots_bwd = bb * 4 * (32 / gb);

@@ -165,7 +165,7 @@ inline double rcp_seed(double s)
 	const float r = 1.0f / (float)m;
 	uint32_t rb;
 	memcpy(&rb, &r, 4);
-	rb &= 0xfffff000u;
+	rb &= 0xfffffff8u; // 20 mantissa bits
 	float rt;
 	memcpy(&rt, &rb, 4);
 	return ldexp((double)rt, -e);

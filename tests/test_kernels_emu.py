@@ -1,0 +1,148 @@
+"""The CUDA kernels' SOURCE executed on the host by a SIMT emulation (tests/emu), checked against the oracle.
+
+Why: the GPU is a scarce resource and lives elsewhere; these tests run everywhere and catch logic errors in the kernels
+(lane-group scans, chunk plans, warm-up / certificate / repair, software-pipelined stores) before GPU time is spent.
+tests/emu/libpsmc_b200_emu.so is psmc_b200/csrc/psmc_estep.cu itself, compiled by g++ with CUDA threads as fibers.  It is
+test infrastructure: nothing under psmc_b200/ or host/ loads it, and the `-m gpu` tests remain the parity tests proper.
+Sizes are small (the emulation is slow); tolerance is the same 1e-10 as on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import compare_stats, make_model, oracle_stats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def emu_built():
+    subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
+    return EMU_DIR
+
+
+@pytest.fixture(params=["libpsmc_b200_emu.so", "libpsmc_b200_emu_boost.so"], ids=["emu", "emu-boost"])
+def emu(request, emu_built, monkeypatch):
+    """the ctypes mirror (psmc_b200.EStep ...) bound to the emulated library for the duration of one test"""
+    from psmc_b200 import _lib
+    lib = _lib.load_library(path=os.path.join(emu_built, request.param))
+    monkeypatch.setattr(_lib, "_lib", lib)
+    monkeypatch.setenv("PSMC_EMU_SMS", "2")
+    return lib
+
+
+@pytest.fixture
+def emu_plain(emu_built, monkeypatch):
+    from psmc_b200 import _lib
+    lib = _lib.load_library(path=os.path.join(emu_built, "libpsmc_b200_emu.so"))
+    monkeypatch.setattr(_lib, "_lib", lib)
+    return lib
+
+
+def _model(m):
+    from psmc_b200 import Model
+    return Model.from_dense(m["a0"], m["a"], m["e"])
+
+
+def _seqs(m, lengths, seed):
+    from psmc_b200 import synth
+    return synth.simulate_genome(m["a0"], m["a"], m["e"], lengths, seed, miss_frac=0.03, miss_mean=20)
+
+
+@pytest.mark.parametrize("gen", ["1", "2"])
+@pytest.mark.parametrize("N,chunk_len", [(5, 7), (23, 64), (33, 16), (64, 7), (64, 1 << 20), (100, 64)])
+def test_emulated_estep_matches_oracle_ragged(oracle, emu, monkeypatch, N, chunk_len, gen):
+    """both kernel generations, every lane-group layout (NP = 32 / 64 / 128), ragged records, transfer-matrix path"""
+    from psmc_b200 import EStep
+    monkeypatch.setenv("PSMC_B200_GEN", gen)
+    monkeypatch.setenv("PSMC_B200_WARM", "0")
+    m = make_model(oracle, N, seed=N)
+    seqs = _seqs(m, [1, 2, 3, 17, 150, 260, 64], seed=100 + N)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=chunk_len) as es:
+        got = es.run(_model(m))
+    compare_stats(got, want, TOL, N)
+
+
+@pytest.mark.parametrize("N", [23, 64, 100])
+@pytest.mark.parametrize("warm", [8, 60, 2500])
+def test_emulated_warmup_certificate_and_repair(oracle, emu, N, warm):
+    """fast path: warm-up overlaps + certificate; short overlaps are caught and repaired, long ones pass untouched"""
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=31)
+    seqs = _seqs(m, [3000, 1100, 40], seed=32)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=500) as es:
+        es.set_warm(warm)
+        got = es.run(_model(m))
+        info = es.info()
+    compare_stats(got, want, TOL, N)
+    assert info["fallbacks"] == 0
+    assert info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
+    if warm == 8:
+        assert info["repaired_fwd"] > 0 and info["repaired_bwd"] > 0
+    if warm == 2500:
+        assert info["repaired_fwd"] == 0 and info["repaired_bwd"] == 0
+
+
+def test_emulated_chunking_is_exact(oracle, emu_plain):
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=3)
+    seqs = _seqs(m, [700, 234], seed=9)
+    res = []
+    for cl in (1 << 20, 97, 16, 5):
+        with EStep(seqs, N, chunk_len=cl) as es:
+            res.append(es.run(_model(m)))
+    for r in res[1:]:
+        compare_stats(r, res[0], 1e-11, N)
+
+
+def test_emulated_edge_tracks(oracle, emu_plain):
+    from psmc_b200 import EStep
+    N = 23
+    m = make_model(oracle, N, seed=5)
+    seqs = [np.full(200, 2, dtype=np.int8), np.zeros(300, dtype=np.int8), np.ones(40, dtype=np.int8)]
+    want = oracle_stats(oracle, m, seqs)
+    with EStep([np.zeros(0, dtype=np.int8)] + seqs, N, chunk_len=50) as es:
+        got = es.run(_model(m))
+        assert es.info()["n_seqs"] == 3
+    compare_stats(got, want, TOL, N)
+
+
+def test_emulated_multiplicity_and_repeatability(oracle, emu_plain):
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=8)
+    seqs = _seqs(m, [300, 200, 250, 100], seed=4)
+    mult = [2, 0, 1, 3]
+    expanded = [s for s, k in zip(seqs, mult) for _ in range(k)]
+    want = oracle_stats(oracle, m, expanded)
+    with EStep(seqs, N, chunk_len=64) as es:
+        es.set_multiplicity(mult)
+        a = es.run(_model(m))
+        b = es.run(_model(m))
+    compare_stats(a, want, TOL, N)
+    assert a["LL"] == b["LL"]
+    for k in ("E", "RL", "CL", "RU", "CU", "AD"):
+        assert np.array_equal(a[k], b[k])
+
+
+@pytest.mark.parametrize("N", [23, 64])
+def test_emulated_decode_matches_oracle(oracle, emu_plain, N):
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=21)
+    seqs = _seqs(m, [600, 155], seed=22)
+    with EStep(seqs, N, chunk_len=100) as es:
+        mod = _model(m)
+        for i, s in enumerate(seqs):
+            got = es.decode(mod if i == 0 else None, i, full=True, want_s=True)
+            want = oracle.decode(m["a"], m["e"], m["a0"], s, full=True)
+            f, b, sc = oracle.fwdbwd(m["a"], m["e"], m["a0"], s)
+            assert np.max(np.abs(got["s"] / sc - 1)) < 1e-11
+            assert np.max(np.abs(got["post"] - want["post"])) < 1e-11
+            assert np.max(np.abs(got["p_recomb"] - want["p_recomb"])) < 1e-10
+            assert np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
