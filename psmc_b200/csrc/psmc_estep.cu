@@ -889,8 +889,14 @@ struct ForwardRun {
 	double *__restrict__ fhat, *__restrict__ sc, *__restrict__ fwarm_c;
 	DualScan<G> ds;
 	double g[SPL], ps, inv_prev, qc, rq_cur, Sstart;
-	int kq, ubase, ubeg, wlast, tpend, mystart;
-	bool warmed;
+	// `valid`, "has this group started" and "is there a warm-up vector to publish" are folded into bin indices the
+	// loop compares u with (one ISETP each; a bool that lives across the loop gets re-derived from threadIdx in every
+	// iteration once registers are tight -- measured):
+	int u_store; // bins u-1 >= u_store are stored                (u0, or never for an idle shadow group)
+	int u_first; // Sstart = S of the bin before bin u_first      (u0, or never)
+	int u_warm;  // the vector of bin u_warm - 1 goes to fwarm_c  (u0 after a warm-up, or never)
+	int u_boost; // boosts of bins >= u_boost enter the log-likelihood
+	int kq, ubase, wlast, tpend, mystart;
 	uint32_t word, wnext;
 
 	__device__ __forceinline__ ForwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_,
@@ -903,19 +909,17 @@ struct ForwardRun {
 
 	// A group whose chunk needs fewer steps than the longest one of its warp starts late: until then it computes on
 	// whatever its registers hold (no per-step select keeps it idle) and picks up its real start vector here.
-	__device__ __forceinline__ void start_if_due(int t, const double (&f)[SPL], double inv_before)
+	__device__ __forceinline__ void start_due(int t, const double (&f)[SPL], double inv_before)
 	{
-		if (t == tpend) { // warp-uniform, rare
-			if (mystart == t) {
+		if (mystart == t) {
 #pragma unroll
-				for (int i = 0; i < SPL; ++i) g[i] = f[i];
-				ps = local_sum<SPL>(g);
-				inv_prev = inv_before;
-				rq_cur = 1.0;
-				qc = 1.0;
-			}
-			tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
+			for (int i = 0; i < SPL; ++i) g[i] = f[i];
+			ps = local_sum<SPL>(g);
+			inv_prev = inv_before;
+			rq_cur = 1.0;
+			qc = 1.0;
 		}
+		tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
 	}
 
 	// bin u = ubase + t is formed from the current vector (bin u-1); BOOK: finish bin u-1 (sum, reciprocal, stores) alongside
@@ -923,17 +927,19 @@ struct ForwardRun {
 	__device__ __forceinline__ void step(int t)
 	{
 		const int u = ubase + t;
-		if (valid && u > ubeg && (u & 15) == 0) {
+		if ((u & 15) == 0) { // next packed word (indices clamped to the sequence, so idle groups read legal words too)
 			word = wnext;
-			wnext = __ldg(obs + ch.ow0 + min((u >> 4) + 1, wlast));
+			wnext = __ldg(obs + ch.ow0 + min(max((u >> 4) + 1, 0), wlast));
 		}
 		const int x = (word >> ((u & 15) * 2)) & 3;
-		double inv1 = inv_prev, qn = 1.0;
+		double c0, c1;
+		emis_coef(x, c0, c1);
+		c0 *= qc;
+		c1 *= qc;
 		if (BOOK) {
 			const double S1 = gsum<G>(ps); // = S_{u-1}
-			inv1 = fast_rcp(S1);
-			const bool st_f = valid && u - 1 >= u0;               // (implies that the group has started)
-			const bool st_w = valid && u == u0 && warmed && fwarm_c != nullptr;
+			const double inv1 = fast_rcp(S1);
+			const bool st_f = u - 1 >= u_store, st_w = u == u_warm;
 			if (st_f || st_w) {
 				double fn[SPL];
 #pragma unroll
@@ -941,37 +947,33 @@ struct ForwardRun {
 				store_vec<SPL>(st_f ? fhat + ((size_t)ch.gb0 + (u - 1 - u0)) * NP + s0 : fwarm_c + s0, fn);
 			}
 			if (st_f && gl == 0) sc[ch.gb0 + (u - 1 - u0)] = S1 * inv_prev * rq_cur;
-			if (u == u0 && u >= ubeg) Sstart = S1;             // (u >= ubeg: the group has started)
-			qn = (S1 < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
-		} else if ((t & 15) == 0) {
-			qn = (gsum<G>(ps) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+			if (u == u_first) Sstart = S1;
+			const bool boosted = qc != 1.0;
+			rq_cur = boosted ? PSMC_BOOST_LOW : 1.0;
+			if (boosted && u >= u_boost) kq += PSMC_BOOST_BITS;
+			inv_prev = inv1;
+			qc = (S1 < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0; // acts on the NEXT bin: off the dependency chain
+		} else {
+			qc = 1.0; // (the warm-up phase decides once per block of 16 bins, see run)
 		}
-		double c0, c1;
-		emis_coef(x, c0, c1);
-		c0 *= qc;
-		c1 *= qc;
 		double out[SPL];
 		semisep2<SPL, G>(g, M.W, M.Z, M.U, M.V, M.D, ds, out);
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) g[i] = out[i] * fma(c1, M.e0[i], c0);
 		ps = local_sum<SPL>(g);
-		inv_prev = inv1;
-		const bool boosted = qc != 1.0;
-		rq_cur = boosted ? PSMC_BOOST_LOW : 1.0;
-		if (boosted && u >= u0 && u >= ubeg) kq += PSMC_BOOST_BITS;
-		qc = qn;
 	}
 
 	__device__ __forceinline__ double run(int ubeg_in, double (&f)[SPL])
 	{
-		ubeg = ubeg_in;
-		warmed = ubeg_in < u0;
+		int ubeg = ubeg_in;
+		const bool warmed = ubeg_in < u0;
 		wlast = (ch.Lseq - 1) >> 4;
 		ds.init(gl);
 		Sstart = 1.0;
 		kq = 0;
 		double inv_before = 1.0; // 1 / S of the bin before the start vector's bin (only the first bin of a sequence needs it)
 		const double S_init = gsum<G>(local_sum<SPL>(f)); // (every lane of the warp takes part)
+		bool have_start = false;
 		if (ubeg_in == 0) {
 			// first bin of a sequence: emission only, no transition (khmm.c:171-174); f is a0 here.  Done in front of the loop
 			// so that the loop body has no special case: the start vector becomes bin 0 (unnormalised) and bin 1 is formed first.
@@ -981,17 +983,26 @@ struct ForwardRun {
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) f[i] *= fma(c1, M.e0[i], c0);
 			inv_before = fast_rcp(S_init);
-			if (u0 == 0) Sstart = S_init;
+			if (u0 == 0) {
+				Sstart = S_init;
+				have_start = true;
+			}
 			ubeg = 1;
 		}
 		// from here on: f = vector of bin ubeg-1, the group forms bins ubeg .. uend-1 and is aligned with the other groups at the END
+		const int never = INT_MAX / 2;
+		u_store = valid ? u0 : never;
+		u_first = (valid && !have_start) ? u0 : never;
+		u_warm = (valid && warmed && fwarm_c != nullptr) ? u0 : never;
+		u_boost = valid ? max(u0, ubeg) : never;
 		const int mytrips = valid ? uend - ubeg : 0;
 		const int trips = warp_trips(mytrips);
 		const int tB = warp_min_i(valid ? trips - (uend - max(u0, ubeg)) : trips); // first step in which some group forms a bin it stores
 		ubase = uend - trips;
 		mystart = valid ? trips - mytrips : INT_MAX;
-		word = __ldg(obs + ch.ow0 + (ubeg >> 4));
-		wnext = __ldg(obs + ch.ow0 + min((ubeg >> 4) + 1, wlast));
+		// (as if bin ubase-1 had just been processed: the first step shifts if ubase starts a word)
+		word = __ldg(obs + ch.ow0 + min(max((ubase - 1) >> 4, 0), wlast));
+		wnext = __ldg(obs + ch.ow0 + min(max(((ubase - 1) >> 4) + 1, 0), wlast));
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) g[i] = f[i];
 		ps = local_sum<SPL>(g);
@@ -1000,13 +1011,17 @@ struct ForwardRun {
 		qc = 1.0;
 		tpend = warp_min_i(mystart);
 		int t = 0;
-		for (; t < tB; ++t) {
-			start_if_due(t, f, inv_before);
-			step<false>(t);
+		while (t < tB) { // warm-up phase, in blocks of at most 16 bins: late starts and the boost decision sit between blocks
+			if (t == tpend) start_due(t, f, inv_before);
+			const int tstop = min(min(tB, tpend), (t & ~15) + 16);
+			qc = (gsum<G>(ps) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+			for (; t < tstop; ++t) step<false>(t);
 		}
-		for (; t < trips; ++t) {
-			start_if_due(t, f, inv_before);
-			step<true>(t);
+		qc = 1.0;
+		while (t < trips) { // store phase
+			if (t == tpend) start_due(t, f, inv_before);
+			const int tstop = min(trips, tpend);
+			for (; t < tstop; ++t) step<true>(t);
 		}
 		if (mytrips == 0) { // nothing formed in the loop (a one-bin chunk at the start of a sequence): the start vector is the last bin
 #pragma unroll
@@ -1280,54 +1295,55 @@ struct BackwardRun {
 	const uint32_t *__restrict__ obs;
 	const double *__restrict__ frow, *__restrict__ srow; // row of bin ulast
 	double *__restrict__ bsave_c;
-	const int usave;
 	DualScan<G> ds;
 	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
 	double nf[PF][SPL], ns[PF];
 	uint32_t word, wprev;
-	int xu;
+	// `valid` and the chunk limits folded into bin indices the loop compares u with (see ForwardRun)
+	int u_lo;   // transitions into bins u >= u_lo are this group's (max(u0, 1), or never for an idle shadow group)
+	int u_save; // b of bin u_save goes to bsave_c (or never)
+	int xu, wlast;
 
 	__device__ __forceinline__ BackwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_, const uint32_t *__restrict__ obs_,
 	                                       const double *__restrict__ fhat, const double *__restrict__ sc, double *__restrict__ bsave_c_, int usave_)
 	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), ulast(ch_.u0 + ch_.len - 1), obs(obs_),
-	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_), usave(usave_)
+	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_)
 	{
+		u_lo = valid_ ? max(ch_.u0, 1) : INT_MAX / 2;
+		u_save = (valid_ && bsave_c_ != nullptr && usave_ >= ch_.u0) ? usave_ : INT_MIN;
 	}
 
 	template <int J>
 	__device__ __forceinline__ void step(int t, double (&b)[SPL])
 	{
 		const int u = ulast - t;
-		const bool act = valid && u >= ch.u0;
-		const bool trans = act && u > 0; // no transition into the first bin of a sequence
-		if (act && u == usave && bsave_c) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
-		// row u-1 from the ring, then refill the slot with row u-1-PF
+		if (u == u_save) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
+		// row u-1 from the ring, then refill the slot with row u-1-PF (unconditionally, the row index clamped to the sequence:
+		// a predicated load would force a copy of the slot)
 		double fm[SPL];
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) fm[i] = nf[J][i];
 		const double sm = ns[J];
-		if (act && u - 1 - PF >= 0) {
-			const size_t back = (size_t)(t + 1 + PF);
+		{
+			const size_t back = (size_t)min(t + 1 + PF, ulast);
 			load_vec<SPL>(frow - back * NP, nf[J]);
 			ns[J] = __ldg(srow - back);
 		}
 		// symbol of bin u-1 (the emission counts of this transition belong to it)
 		const int v = u - 1;
-		int xm = 2;
-		if (trans) {
-			if (t > 0 && (v & 15) == 15) {
-				word = wprev;
-				wprev = __ldg(obs + ch.ow0 + max((v >> 4) - 1, 0));
-			}
-			xm = (word >> ((v & 15) * 2)) & 3;
+		if ((v & 15) == 15) {
+			word = wprev;
+			wprev = __ldg(obs + ch.ow0 + min(max((v >> 4) - 1, 0), wlast));
 		}
+		const int xm = (word >> ((v & 15) * 2)) & 3;
 		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
 		emis_coef(xu, c0, c1);
+		xu = xm;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
 		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
 		prefsuf2<SPL, G>(fm, M.W, M.U, ds, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
-		if (trans) {
+		if (u >= u_lo) { // (no transition into the first bin of a sequence; nothing at all below the chunk)
 			const double inv = fast_rcp(sm);
 			const double w0 = (xm == 0) ? 1.0 : 0.0, w1 = (xm == 1) ? 1.0 : 0.0;
 #pragma unroll
@@ -1343,7 +1359,6 @@ struct BackwardRun {
 				aE1[i] = fma(gam, w1, aE1[i]);
 				b[i] = bb * inv;
 			}
-			xu = xm;
 		}
 	}
 
@@ -1353,20 +1368,16 @@ struct BackwardRun {
 		for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
 #pragma unroll
 		for (int j = 0; j < PF; ++j) {
-			if (ulast - 1 - j >= 0) {
-				load_vec<SPL>(frow - (size_t)(1 + j) * NP, nf[j]);
-				ns[j] = __ldg(srow - (1 + j));
-			} else {
-#pragma unroll
-				for (int i = 0; i < SPL; ++i) nf[j][i] = 0.0;
-				ns[j] = 1.0;
-			}
+			const size_t back = (size_t)min(1 + j, ulast);
+			load_vec<SPL>(frow - back * NP, nf[j]);
+			ns[j] = __ldg(srow - back);
 		}
 		ds.init(gl);
+		wlast = (ch.Lseq - 1) >> 4;
 		xu = (__ldg(obs + ch.ow0 + (ulast >> 4)) >> ((ulast & 15) * 2)) & 3;
-		const int v0 = max(ulast - 1, 0);
-		word = __ldg(obs + ch.ow0 + (v0 >> 4));
-		wprev = __ldg(obs + ch.ow0 + max((v0 >> 4) - 1, 0));
+		// `word` holds the word of bin v = u-1, `wprev` the one below (initialised as if v = ulast had just been processed)
+		word = __ldg(obs + ch.ow0 + (ulast >> 4));
+		wprev = __ldg(obs + ch.ow0 + min(max((ulast >> 4) - 1, 0), wlast));
 		const int trips = (warp_trips(valid ? ch.len : 0) + PF - 1) / PF * PF;
 		for (int t = 0; t < trips; t += PF) {
 			step<0>(t, b);
@@ -1472,34 +1483,41 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 		const int mytrips = id.valid ? z0 - ulast : 0;
 		const int mystart = mytrips > 0 ? trips - mytrips : INT_MAX;
 		int tpend = warp_min_i(mystart);
-		uint32_t word = __ldg(obs + ch.ow0 + (z0 >> 4)), wprev = __ldg(obs + ch.ow0 + max((z0 >> 4) - 1, 0));
+		const int wlast = (ch.Lseq - 1) >> 4, ufirst = ulast + trips;
+		// packed words: `word` holds the word of the bin being processed, `wprev` the one below it; indices are clamped to
+		// the sequence so that idle groups read legal words too (initialised as if bin ufirst+1 had just been processed)
+		uint32_t word = __ldg(obs + ch.ow0 + min(max((ufirst + 1) >> 4, 0), wlast));
+		uint32_t wprev = __ldg(obs + ch.ow0 + min(max(((ufirst + 1) >> 4) - 1, 0), wlast));
 		double q = 1.0, bc[SPL];
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
-		for (int t = 0; t < trips; ++t) {
-			const int u = ulast + trips - t; // bin whose emission enters; the step yields the direction of bin u-1
-			if (t == tpend) {                // warp-uniform, rare
+		int t = 0;
+		while (t < trips) { // blocks of at most 16 bins: late starts and the boost decision sit between blocks
+			if (t == tpend) { // warp-uniform, rare
 				if (mystart == t) {
 #pragma unroll
 					for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
-					q = 1.0;
 				}
 				tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
 			}
-			if (id.valid && u < z0 && (u & 15) == 15) {
-				word = wprev;
-				wprev = __ldg(obs + ch.ow0 + max((u >> 4) - 1, 0));
-			}
-			const int x = (word >> ((u & 15) * 2)) & 3;
-			double g[SPL], c0, c1;
-			emis_coef(x, c0, c1);
-			c0 *= q;
-			c1 *= q;
+			const int tstop = min(min(trips, tpend), (t & ~15) + 16);
+			q = (gsum<G>(local_sum<SPL>(bc)) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+			for (; t < tstop; ++t) {
+				const int u = ufirst - t; // bin whose emission enters; the step yields the direction of bin u-1
+				if ((u & 15) == 15) {
+					word = wprev;
+					wprev = __ldg(obs + ch.ow0 + min(max((u >> 4) - 1, 0), wlast));
+				}
+				const int x = (word >> ((u & 15) * 2)) & 3;
+				double g[SPL], c0, c1;
+				emis_coef(x, c0, c1);
+				c0 *= q;
+				c1 *= q;
+				q = 1.0;
 #pragma unroll
-			for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * bc[i];
-			semisep2<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, ds, bc);
-			q = 1.0;
-			if ((t & 15) == 15) q = (gsum<G>(local_sum<SPL>(bc)) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+				for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * bc[i];
+				semisep2<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, ds, bc);
+			}
 		}
 		if (mytrips > 0) {
 #pragma unroll
@@ -1863,6 +1881,7 @@ struct psmc_b200_ctx {
 	int fallbacks = 0, repair_rounds = 3;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
+	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
 	int gen = 2;                // kernel generation (PSMC_B200_GEN=1: the Kogge-Stone kernels)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
@@ -2239,6 +2258,10 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	{
 		const char *env = getenv("PSMC_B200_GEN");
 		if (env && atoi(env) == 1) c->gen = 1;
+		env = getenv("PSMC_B200_G2_FWD");
+		if (env && atoi(env) == 16) c->g2_fwd = 16;
+		env = getenv("PSMC_B200_G2_BWW");
+		if (env && atoi(env) == 16) c->g2_bww = 16;
 		env = getenv("PSMC_B200_G_FWD");
 		if (env && (atoi(env) == 8 || atoi(env) == 16 || atoi(env) == 32)) c->g_fwd = atoi(env);
 		env = getenv("PSMC_B200_G_BWD");
@@ -2453,7 +2476,6 @@ static inline int blocks_for(int n_chunks, int G) { const int per_block = 4 * (3
 // PSMC_B200_GEN=1 selects generation 1 everywhere (then PSMC_B200_G_FWD / _BWD / _BWW choose the group widths as before).
 template <int NP>
 struct Gen2 {
-	static constexpr int G_FWD = (NP > 64) ? 16 : 8;
 	static constexpr int G_BWD = (NP == 32) ? 8 : 16;
 	static constexpr bool BWD_OK = NP <= 64;
 };
@@ -2463,7 +2485,8 @@ static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
 #define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
-	if (c->gen == 2) FWD(Gen2<NP>::G_FWD, 2);
+	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWD(16, 2);
+	else if (c->gen == 2) FWD(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8, 1);
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWD(16, 1);
 	else FWD(32, 1);
@@ -2474,7 +2497,8 @@ static void run_forward_repair(psmc_b200_ctx *c)
 {
 	cudaStream_t st = c->stream;
 #define FWR(G_, V_) LAUNCH((k_forward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub, G_), 128, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4)
-	if (c->gen == 2) FWR(Gen2<NP>::G_FWD, 2);
+	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWR(16, 2);
+	else if (c->gen == 2) FWR(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWR(8, 1);
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWR(16, 1);
 	else FWR(32, 1);
@@ -2501,7 +2525,8 @@ template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
 #define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
-	if (c->gen == 2) BWW(Gen2<NP>::G_FWD, 2);
+	if (c->gen == 2 && (c->g2_bww == 16 || NP > 64)) BWW(16, 2);
+	else if (c->gen == 2) BWW(8, 2);
 	else if (c->g_bww == 8 && NP / 8 <= 8) BWW(8, 1);
 	else if (c->g_bww <= 16 && NP / 16 <= 8) BWW(16, 1);
 	else BWW(32, 1);
@@ -2530,7 +2555,8 @@ static void chunk_slots(const psmc_b200_ctx *c, int *slots_fwd, int *slots_bwd)
 {
 	int bf = 1, bb = 1, gf = 32, gb = 32;
 #define OCC(K_, G_, V_, out_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out_, K_<NP / G_, G_, V_>, 128, 0)
-	if (c->gen == 2) { gf = Gen2<NP>::G_FWD; OCC(k_forward, Gen2<NP>::G_FWD, 2, bf); }
+	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) { gf = 16; OCC(k_forward, 16, 2, bf); }
+	else if (c->gen == 2) { gf = 8; OCC(k_forward, 8, 2, bf); }
 	else if (c->g_fwd == 8 && NP / 8 <= 8) { gf = 8; OCC(k_forward, 8, 1, bf); }
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) { gf = 16; OCC(k_forward, 16, 1, bf); }
 	else OCC(k_forward, 32, 1, bf);
