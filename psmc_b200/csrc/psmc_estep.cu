@@ -1295,55 +1295,54 @@ struct BackwardRun {
 	const uint32_t *__restrict__ obs;
 	const double *__restrict__ frow, *__restrict__ srow; // row of bin ulast
 	double *__restrict__ bsave_c;
+	const int usave;
 	DualScan<G> ds;
 	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
 	double nf[PF][SPL], ns[PF];
 	uint32_t word, wprev;
-	// `valid` and the chunk limits folded into bin indices the loop compares u with (see ForwardRun)
-	int u_lo;   // transitions into bins u >= u_lo are this group's (max(u0, 1), or never for an idle shadow group)
-	int u_save; // b of bin u_save goes to bsave_c (or never)
-	int xu, wlast;
+	int xu;
 
 	__device__ __forceinline__ BackwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_, const uint32_t *__restrict__ obs_,
 	                                       const double *__restrict__ fhat, const double *__restrict__ sc, double *__restrict__ bsave_c_, int usave_)
 	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), ulast(ch_.u0 + ch_.len - 1), obs(obs_),
-	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_)
+	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_), usave(usave_)
 	{
-		u_lo = valid_ ? max(ch_.u0, 1) : INT_MAX / 2;
-		u_save = (valid_ && bsave_c_ != nullptr && usave_ >= ch_.u0) ? usave_ : INT_MIN;
 	}
 
 	template <int J>
 	__device__ __forceinline__ void step(int t, double (&b)[SPL])
 	{
 		const int u = ulast - t;
-		if (u == u_save) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
-		// row u-1 from the ring, then refill the slot with row u-1-PF (unconditionally, the row index clamped to the sequence:
-		// a predicated load would force a copy of the slot)
+		const bool act = valid && u >= ch.u0;
+		const bool trans = act && u > 0; // no transition into the first bin of a sequence
+		if (act && u == usave && bsave_c) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
+		// row u-1 from the ring, then refill the slot with row u-1-PF
 		double fm[SPL];
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) fm[i] = nf[J][i];
 		const double sm = ns[J];
-		{
-			const size_t back = (size_t)min(t + 1 + PF, ulast);
+		if (act && u - 1 - PF >= 0) {
+			const size_t back = (size_t)(t + 1 + PF);
 			load_vec<SPL>(frow - back * NP, nf[J]);
 			ns[J] = __ldg(srow - back);
 		}
 		// symbol of bin u-1 (the emission counts of this transition belong to it)
 		const int v = u - 1;
-		if ((v & 15) == 15) {
-			word = wprev;
-			wprev = __ldg(obs + ch.ow0 + min(max((v >> 4) - 1, 0), wlast));
+		int xm = 2;
+		if (trans) {
+			if (t > 0 && (v & 15) == 15) {
+				word = wprev;
+				wprev = __ldg(obs + ch.ow0 + max((v >> 4) - 1, 0));
+			}
+			xm = (word >> ((v & 15) * 2)) & 3;
 		}
-		const int xm = (word >> ((v & 15) * 2)) & 3;
 		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
 		emis_coef(xu, c0, c1);
-		xu = xm;
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
 		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
 		prefsuf2<SPL, G>(fm, M.W, M.U, ds, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
-		if (u >= u_lo) { // (no transition into the first bin of a sequence; nothing at all below the chunk)
+		if (trans) {
 			const double inv = fast_rcp(sm);
 			const double w0 = (xm == 0) ? 1.0 : 0.0, w1 = (xm == 1) ? 1.0 : 0.0;
 #pragma unroll
@@ -1359,6 +1358,7 @@ struct BackwardRun {
 				aE1[i] = fma(gam, w1, aE1[i]);
 				b[i] = bb * inv;
 			}
+			xu = xm;
 		}
 	}
 
@@ -1368,16 +1368,20 @@ struct BackwardRun {
 		for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
 #pragma unroll
 		for (int j = 0; j < PF; ++j) {
-			const size_t back = (size_t)min(1 + j, ulast);
-			load_vec<SPL>(frow - back * NP, nf[j]);
-			ns[j] = __ldg(srow - back);
+			if (ulast - 1 - j >= 0) {
+				load_vec<SPL>(frow - (size_t)(1 + j) * NP, nf[j]);
+				ns[j] = __ldg(srow - (1 + j));
+			} else {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) nf[j][i] = 0.0;
+				ns[j] = 1.0;
+			}
 		}
 		ds.init(gl);
-		wlast = (ch.Lseq - 1) >> 4;
 		xu = (__ldg(obs + ch.ow0 + (ulast >> 4)) >> ((ulast & 15) * 2)) & 3;
-		// `word` holds the word of bin v = u-1, `wprev` the one below (initialised as if v = ulast had just been processed)
-		word = __ldg(obs + ch.ow0 + (ulast >> 4));
-		wprev = __ldg(obs + ch.ow0 + min(max((ulast >> 4) - 1, 0), wlast));
+		const int v0 = max(ulast - 1, 0);
+		word = __ldg(obs + ch.ow0 + (v0 >> 4));
+		wprev = __ldg(obs + ch.ow0 + max((v0 >> 4) - 1, 0));
 		const int trips = (warp_trips(valid ? ch.len : 0) + PF - 1) / PF * PF;
 		for (int t = 0; t < trips; t += PF) {
 			step<0>(t, b);
