@@ -285,7 +285,7 @@ def run_own(args):
             em.set_raw(raw, n_seqs_total)
         ci = CInfo()
         lib.psmc_b200_get_info(ctx, ctypes.byref(ci))
-        kern_ms.append(list(ci.ms)[:6]); launches[0] += ci.launches
+        kern_ms.append(list(ci.ms)[:8]); launches[0] += ci.launches
         em.mstep()                                          # replicated on every rank on identical inputs
 
     def barrier():
@@ -346,6 +346,10 @@ def run_own(args):
         kb = {"forward": (8 * NST + 8 + 0.25), "backward": (8 * NST + 8 + 0.25)}
         for i, nm in enumerate(names):
             per_kernel[nm] = {"ms": float(mean_ms[i])}
+            if nm == "forward" and mean_ms[6] > 0:
+                per_kernel[nm]["kernel_alone_ms"] = float(mean_ms[6])      # k_forward without its repair rounds
+            if nm == "backward" and mean_ms[7] > 0:
+                per_kernel[nm]["kernel_alone_ms"] = float(mean_ms[7])
             if nm in kb and mean_ms[i] > 0:
                 per_kernel[nm]["alg_GBps"] = kb[nm] * my_bins / (mean_ms[i] * 1e-3) / 1e9
         achieved = alg_bytes_per_bin * my_bins / (estep_ms * 1e-3) / 1e9

@@ -65,7 +65,8 @@ typedef struct {
 	int64_t bytes_obs, bytes_forward, bytes_transfer, bytes_total;
 	/* device time of the kernels of the LAST run, milliseconds (CUDA events on the context's stream):
 	 * [0] transfer-matrix kernel  [1] boundary-chain kernel  [2] forward kernel
-	 * [3] backward+counts kernel  [4] reduction kernel        [5] whole E-step (first launch .. last) */
+	 * [3] backward+counts kernel  [4] reduction kernel        [5] whole E-step (first launch .. last)
+	 * fast path: [2] / [3] include the repair rounds of their direction; [6] / [7] the forward / backward chunk kernel alone */
 	float ms[8];
 	int32_t launches; /* kernels launched by the last run */
 	/* fast path (warm-up overlaps + boundary certificate): overlap in bins (0 = disabled), how many E-steps of this

@@ -463,15 +463,18 @@ template <int SPL, int G, int COLS>
 __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ chunks, const int32_t *__restrict__ k1_list,
                                                       const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                       double *__restrict__ T, int32_t *__restrict__ Tex, int N,
-                                                      const int32_t *__restrict__ flag, int sel, const int32_t *__restrict__ skip)
+                                                      const int32_t *__restrict__ flag, int sel, const int32_t *__restrict__ skip,
+                                                      int n_items)
 {
 	constexpr int NP = SPL * G;
-	// sel 0: chunk list (transfer mode).  sel 3: repair rounds of the warm-up mode: `chunks` is the SUB-chunk table,
-	// one block row per sub-chunk, only those whose parent chunk is flagged (flag has guard entries at -1 and n).
-	const int c = sel == 0 ? k1_list[blockIdx.x] : (int)blockIdx.x;
-	// k1_list = parent chunk of every sub-chunk in this mode; `skip` marks parents whose operators are already there
-	// (computed ahead of time from the previous E-step's failures, see launch_warm)
-	if (sel == 3 && (!flag[k1_list[c]] || (skip && skip[k1_list[c]]))) return;
+	// sel 0: chunk list (transfer mode), one block row per listed chunk.  sel 3: repair rounds of the warm-up mode: `chunks`
+	// is the SUB-chunk table; the block rows stride over it and work on the sub-chunks whose parent chunk is flagged (flag has
+	// guard entries at -1 and n) -- a few hundred of ~19 000, so a block row per sub-chunk would spend 0.1 ms per launch on
+	// scheduling empty blocks (measured).  k1_list = parent chunk of every sub-chunk in this mode; `skip` marks parents whose
+	// operators are already there (computed ahead of time from the previous E-step's failures, see launch_warm).
+	for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+	const int c = sel == 0 ? k1_list[item] : item;
+	if (sel == 3 && (!flag[k1_list[c]] || (skip && skip[k1_list[c]]))) continue;
 	const Chunk ch = chunks[c];
 	const int gl = threadIdx.x % G;
 	const int col = blockIdx.y * COLS + threadIdx.x / G;
@@ -529,6 +532,7 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
 	double *Tc = T + (size_t)c * NP * NP + (size_t)col * NP + s0;
 	store_vec<SPL>(Tc, f);
 	if (gl == 0) Tex[(size_t)c * NP + col] = ex;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1886,6 +1890,7 @@ struct psmc_b200_ctx {
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
+	int side_order = 0;         // PSMC_B200_SIDE_ORDER, see launch_warm
 	int gen = 2;                // kernel generation (PSMC_B200_GEN=1: the Kogge-Stone kernels)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
@@ -2262,6 +2267,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	{
 		const char *env = getenv("PSMC_B200_GEN");
 		if (env && atoi(env) == 1) c->gen = 1;
+		env = getenv("PSMC_B200_SIDE_ORDER");
+		if (env) c->side_order = atoi(env);
 		env = getenv("PSMC_B200_G2_FWD");
 		if (env && atoi(env) == 16) c->g2_fwd = 16;
 		env = getenv("PSMC_B200_G2_BWW");
@@ -2299,7 +2306,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		c->warm_len = env ? atoi(env) : 12288;
 		if (c->warm_len < 0) c->warm_len = 0;
 		env = getenv("PSMC_B200_WARM_BWD");
-		c->warm_len_bwd = (env && atoi(env) > 0) ? atoi(env) : 2 * c->warm_len;
+		c->warm_len_bwd = (env && atoi(env) > 0) ? atoi(env) : c->warm_len + c->warm_len / 3; // (it shares the SMs with the forward kernel: not free)
 		c->warm_bwd_fixed = (env && atoi(env) > 0);
 		env = getenv("PSMC_B200_WARM_HOT");
 		if (env && atoi(env) >= 0) c->warm_hot = atoi(env);
@@ -2587,7 +2594,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	if (c->n_k1 > 0) {
 		constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 		dim3 grid((unsigned)c->n_k1, NP / COLS);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), grid, COLS * G1, st, c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), grid, COLS * G1, st, c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr, c->n_k1);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[1], st);
@@ -2632,32 +2639,47 @@ static int launch_warm(psmc_b200_ctx *c)
 	const int wpb = 4, nblk = (c->n_chunks + wpb - 1) / wpb;
 	const int hot = (c->have_prev && c->warm_hot > 0) ? 1 : 0;
 	const int wl = hot ? c->warm_hot : c->warm_len;
-	// the backward warm-up needs only observations + model: run it on the side stream, concurrently with the forward pass
+	// The backward warm-up needs only observations + model: it runs on the side stream, concurrently with the forward pass;
+	// on small shards (multi-GPU) a long one would become the critical path, so it is capped at the forward kernel's length.
+	// The side stream also computes, ahead of time, the operators of the chunks that failed in the previous E-step.
+	// Order on the side stream (PSMC_B200_SIDE_ORDER): 0 = warm-up, forward operators, backward operators;
+	//                                                  1 = forward operators first (the forward repair rounds wait for them only).
 	cudaEventRecord(c->ev_fork, st);
 	cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
-	// the backward warm-up hides behind the forward kernel (warm_len + chunk_len steps per chunk): on small shards
-	// (multi-GPU) a longer one would become the critical path, so it is capped at the forward kernel's length
 	const int wl_b = (c->warm_bwd_fixed || c->warm_len_bwd <= c->warm_len + c->chunk_len) ? c->warm_len_bwd : std::max(c->warm_len, c->warm_len + c->chunk_len);
-	run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : wl_b, hot);
-	cudaEventRecord(c->ev_join, c->stream2);
-	run_forward<NP>(c, wl, hot);
 	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
-	const dim3 gridT((unsigned)c->n_sub, NP / COLS);
+	const dim3 gridT((unsigned)std::min(c->n_sub, 8 * c->sm_count), NP / COLS); // block rows stride over the sub-chunks
 	const int nblk_b = (c->n_chunks_b + wpb - 1) / wpb;
-	const dim3 gridTb((unsigned)c->n_sub_b, NP / COLS);
-	// operators of the chunks that failed in the previous E-step, ahead of time on the side stream (behind the backward warm-up)
+	const dim3 gridTb((unsigned)std::min(c->n_sub_b, 8 * c->sm_count), NP / COLS);
 	const int32_t *pred = c->predict ? c->d_pred[c->pred_cur] + 1 : nullptr, *pred_b = c->predict ? c->d_pred_b[c->pred_cur] + 1 : nullptr;
 	int32_t *pred_next = c->d_pred[c->pred_cur ^ 1] + 1, *pred_next_b = c->d_pred_b[c->pred_cur ^ 1] + 1;
-	if (c->predict) {
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, c->stream2, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr);
+	auto side_k1f = [&]() {
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, c->stream2, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr, c->n_sub);
 		cudaEventRecord(c->ev_k1f, c->stream2);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr);
+	};
+	auto side_warm = [&]() {
+		run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : wl_b, hot);
+		cudaEventRecord(c->ev_join, c->stream2);
+	};
+	if (c->side_order == 1) {
+		run_forward<NP>(c, wl, hot);
+		cudaEventRecord(c->ev[6], st); // forward kernel done (the repair rounds follow)
+		if (c->predict) side_k1f();
+		side_warm();
+	} else {
+		side_warm();
+		run_forward<NP>(c, wl, hot);
+		cudaEventRecord(c->ev[6], st);
+		if (c->predict) side_k1f();
+	}
+	if (c->predict) {
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr, c->n_sub_b);
 		cudaEventRecord(c->ev_k1b, c->stream2);
 		cudaStreamWaitEvent(st, c->ev_k1f, 0);
 	}
 	for (int r = 0; r < c->repair_rounds; ++r) {
 		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_forward_repair<NP>(c);
 		LAUNCH((k_fold), c->n_chunks, 128, st, c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
@@ -2665,11 +2687,12 @@ static int launch_warm(psmc_b200_ctx *c)
 	cudaEventRecord(c->ev[3], st);
 	cudaStreamWaitEvent(st, c->ev_join, 0);
 	run_backward<NP>(c, c->d_chunks_b, c->n_chunks_b, c->d_bwarm, 1, c->d_bsave[c->bsave_cur ^ 1]);
+	cudaEventRecord(c->ev[7], st); // backward kernel done
 	c->bsave_cur ^= 1;
 	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
 	for (int r = 0; r < c->repair_rounds; ++r) {
 		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
 		LAUNCH((k_fold), c->n_chunks_b, 128, st, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
@@ -2738,6 +2761,10 @@ static void collect_times(psmc_b200_ctx *c, bool with_counts)
 		cudaEventElapsedTime(&c->ms[3], c->ev[3], c->ev[4]);
 		cudaEventElapsedTime(&c->ms[4], c->ev[4], c->ev[5]);
 		cudaEventElapsedTime(&c->ms[5], c->ev[0], c->ev[5]);
+		if (c->mode_warm) { // fast path: the two chunk kernels on their own (ms[2] / ms[3] include the repair rounds)
+			cudaEventElapsedTime(&c->ms[6], c->ev[2], c->ev[6]);
+			cudaEventElapsedTime(&c->ms[7], c->ev[3], c->ev[7]);
+		}
 	} else {
 		cudaEventElapsedTime(&c->ms[5], c->ev[0], c->ev[3]);
 	}

@@ -13,8 +13,8 @@ for spec in sys.argv[1:]:
         d = json.loads(r.stdout.strip().splitlines()[-1])
         k = d["roofline"]["kernels"]
         fp = d["estep"]["fast_path"]
-        print("%-60s it/s %.2f e2e %.2f estep %.2f ms (fwd %.2f bwd %.2f) mstep %.2f fail f/b %d/%d rep %d/%d fb %d" % (
-            spec or "(defaults)", d["value"], d["e2e"]["value"], d["roofline"]["estep_ms"], k["forward"]["ms"], k["backward"]["ms"],
+        print("%-60s it/s %.2f e2e %.2f estep %.2f ms (fwd %.2f [%.2f] bwd %.2f [%.2f]) mstep %.2f fail f/b %d/%d rep %d/%d fb %d" % (
+            spec or "(defaults)", d["value"], d["e2e"]["value"], d["roofline"]["estep_ms"], k["forward"]["ms"], k["forward"].get("kernel_alone_ms", 0), k["backward"]["ms"], k["backward"].get("kernel_alone_ms", 0),
             d["estep"]["mstep_ms"], fp["failed_fwd"], fp["failed_bwd"], fp["repaired_fwd"], fp["repaired_bwd"], fp["fallbacks"]), flush=True)
     except Exception as e:
         print("%-60s FAILED rc=%d %s %s" % (spec, r.returncode, e, r.stderr[-300:]), flush=True)
