@@ -1066,19 +1066,22 @@ template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                  const double *__restrict__ vstart, int warm, int use_prev, double *__restrict__ fhat,
-                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm)
+                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm,
+                                                 const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
 	if (!__any_sync(FULLMASK, id.valid)) return;
-	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	// order: chunks sorted by their number of steps, so that the groups of a warp finish together (adaptive overlaps);
+	// warm_of: this chunk's own overlap (nullptr: `warm` for every chunk)
+	const int c = order ? order[id.c] : id.c, gl = id.gl, s0 = gl * SPL;
 	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
 	M.load(model, s0, NP);
 	double f[SPL];
 	int ubeg = ch.u0;
 	if ((ch.flags & CH_FIRST) || warm > 0) {
-		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - warm);
+		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - (warm_of ? min(warm_of[c], warm) : warm));
 		if (use_prev && ubeg > 0) {
 			// warm start: the vector the PREVIOUS E-step stored for bin ubeg-1 (the parameters moved only a little since;
 			// any positive vector is a legal start -- the certificate decides -- so a stale or concurrently rewritten row is harmless)
@@ -1096,6 +1099,46 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	if constexpr (VER == 2) ll = forward_chunk2<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	else ll = forward_chunk<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	if (gl == 0 && id.valid) llpart[c] = ll;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adaptive overlaps.  How many bins of warm-up a boundary needs is a property of the data around it (het-poor,
+// low-TMRCA tracts mix slowly) and varies by an order of magnitude between boundaries; the mismatch the certificate
+// measures anyway tells, per boundary, whether the overlap of this E-step was ample (mismatch at the rounding floor),
+// tight, or too short.  Additive-decrease / multiplicative-increase on that signal: shrink by 1/8 while the mismatch
+// stays at the floor, grow by 1/2 as soon as it leaves the safe band (the boundary still passes at 1e-12, or is
+// repaired).  All on the device, inside the mark kernels of the first repair round; the next E-step reads the new lengths.
+// ------------------------------------------------------------------------------------------------
+// w: the overlap used in this E-step; tight: the longest overlap seen so far whose mismatch was NOT at the floor (memory,
+// so that a boundary approaches its need from above once instead of probing it again and again).
+__device__ __forceinline__ int adapt_overlap(int w, double mismatch, int w_max, int32_t *tight)
+{
+	const int w_min = 1536;
+	int t = *tight;
+	if (!(mismatch <= 2e-14)) { // off the floor (or failed): remember, and keep a safe distance from now on
+		t = max(t, w);
+		*tight = t;
+	}
+	const int floor_w = max(w_min, (t + (t >> 1)) & ~15); // 1.5 x the tightest length seen
+	if (mismatch <= 2e-14) w = max(floor_w, (w - (w >> 4)) & ~15); // 1/16 per E-step: a step multiplies the mismatch by < 10
+	else w = max(floor_w, w);
+	return max(min(w, w_max), 16);
+}
+
+// order[] = chunk indices sorted (stably) by their number of steps, longest first: every thread ranks one chunk
+// (O(n^2 / threads); n is a few thousand).  steps = (overlap unless the chunk starts / ends its sequence) + chunk length.
+__global__ void __launch_bounds__(256) k_order(const Chunk *__restrict__ chunks, int n_chunks, const int32_t *__restrict__ warm_of,
+                                               int warm_cap, int edge_flag, int32_t *__restrict__ order)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_chunks) return;
+	const int ki = ((chunks[i].flags & edge_flag) ? 0 : min(warm_of[i], warm_cap)) + chunks[i].len;
+	int rank = 0;
+	for (int j = 0; j < n_chunks; ++j) {
+		const int kj = ((chunks[j].flags & edge_flag) ? 0 : min(warm_of[j], warm_cap)) + chunks[j].len;
+		rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
+	}
+	order[rank] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1124,18 +1167,23 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ fhat, const double *__restrict__ fwarm,
                                                   int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next)
+                                                  int32_t *__restrict__ pred_next, int32_t *__restrict__ warm_of, int warm_max, int32_t *__restrict__ tight)
 {
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31;
 	const Chunk ch = chunks[c];
 	int fl = 0;
-	if (!(ch.flags & CH_FIRST)) fl = fwd_boundary_mismatch<SPL>(ch, c, fhat, fwarm, gl * SPL, N) > eps ? 1 : 0;
+	double m = 0.0;
+	if (!(ch.flags & CH_FIRST)) {
+		m = fwd_boundary_mismatch<SPL>(ch, c, fhat, fwarm, gl * SPL, N);
+		fl = m > eps ? 1 : 0;
+	}
 	if (gl == 0) {
 		flag_f[c] = fl;
 		if (pred_next) pred_next[c] = fl;
 		if (fl) atomicAdd(&stat[0], 1ull);
+		if (warm_of && pred_next && !(ch.flags & CH_FIRST)) warm_of[c] = adapt_overlap(warm_of[c], m, warm_max, tight + c); // first round only
 	}
 }
 
@@ -1456,12 +1504,13 @@ __device__ __forceinline__ void publish_direction(const double (&b)[SPL], double
 template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__ chunks, int n_chunks,
                                                        const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev)
+                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev,
+                                                       const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
 	if (!__any_sync(FULLMASK, id.valid)) return;
-	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const int c = order ? order[id.c] : id.c, gl = id.gl, s0 = gl * SPL; // (order / warm_of: adaptive overlaps, see k_forward)
 	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
 	M.load(model, s0, NP);
@@ -1470,6 +1519,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 	double beta[SPL];
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
+	if (warm_of) warm = min(warm_of[c], warm);
 	int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
 	if (bsave_prev && !is_last) {
 		// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin
@@ -1628,17 +1678,23 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ bwarm, const double *__restrict__ bexact,
                                                   int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next)
+                                                  int32_t *__restrict__ pred_next, int32_t *__restrict__ warm_of, int warm_max, int32_t *__restrict__ tight)
 {
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31;
 	int fl = 0;
-	if (!(chunks[c].flags & CH_LAST)) fl = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, gl * SPL, N) > eps ? 1 : 0;
+	double m = 0.0;
+	const bool inner = !(chunks[c].flags & CH_LAST);
+	if (inner) {
+		m = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, gl * SPL, N);
+		fl = m > eps ? 1 : 0;
+	}
 	if (gl == 0) {
 		flag_b[c] = fl;
 		if (pred_next) pred_next[c] = fl;
 		if (fl) atomicAdd(&stat[2], 1ull);
+		if (warm_of && pred_next && inner) warm_of[c] = adapt_overlap(warm_of[c], m, warm_max, tight + c); // first round only
 	}
 }
 
@@ -1891,6 +1947,11 @@ struct psmc_b200_ctx {
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
 	int side_order = 0;         // PSMC_B200_SIDE_ORDER, see launch_warm
+	bool adapt = false;         // adaptive per-boundary overlaps (PSMC_B200_ADAPT=1; measured on B200: no gain -- the kernels' duration is set by
+	                            // the slowest boundaries either way and the extra failures while adapting cost more than the shorter warm-ups save)
+	int adapt_max_chunks = 16384; // (k_order ranks in O(n^2))
+	int warm_max_b = 0;         // ceiling of an adaptive backward overlap
+	int32_t *d_warm_f = nullptr, *d_warm_b = nullptr, *d_order_f = nullptr, *d_order_b = nullptr, *d_tight_f = nullptr, *d_tight_b = nullptr;
 	int gen = 2;                // kernel generation (PSMC_B200_GEN=1: the Kogge-Stone kernels)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
@@ -1962,7 +2023,8 @@ static void free_plan(psmc_b200_ctx *c)
 	              (void **)&c->d_chunk_sub0, (void **)&c->d_Tsub, (void **)&c->d_Texsub, (void **)&c->d_vsub, (void **)&c->d_bsub,
 	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b,
 	              (void **)&c->d_pred[0], (void **)&c->d_pred[1], (void **)&c->d_pred_b[0], (void **)&c->d_pred_b[1],
-	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b};
+	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b,
+	              (void **)&c->d_warm_f, (void **)&c->d_warm_b, (void **)&c->d_order_f, (void **)&c->d_order_b, (void **)&c->d_tight_f, (void **)&c->d_tight_b};
 	for (auto q : p) { cudaFree(*q); *q = nullptr; }
 	c->bytes_total -= c->bytes_plan;
 	c->bytes_plan = 0;
@@ -2059,6 +2121,26 @@ static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 
 // (Re)build both chunk plans over the sequences with multiplicity > 0 and upload them.  The packed observations,
 // the forward spill (indexed by bin) and everything else that does not depend on the plan stay where they are.
+// adaptive overlaps start from the configured lengths, in plan order
+static int reset_overlaps(psmc_b200_ctx *c)
+{
+	if (!c->d_warm_f) return 0;
+	c->warm_max_b = std::max(c->warm_len_bwd, 2 * c->warm_len);
+	std::vector<int32_t> wf((size_t)std::max(c->n_chunks, 1), c->warm_len), wb((size_t)std::max(c->n_chunks_b, 1), c->warm_len_bwd);
+	std::vector<int32_t> of((size_t)std::max(c->n_chunks, 1)), ob((size_t)std::max(c->n_chunks_b, 1));
+	for (size_t i = 0; i < of.size(); ++i) of[i] = (int32_t)i;
+	for (size_t i = 0; i < ob.size(); ++i) ob[i] = (int32_t)i;
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemcpyAsync(c->d_warm_f, wf.data(), sizeof(int32_t) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemcpyAsync(c->d_warm_b, wb.data(), sizeof(int32_t) * (size_t)c->n_chunks_b, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemcpyAsync(c->d_order_f, of.data(), sizeof(int32_t) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemcpyAsync(c->d_order_b, ob.data(), sizeof(int32_t) * (size_t)c->n_chunks_b, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemsetAsync(c->d_tight_f, 0, sizeof(int32_t) * (size_t)std::max(c->n_chunks, 1), c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMemsetAsync(c->d_tight_b, 0, sizeof(int32_t) * (size_t)std::max(c->n_chunks_b, 1), c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	return 0;
+}
+
 static int replan(psmc_b200_ctx *c)
 {
 	const int NP = c->NP;
@@ -2194,6 +2276,12 @@ static int replan(psmc_b200_ctx *c)
 		alloc((void **)&c->d_bsub, sizeof(double) * (size_t)csb * NP);
 		alloc((void **)&c->d_llsub, sizeof(double) * (size_t)cs);
 		alloc((void **)&c->d_partsub, sizeof(double) * (size_t)csb * S_COUNT * NP);
+		alloc((void **)&c->d_warm_f, sizeof(int32_t) * (size_t)cc);
+		alloc((void **)&c->d_warm_b, sizeof(int32_t) * (size_t)cb);
+		alloc((void **)&c->d_order_f, sizeof(int32_t) * (size_t)cc);
+		alloc((void **)&c->d_order_b, sizeof(int32_t) * (size_t)cb);
+		alloc((void **)&c->d_tight_f, sizeof(int32_t) * (size_t)cc);
+		alloc((void **)&c->d_tight_b, sizeof(int32_t) * (size_t)cb);
 		alloc((void **)&c->d_cw, sizeof(double) * (size_t)cc);
 		alloc((void **)&c->d_cw_b, sizeof(double) * (size_t)cb);
 		c->bytes_total += c->bytes_plan;
@@ -2221,6 +2309,10 @@ static int replan(psmc_b200_ctx *c)
 	CUDA_TRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(st), PSMC_B200_ECUDA); // the host vectors above go out of scope
+	{
+		int rc = reset_overlaps(c);
+		if (rc) return rc;
+	}
 	c->have_prev = false;
 	c->fwd_valid = false;
 	c->launched = false;
@@ -2267,6 +2359,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	{
 		const char *env = getenv("PSMC_B200_GEN");
 		if (env && atoi(env) == 1) c->gen = 1;
+		env = getenv("PSMC_B200_ADAPT");
+		if (env) c->adapt = atoi(env) != 0;
 		env = getenv("PSMC_B200_SIDE_ORDER");
 		if (env) c->side_order = atoi(env);
 		env = getenv("PSMC_B200_G2_FWD");
@@ -2495,7 +2589,8 @@ template <int NP>
 static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
-#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
+	const bool ad = c->adapt && warm > 0 && !use_prev && c->n_chunks <= c->adapt_max_chunks;
+#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, ad ? c->d_order_f : nullptr, ad ? c->d_warm_f : nullptr)
 	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWD(16, 2);
 	else if (c->gen == 2) FWD(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8, 1);
@@ -2535,7 +2630,8 @@ static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const dou
 template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
-#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
+	const bool ad = c->adapt && !use_prev && c->n_chunks_b <= c->adapt_max_chunks;
+#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr, ad ? c->d_order_b : nullptr, ad ? c->d_warm_b : nullptr)
 	if (c->gen == 2 && (c->g2_bww == 16 || NP > 64)) BWW(16, 2);
 	else if (c->gen == 2) BWW(8, 2);
 	else if (c->g_bww == 8 && NP / 8 <= 8) BWW(8, 1);
@@ -2639,6 +2735,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	const int wpb = 4, nblk = (c->n_chunks + wpb - 1) / wpb;
 	const int hot = (c->have_prev && c->warm_hot > 0) ? 1 : 0;
 	const int wl = hot ? c->warm_hot : c->warm_len;
+	const bool adf = c->adapt && !hot && c->n_chunks <= c->adapt_max_chunks, adb = c->adapt && !hot && c->n_chunks_b <= c->adapt_max_chunks;
 	// The backward warm-up needs only observations + model: it runs on the side stream, concurrently with the forward pass;
 	// on small shards (multi-GPU) a long one would become the critical path, so it is capped at the forward kernel's length.
 	// The side stream also computes, ahead of time, the operators of the chunks that failed in the previous E-step.
@@ -2647,6 +2744,8 @@ static int launch_warm(psmc_b200_ctx *c)
 	cudaEventRecord(c->ev_fork, st);
 	cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
 	const int wl_b = (c->warm_bwd_fixed || c->warm_len_bwd <= c->warm_len + c->chunk_len) ? c->warm_len_bwd : std::max(c->warm_len, c->warm_len + c->chunk_len);
+	// adaptive overlaps may grow beyond the default, up to warm_max_b (but never beyond what hides behind the forward kernel)
+	const int cap_b = adb ? std::min(c->warm_max_b, std::max(wl_b, c->warm_len + c->chunk_len)) : wl_b;
 	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 	const dim3 gridT((unsigned)std::min(c->n_sub, 8 * c->sm_count), NP / COLS); // block rows stride over the sub-chunks
 	const int nblk_b = (c->n_chunks_b + wpb - 1) / wpb;
@@ -2658,7 +2757,7 @@ static int launch_warm(psmc_b200_ctx *c)
 		cudaEventRecord(c->ev_k1f, c->stream2);
 	};
 	auto side_warm = [&]() {
-		run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : wl_b, hot);
+		run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : cap_b, hot);
 		cudaEventRecord(c->ev_join, c->stream2);
 	};
 	if (c->side_order == 1) {
@@ -2678,7 +2777,7 @@ static int launch_warm(psmc_b200_ctx *c)
 		cudaStreamWaitEvent(st, c->ev_k1f, 0);
 	}
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr);
+		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr, adf ? c->d_warm_f : nullptr, c->warm_len, c->d_tight_f);
 		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_forward_repair<NP>(c);
@@ -2691,7 +2790,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	c->bsave_cur ^= 1;
 	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr);
+		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr, adb ? c->d_warm_b : nullptr, cap_b, c->d_tight_b);
 		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
@@ -2701,8 +2800,11 @@ static int launch_warm(psmc_b200_ctx *c)
 	LAUNCH((k_reduce), 1 + S_COUNT * c->N, 256, st, c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
 	LAUNCH((k_certify<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
 	LAUNCH((k_certify<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
+	// adaptive overlaps: sort the chunks by their new number of steps for the next E-step (two tiny launches)
+	if (adf) LAUNCH((k_order), (c->n_chunks + 255) / 256, 256, st, c->d_chunks, c->n_chunks, c->d_warm_f, c->warm_len, CH_FIRST, c->d_order_f);
+	if (adb) LAUNCH((k_order), (c->n_chunks_b + 255) / 256, 256, st, c->d_chunks_b, c->n_chunks_b, c->d_warm_b, cap_b, CH_LAST, c->d_order_b);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0);
+	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0) + (adf ? 1 : 0) + (adb ? 1 : 0);
 	c->pred_cur ^= 1;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -2967,7 +3069,12 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
 extern "C" int psmc_b200_set_warm(psmc_b200_ctx *c, int32_t warm_len, double eps)
 {
 	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
-	if (warm_len >= 0) { c->warm_len = warm_len; c->warm_len_bwd = 2 * warm_len; }
+	if (warm_len >= 0) {
+		c->warm_len = warm_len;
+		c->warm_len_bwd = warm_len + warm_len / 3;
+		int rc = reset_overlaps(c);
+		if (rc) return rc;
+	}
 	if (eps > 0) c->cert_eps = eps;
 	return 0;
 }

@@ -133,15 +133,22 @@ def test_warmup_certificate_and_fallback(oracle, warm):
 
 
 def test_repeatable_bitwise(oracle):
+    """same inputs, same call history -> the same bits (fixed-order reductions, no atomics in the data path).  A context
+    adapts its per-boundary overlaps from one E-step to the next, so consecutive E-steps of ONE context agree to the
+    certificate's 1e-12 rather than bitwise; two contexts with the same history agree bitwise, E-step by E-step."""
     from psmc_b200 import EStep
     N = 64
     m = make_model(oracle, N, seed=2)
     seqs = _seqs(m, [30000], seed=3)
-    with EStep(seqs, N, chunk_len=1000) as es:
-        a = es.run(_model(m)); b = es.run(_model(m))
-    assert a["LL"] == b["LL"]
-    for k in ("E", "RL", "CL", "RU", "CU", "AD"):
-        assert np.array_equal(a[k], b[k])
+    runs = []
+    for rep in range(2):
+        with EStep(seqs, N, chunk_len=1000) as es:
+            runs.append([es.run(_model(m)) for _ in range(3)])
+    for a, b in zip(*runs):
+        assert a["LL"] == b["LL"]
+        for k in ("E", "RL", "CL", "RU", "CU", "AD"):
+            assert np.array_equal(a[k], b[k])
+    compare_stats(runs[0][2], runs[0][0], 1e-11, N)
 
 
 @pytest.mark.parametrize("N", [23, 64])

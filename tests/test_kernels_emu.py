@@ -146,3 +146,25 @@ def test_emulated_decode_matches_oracle(oracle, emu_plain, N):
             assert np.max(np.abs(got["post"] - want["post"])) < 1e-11
             assert np.max(np.abs(got["p_recomb"] - want["p_recomb"])) < 1e-10
             assert np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
+
+
+def test_emulated_adaptive_overlaps_over_iterations(oracle, emu_plain, monkeypatch):
+    """per-boundary overlaps shrink while the certificate's mismatch stays at the rounding floor and grow when it does not;
+    the chunks are re-sorted by their number of steps after every E-step -- the result must stay exact throughout"""
+    from psmc_b200 import EStep
+    monkeypatch.setenv("PSMC_B200_ADAPT", "1")   # experimental, off by default
+    N = 64
+    m = make_model(oracle, N, seed=41)
+    seqs = _seqs(m, [5000, 1700, 900, 30], seed=42)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=400) as es:
+        es.set_warm(2500)
+        first = None
+        for it in range(7):
+            got = es.run(_model(m))
+            info = es.info()
+            compare_stats(got, want, TOL, N)
+            assert info["fallbacks"] == 0 and info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
+            first = first or got
+        # different overlaps, different chunk-to-warp assignment: same counts to rounding
+        compare_stats(got, first, 1e-11, N)
