@@ -901,7 +901,8 @@ struct ForwardRun {
 	int u_warm;  // the vector of bin u_warm - 1 goes to fwarm_c  (u0 after a warm-up, or never)
 	int u_boost; // boosts of bins >= u_boost enter the log-likelihood
 	int kq, ubase, wlast, tpend, mystart;
-	uint32_t word, wnext;
+	uint32_t word, wnext, wnext2;
+	double *prow, *psc; // where the row / scale factor of the bin finished by the next store-phase step go (advance one bin per step)
 
 	__device__ __forceinline__ ForwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_,
 	                                      const uint32_t *__restrict__ obs_, double *__restrict__ fhat_, double *__restrict__ sc_,
@@ -931,16 +932,19 @@ struct ForwardRun {
 	__device__ __forceinline__ void step(int t)
 	{
 		const int u = ubase + t;
-		if ((u & 15) == 0) { // next packed word (indices clamped to the sequence, so idle groups read legal words too)
-			word = wnext;
-			wnext = __ldg(obs + ch.ow0 + min(max((u >> 4) + 1, 0), wlast));
+		if ((u & 15) == 0) { // next packed word; fetched TWO words ahead, so that nothing waits for the load (indices clamped
+			word = wnext;    // to the sequence: idle groups read legal words too)
+			wnext = wnext2;
+			wnext2 = __ldg(obs + ch.ow0 + min(max((u >> 4) + 2, 0), wlast));
 		}
 		const int x = (word >> ((u & 15) * 2)) & 3;
 		double c0, c1;
 		emis_coef(x, c0, c1);
 		c0 *= qc;
 		c1 *= qc;
-		if (BOOK) {
+		double out[SPL];
+		semisep2<SPL, G>(g, M.W, M.Z, M.U, M.V, M.D, ds, out);
+		if (BOOK) { // (written after the scan so that the scheduler issues the scan's shuffles first and this reduction in their shadow)
 			const double S1 = gsum<G>(ps); // = S_{u-1}
 			const double inv1 = fast_rcp(S1);
 			const bool st_f = u - 1 >= u_store, st_w = u == u_warm;
@@ -948,9 +952,11 @@ struct ForwardRun {
 				double fn[SPL];
 #pragma unroll
 				for (int i = 0; i < SPL; ++i) fn[i] = g[i] * inv1;
-				store_vec<SPL>(st_f ? fhat + ((size_t)ch.gb0 + (u - 1 - u0)) * NP + s0 : fwarm_c + s0, fn);
+				store_vec<SPL>(st_f ? prow : fwarm_c + s0, fn);
 			}
-			if (st_f && gl == 0) sc[ch.gb0 + (u - 1 - u0)] = S1 * inv_prev * rq_cur;
+			if (st_f && gl == 0) *psc = S1 * inv_prev * rq_cur;
+			prow += NP;
+			psc += 1;
 			if (u == u_first) Sstart = S1;
 			const bool boosted = qc != 1.0;
 			rq_cur = boosted ? PSMC_BOOST_LOW : 1.0;
@@ -960,8 +966,6 @@ struct ForwardRun {
 		} else {
 			qc = 1.0; // (the warm-up phase decides once per block of 16 bins, see run)
 		}
-		double out[SPL];
-		semisep2<SPL, G>(g, M.W, M.Z, M.U, M.V, M.D, ds, out);
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) g[i] = out[i] * fma(c1, M.e0[i], c0);
 		ps = local_sum<SPL>(g);
@@ -1007,6 +1011,7 @@ struct ForwardRun {
 		// (as if bin ubase-1 had just been processed: the first step shifts if ubase starts a word)
 		word = __ldg(obs + ch.ow0 + min(max((ubase - 1) >> 4, 0), wlast));
 		wnext = __ldg(obs + ch.ow0 + min(max(((ubase - 1) >> 4) + 1, 0), wlast));
+		wnext2 = __ldg(obs + ch.ow0 + min(max(((ubase - 1) >> 4) + 2, 0), wlast));
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) g[i] = f[i];
 		ps = local_sum<SPL>(g);
@@ -1022,6 +1027,11 @@ struct ForwardRun {
 			for (; t < tstop; ++t) step<false>(t);
 		}
 		qc = 1.0;
+		{ // integer arithmetic: for idle groups the address lies outside the buffers until their first stored bin (never dereferenced)
+			const long long row0 = (long long)ch.gb0 + ((long long)ubase + t - 1 - u0);
+			prow = (double *)((char *)fhat + (row0 * NP + s0) * (long long)sizeof(double));
+			psc = (double *)((char *)sc + row0 * (long long)sizeof(double));
+		}
 		while (t < trips) { // store phase
 			if (t == tpend) start_due(t, f, inv_before);
 			const int tstop = min(trips, tpend);
@@ -1056,6 +1066,190 @@ __device__ __forceinline__ double forward_chunk2(const Chunk &ch, bool valid, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// FP32 pre-warm-up.  An overlap only has to deliver a start vector that is exact to 1e-12 AFTER its last few thousand
+// bins; what happens in its early part is forgotten geometrically.  So the early part runs in FP32 (one SHFL per
+// value instead of two, FFMA at full rate and 4 cycles of latency instead of DFMA at half rate and 9) in its own short
+// kernel, and the FP64 overlap of the forward / backward warm-up kernel starts from its result instead of from the
+// stationary vector.  FP32 leaves a relative error of ~1e-6 in the vector; the FP64 part contracts it like any other
+// start error (the certificate decides, as always).  8-lane groups only (NP <= 64).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DualScan8T { // DualScan<8> in the scalar type T
+	bool h0, h1, h2;
+	T u0, u1, u2, d0, d1, d2;
+	__device__ __forceinline__ void init(int gl)
+	{
+		h0 = (gl & 1) != 0; h1 = (gl & 2) != 0; h2 = (gl & 4) != 0;
+		u0 = h0 ? T(1) : T(0); u1 = h1 ? T(1) : T(0); u2 = h2 ? T(1) : T(0);
+		d0 = T(1) - u0; d1 = T(1) - u1; d2 = T(1) - u2;
+	}
+	__device__ __forceinline__ void run(T tp, T ts, T &P, T &S) const
+	{
+		const T s0 = h0 ? ts : tp, s1 = h1 ? ts : tp, s2 = h2 ? ts : tp;
+		const T r1 = __shfl_xor_sync(FULLMASK, s0, 1, 8);
+		const T r2 = __shfl_xor_sync(FULLMASK, s1, 2, 8), r3 = __shfl_xor_sync(FULLMASK, s1, 3, 8);
+		const T r4 = __shfl_xor_sync(FULLMASK, s2, 4, 8), r5 = __shfl_xor_sync(FULLMASK, s2, 5, 8);
+		const T r6 = __shfl_xor_sync(FULLMASK, s2, 6, 8), r7 = __shfl_xor_sync(FULLMASK, s2, 7, 8);
+		const T q1 = r2 + r3, q2 = (r4 + r5) + (r6 + r7);
+		P = fma(u2, q2, fma(u1, q1, u0 * r1));
+		S = fma(d2, q2, fma(d1, q1, d0 * r1));
+	}
+};
+template <typename T, int SPL>
+__device__ __forceinline__ void local_prefix_t(const T (&a)[SPL], T (&lp)[SPL], T &tot)
+{
+	T t = T(0);
+	if (SPL == 8) {
+		const T p01 = a[0] + a[1], p23 = a[2] + a[3], p45 = a[4] + a[5], p67 = a[6] + a[7];
+		const T q03 = p01 + p23, q47 = p45 + p67, q05 = q03 + p45;
+		lp[0] = T(0); lp[1] = a[0]; lp[2] = p01; lp[3] = p01 + a[2];
+		lp[4] = q03; lp[5] = q03 + a[4]; lp[6] = q05; lp[7] = q05 + a[6];
+		tot = q03 + q47;
+		return;
+	}
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		lp[i] = t;
+		t += a[i];
+	}
+	tot = t;
+}
+template <typename T, int SPL>
+__device__ __forceinline__ T local_sum_t(const T (&a)[SPL])
+{
+	T t = T(0);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) t += a[i];
+	return t;
+}
+template <typename T>
+__device__ __forceinline__ T gsum8_t(T t)
+{
+#pragma unroll
+	for (int d = 4; d > 0; d >>= 1) t += __shfl_xor_sync(FULLMASK, t, d, 8);
+	return t;
+}
+// out[i] = D[i] x[i] + pc[i] * sum_{j<i} pm[j] x[j] + sc[i] * sum_{j>i} sm[j] x[j]  (semisep2 in the scalar type T, 8 lanes)
+template <typename T, int SPL>
+__device__ __forceinline__ void semisep2_t(const T (&x)[SPL], const T (&pm)[SPL], const T (&pc)[SPL], const T (&sm)[SPL],
+                                           const T (&sc)[SPL], const T (&D)[SPL], const DualScan8T<T> &ds, T (&out)[SPL])
+{
+	T a[SPL], c[SPL], r[SPL], lp[SPL], lr[SPL], tp, ts, P, S;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		a[i] = x[i] * pm[i];
+		c[i] = x[i] * sm[i];
+		r[SPL - 1 - i] = c[i];
+	}
+	local_prefix_t<T, SPL>(a, lp, tp);
+	local_prefix_t<T, SPL>(r, lr, ts); // suffix sums = prefix sums of the reversed array
+	ds.run(tp, ts, P, S);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		T base = D[i] * x[i];
+		if (i > 0) base = fma(pc[i], lp[i], base);
+		if (i < SPL - 1) base = fma(sc[i], lr[SPL - 1 - i], base);
+		out[i] = fma(sc[i], S, fma(pc[i], P, base));
+	}
+}
+
+// DIR 0: for every forward chunk whose FP64 overlap [u0 - warm64, u0) does not reach the start of its sequence, the forward
+//        vector of bin u0 - warm64 - 1 from warm32 bins further left (sum-normalised, as doubles) -> start[c].
+// DIR 1: for every backward chunk whose FP64 overlap (ulast, ulast + warm64] does not reach the end of its sequence, the
+//        direction of b at bin ulast + warm64 from warm32 bins further right -> start[c].
+// Same loop structure as the FP64 warm-up (groups aligned at the end, late starts between 16-bin blocks, boosts).
+template <int SPL, int DIR>
+__global__ void __launch_bounds__(128) k_prewarm(const Chunk *__restrict__ chunks, int n_chunks, const uint32_t *__restrict__ obs,
+                                                 const double *__restrict__ model, int warm64, int warm32, double *__restrict__ start)
+{
+	typedef float T;
+	constexpr int G = 8, NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	T cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], v[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = (T)model[M_U * NP + s0 + i];
+		cV[i] = (T)model[M_V * NP + s0 + i];
+		cW[i] = (T)model[M_W * NP + s0 + i];
+		cZ[i] = (T)model[M_Z * NP + s0 + i];
+		cD[i] = (T)model[M_D * NP + s0 + i];
+		e0[i] = (T)model[M_E0 * NP + s0 + i];
+		v[i] = DIR == 0 ? (T)model[M_A0 * NP + s0 + i] : T(1);
+	}
+	const int ulast = ch.u0 + ch.len - 1;
+	// bins processed: DIR 0: ua .. ub ascending (ub = u0 - warm64 - 1);  DIR 1: ua .. ub descending (ub = ulast + warm64 + 1)
+	bool need;
+	int ua, ub;
+	if (DIR == 0) {
+		need = id.valid && !(ch.flags & CH_FIRST) && ch.u0 - warm64 > 0;
+		ub = ch.u0 - warm64 - 1;
+		ua = max(0, ub - warm32 + 1);
+	} else {
+		need = id.valid && !(ch.flags & CH_LAST) && ulast + warm64 < ch.Lseq - 1;
+		ub = ulast + warm64 + 1;
+		ua = min(ch.Lseq - 1, ub + warm32 - 1);
+	}
+	const int mytrips = need ? (DIR == 0 ? ub - ua + 1 : ua - ub + 1) : 0;
+	const int trips = warp_trips(mytrips);
+	const int mystart = mytrips > 0 ? trips - mytrips : INT_MAX;
+	int tpend = warp_min_i(mystart);
+	const int wlast = (ch.Lseq - 1) >> 4;
+	const int ufirst = DIR == 0 ? ub - trips + 1 : ub + trips - 1; // bin of step 0 (may lie outside the sequence: clamped words)
+	const int uprev = DIR == 0 ? ufirst - 1 : ufirst + 1;          // as if this bin had just been processed
+	uint32_t word = __ldg(obs + ch.ow0 + min(max(uprev >> 4, 0), wlast));
+	uint32_t wnext = __ldg(obs + ch.ow0 + min(max((uprev >> 4) + (DIR == 0 ? 1 : -1), 0), wlast));
+	DualScan8T<T> ds;
+	ds.init(gl);
+	T g[SPL], q = T(1);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) g[i] = v[i];
+	int t = 0;
+	while (t < trips) {
+		if (t == tpend) { // warp-uniform, rare
+			if (mystart == t) {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) g[i] = v[i];
+			}
+			tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
+		}
+		const int tstop = min(min(trips, tpend), (t & ~15) + 16);
+		q = (gsum8_t<T>(local_sum_t<T, SPL>(g)) < T(9.094947e-13)) ? T(1.0995116e12) : T(1); // 2^-40 / 2^40
+		for (; t < tstop; ++t) {
+			const int u = DIR == 0 ? ufirst + t : ufirst - t;
+			if ((u & 15) == (DIR == 0 ? 0 : 15)) {
+				word = wnext;
+				wnext = __ldg(obs + ch.ow0 + min(max((u >> 4) + (DIR == 0 ? 1 : -1), 0), wlast));
+			}
+			const int x = (word >> ((u & 15) * 2)) & 3;
+			const T c0 = (x == 0 ? T(0) : T(1)) * q, c1 = (x == 0 ? T(1) : (x == 1 ? T(-1) : T(0))) * q;
+			q = T(1);
+			T out[SPL];
+			if (DIR == 0) {
+				semisep2_t<T, SPL>(g, cW, cZ, cU, cV, cD, ds, out);
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) g[i] = out[i] * fma(c1, e0[i], c0);
+			} else {
+				T h[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) h[i] = fma(c1, e0[i], c0) * g[i];
+				semisep2_t<T, SPL>(h, cV, cU, cZ, cW, cD, ds, g);
+			}
+		}
+	}
+	const T tot = gsum8_t<T>(local_sum_t<T, SPL>(g));
+	if (need) {
+		const double inv = 1.0 / (double)tot;
+		double o[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) o[i] = fmax((double)g[i] * inv, 1e-300); // (a flushed component restarts positive)
+		store_vec<SPL>(start + (size_t)c * NP + s0, o);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: forward.  One lane group per chunk.
 //   warm == 0 : the exact start vector comes from the boundary chain (vstart, transfer mode).
 //   warm  > 0 : the group starts `warm` bins to the LEFT of its chunk from the stationary vector, runs
@@ -1067,11 +1261,13 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                  const double *__restrict__ vstart, int warm, int use_prev, double *__restrict__ fhat,
                                                  double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm,
-                                                 const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of)
+                                                 const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of,
+                                                 const double *__restrict__ pre_start)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
 	if (!__any_sync(FULLMASK, id.valid)) return;
+	// pre_start: start vectors of the overlaps from the FP32 pre-warm-up (k_prewarm), nullptr = stationary start.
 	// order: chunks sorted by their number of steps, so that the groups of a warp finish together (adaptive overlaps);
 	// warm_of: this chunk's own overlap (nullptr: `warm` for every chunk)
 	const int c = order ? order[id.c] : id.c, gl = id.gl, s0 = gl * SPL;
@@ -1088,6 +1284,8 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 			const double *row = fhat + ((size_t)ch.gb0 - (size_t)(ch.u0 - ubeg) - 1) * NP + s0;
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) f[i] = fmax(row[i], 1e-300);
+		} else if (pre_start && ubeg > 0) {
+			load_vec<SPL>(pre_start + (size_t)c * NP + s0, f);
 		} else {
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
@@ -1505,7 +1703,8 @@ template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__ chunks, int n_chunks,
                                                        const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                        int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev,
-                                                       const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of)
+                                                       const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of,
+                                                       const double *__restrict__ pre_start)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
@@ -1521,6 +1720,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
 	if (warm_of) warm = min(warm_of[c], warm);
 	int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
+	if (pre_start && !is_last && ulast + warm < ch.Lseq - 1) load_vec<SPL>(pre_start + (size_t)c * NP + s0, beta); // (k_prewarm, same condition)
 	if (bsave_prev && !is_last) {
 		// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin
 		// min(ulast + warm, last bin of the right neighbour) -- see usave in k_backward
@@ -1546,6 +1746,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 		// the sequence so that idle groups read legal words too (initialised as if bin ufirst+1 had just been processed)
 		uint32_t word = __ldg(obs + ch.ow0 + min(max((ufirst + 1) >> 4, 0), wlast));
 		uint32_t wprev = __ldg(obs + ch.ow0 + min(max(((ufirst + 1) >> 4) - 1, 0), wlast));
+		uint32_t wprev2 = __ldg(obs + ch.ow0 + min(max(((ufirst + 1) >> 4) - 2, 0), wlast)); // two words ahead: nothing waits for the load
 		double q = 1.0, bc[SPL];
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
@@ -1564,7 +1765,8 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 				const int u = ufirst - t; // bin whose emission enters; the step yields the direction of bin u-1
 				if ((u & 15) == 15) {
 					word = wprev;
-					wprev = __ldg(obs + ch.ow0 + min(max((u >> 4) - 1, 0), wlast));
+					wprev = wprev2;
+					wprev2 = __ldg(obs + ch.ow0 + min(max((u >> 4) - 2, 0), wlast));
 				}
 				const int x = (word >> ((u & 15) * 2)) & 3;
 				double g[SPL], c0, c1;
@@ -1947,6 +2149,8 @@ struct psmc_b200_ctx {
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
 	int side_order = 0;         // PSMC_B200_SIDE_ORDER, see launch_warm
+	int warm32 = 0, warm32_b = 0; // bins of FP32 pre-warm-up in front of the FP64 overlaps (PSMC_B200_WARM32 / _WARM32_BWD; 0 = none)
+	double *d_pre_f = nullptr, *d_pre_b = nullptr; // its results: start vectors of the forward / backward overlaps
 	bool adapt = false;         // adaptive per-boundary overlaps (PSMC_B200_ADAPT=1; measured on B200: no gain -- the kernels' duration is set by
 	                            // the slowest boundaries either way and the extra failures while adapting cost more than the shorter warm-ups save)
 	int adapt_max_chunks = 16384; // (k_order ranks in O(n^2))
@@ -2024,7 +2228,7 @@ static void free_plan(psmc_b200_ctx *c)
 	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b,
 	              (void **)&c->d_pred[0], (void **)&c->d_pred[1], (void **)&c->d_pred_b[0], (void **)&c->d_pred_b[1],
 	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b,
-	              (void **)&c->d_warm_f, (void **)&c->d_warm_b, (void **)&c->d_order_f, (void **)&c->d_order_b, (void **)&c->d_tight_f, (void **)&c->d_tight_b};
+	              (void **)&c->d_warm_f, (void **)&c->d_warm_b, (void **)&c->d_order_f, (void **)&c->d_order_b, (void **)&c->d_tight_f, (void **)&c->d_tight_b, (void **)&c->d_pre_f, (void **)&c->d_pre_b};
 	for (auto q : p) { cudaFree(*q); *q = nullptr; }
 	c->bytes_total -= c->bytes_plan;
 	c->bytes_plan = 0;
@@ -2276,6 +2480,8 @@ static int replan(psmc_b200_ctx *c)
 		alloc((void **)&c->d_bsub, sizeof(double) * (size_t)csb * NP);
 		alloc((void **)&c->d_llsub, sizeof(double) * (size_t)cs);
 		alloc((void **)&c->d_partsub, sizeof(double) * (size_t)csb * S_COUNT * NP);
+		alloc((void **)&c->d_pre_f, sizeof(double) * (size_t)cc * NP);
+		alloc((void **)&c->d_pre_b, sizeof(double) * (size_t)cb * NP);
 		alloc((void **)&c->d_warm_f, sizeof(int32_t) * (size_t)cc);
 		alloc((void **)&c->d_warm_b, sizeof(int32_t) * (size_t)cb);
 		alloc((void **)&c->d_order_f, sizeof(int32_t) * (size_t)cc);
@@ -2359,6 +2565,10 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	{
 		const char *env = getenv("PSMC_B200_GEN");
 		if (env && atoi(env) == 1) c->gen = 1;
+		env = getenv("PSMC_B200_WARM32");
+		if (env && atoi(env) >= 0) c->warm32 = c->warm32_b = atoi(env);
+		env = getenv("PSMC_B200_WARM32_BWD");
+		if (env && atoi(env) >= 0) c->warm32_b = atoi(env);
 		env = getenv("PSMC_B200_ADAPT");
 		if (env) c->adapt = atoi(env) != 0;
 		env = getenv("PSMC_B200_SIDE_ORDER");
@@ -2585,12 +2795,18 @@ struct Gen2 {
 	static constexpr bool BWD_OK = NP <= 64;
 };
 
+// FP32 pre-warm-up (k_prewarm): generation 2, 8-lane groups (NP <= 64), PSMC_B200_WARM32 > 0
+template <int NP>
+static bool prewarm_on(const psmc_b200_ctx *c) { return NP <= 64 && c->gen == 2 && c->g2_fwd == 8 && c->g2_bww == 8 && c->warm32 > 0 && c->d_pre_f != nullptr; }
+
 template <int NP>
 static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
 	const bool ad = c->adapt && warm > 0 && !use_prev && c->n_chunks <= c->adapt_max_chunks;
-#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, ad ? c->d_order_f : nullptr, ad ? c->d_warm_f : nullptr)
+	const bool pre = prewarm_on<NP>(c) && warm > 0 && !use_prev && !ad;
+	if (pre) LAUNCH((k_prewarm<(NP <= 64 ? NP / 8 : 8), 0>), blocks_for(c->n_chunks, 8), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, warm, c->warm32, c->d_pre_f);
+#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, ad ? c->d_order_f : nullptr, ad ? c->d_warm_f : nullptr, pre ? c->d_pre_f : nullptr)
 	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWD(16, 2);
 	else if (c->gen == 2) FWD(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8, 1);
@@ -2631,7 +2847,9 @@ template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
 	const bool ad = c->adapt && !use_prev && c->n_chunks_b <= c->adapt_max_chunks;
-#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr, ad ? c->d_order_b : nullptr, ad ? c->d_warm_b : nullptr)
+	const bool pre = prewarm_on<NP>(c) && !use_prev && !ad;
+	if (pre) LAUNCH((k_prewarm<(NP <= 64 ? NP / 8 : 8), 1>), blocks_for(c->n_chunks_b, 8), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->warm32_b, c->d_pre_b);
+#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr, ad ? c->d_order_b : nullptr, ad ? c->d_warm_b : nullptr, pre ? c->d_pre_b : nullptr)
 	if (c->gen == 2 && (c->g2_bww == 16 || NP > 64)) BWW(16, 2);
 	else if (c->gen == 2) BWW(8, 2);
 	else if (c->g_bww == 8 && NP / 8 <= 8) BWW(8, 1);
@@ -2804,7 +3022,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	if (adf) LAUNCH((k_order), (c->n_chunks + 255) / 256, 256, st, c->d_chunks, c->n_chunks, c->d_warm_f, c->warm_len, CH_FIRST, c->d_order_f);
 	if (adb) LAUNCH((k_order), (c->n_chunks_b + 255) / 256, 256, st, c->d_chunks_b, c->n_chunks_b, c->d_warm_b, cap_b, CH_LAST, c->d_order_b);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0) + (adf ? 1 : 0) + (adb ? 1 : 0);
+	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0) + (adf ? 1 : 0) + (adb ? 1 : 0) + ((prewarm_on<NP>(c) && !hot && !adf) ? 1 : 0) + ((prewarm_on<NP>(c) && !hot && !adb) ? 1 : 0);
 	c->pred_cur ^= 1;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
