@@ -18,21 +18,22 @@ static double now_ms(void)
 	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-typedef struct { psmch_em_t *em; int cnt; } aux_t;
+typedef struct { psmch_em_t *em; psmch_model_t *m; } aux_t;
 
+/* a pure function of the point (the model instance is scratch): the caller and the speculative helper use one each */
 static double objective(int n, double *x, void *data)
 {
 	aux_t *a = (aux_t*)data;
 	psmch_em_t *em = a->em;
+	psmch_model_t *m = a->m;
 	int i;
-	++a->cnt;
-	for (i = 0; i < n; ++i) em->model.params[i] = fabs(x[i]);
+	for (i = 0; i < n; ++i) m->params[i] = fabs(x[i]);
 	if (em->exact_mstep) {
-		psmch_model_update(&em->sp, em->model.params, &em->model);
-		return -psmch_Q(&em->model, &em->counts);
+		psmch_model_update(&em->sp, m->params, m);
+		return -psmch_Q(m, &em->counts);
 	}
-	psmch_model_update_fast(&em->sp, em->model.params, &em->model); /* exp/log through libmvec: a few ulp from the scalar path */
-	return -psmch_Q_fast(&em->model, &em->counts);
+	psmch_model_update_fast(&em->sp, m->params, m); /* exp/log through libmvec: a few ulp from the scalar path */
+	return -psmch_Q_fast(m, &em->counts);
 }
 
 /* parameter space, initial parameters (core.c:32-49) and the first model; sq gives sum_n / sum_L only */
@@ -67,6 +68,7 @@ static int init_model(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t 
 	}
 	psmch_model_update(&em->sp, em->model.params, &em->model);
 	em->exact_mstep = getenv("PSMC_B200_EXACT_MSTEP") != 0; /* scalar libm in every trial evaluation */
+	em->spec_mstep = !(getenv("PSMC_B200_MSTEP_SPEC") && atoi(getenv("PSMC_B200_MSTEP_SPEC")) == 0);
 	em->n_seqs = sq->n_seqs;
 	return 0;
 }
@@ -76,6 +78,7 @@ static int init_model(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t 
 int psmch_em_init_shared(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq, psmc_b200_ctx *ctx, double (*rnd)(void))
 {
 	if (init_model(em, o, sq, rnd) != 0) return -1;
+	em->spec_mstep = 0; /* bootstrap workers already occupy the host cores */
 	em->n_gpus = 1;
 	em->ctx[0] = ctx;
 	em->borrowed = 1;
@@ -126,6 +129,7 @@ void psmch_em_free(psmch_em_t *em)
 {
 	int g;
 	for (g = 0; g < em->n_gpus && !em->borrowed; ++g) psmc_b200_destroy(em->ctx[g]);
+	if (em->spec) { psmch_spec_stop(em->spec); psmch_model_free(&em->model_spec); free(em->spec_aux); }
 	psmch_counts_free(&em->counts);
 	psmch_model_free(&em->model);
 	psmch_space_free(&em->sp);
@@ -187,18 +191,33 @@ int psmch_em_set_raw(psmch_em_t *em, const double *raw, int64_t n_seqs_total)
 int psmch_em_mstep(psmch_em_t *em, FILE *fpout)
 {
 	const int N = em->sp.n + 1, np = em->sp.n_params;
-	double *x, sum = 0.0, t1 = now_ms();
+	double *x, *last, sum = 0.0, t1 = now_ms();
 	aux_t aux;
-	int k;
+	int k, n_calls = 0;
 	psmch_Q0(&em->counts);
 	em->lk = em->counts.LL;
 	x = (double*)malloc(sizeof(double) * np);
 	memcpy(x, em->model.params, sizeof(double) * np);
-	aux.em = em; aux.cnt = 0;
+	aux.em = em; aux.m = &em->model;
 	em->Q0 = psmch_Q(&em->model, &em->counts);
-	em->Q1 = -psmch_hooke_jeeves(objective, np, x, &aux, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL);
-	em->hj_calls = aux.cnt;
-	if (fpout) fprintf(fpout, "IT\t%d\n", aux.cnt);
+	if (em->spec_mstep && em->spec == 0) { /* first M-step: start the helper with its own model instance */
+		aux_t *ha = (aux_t*)calloc(1, sizeof(aux_t));
+		if (ha && psmch_model_alloc(&em->model_spec, &em->sp) == 0) {
+			ha->em = em; ha->m = &em->model_spec;
+			em->spec_aux = ha;
+			em->spec = psmch_spec_start(objective, np, ha);
+			if (em->spec == 0) { psmch_model_free(&em->model_spec); free(ha); em->spec_aux = 0; em->spec_mstep = 0; }
+		} else { free(ha); em->spec_mstep = 0; }
+	}
+	last = (double*)malloc(sizeof(double) * np);
+	memcpy(last, x, sizeof(double) * np);
+	if (em->spec) psmch_spec_begin(em->spec);
+	em->Q1 = -psmch_hooke_jeeves_spec(objective, em->spec, np, x, &aux, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL, last, &n_calls);
+	if (em->spec) psmch_spec_end(em->spec);
+	em->hj_calls = n_calls;
+	if (fpout) fprintf(fpout, "IT\t%d\n", n_calls);
+	for (k = 0; k < np; ++k) em->model.params[k] = fabs(last[k]);
+	free(last);
 	free(x);
 	/* the model stays at the LAST EVALUATED trial point (em.c:61-67), recomputed with the scalar bit-reproducible path */
 	psmch_model_update(&em->sp, em->model.params, &em->model);

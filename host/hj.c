@@ -10,22 +10,46 @@ typedef struct {
 	psmch_func_t f;
 	void *data;
 	int n, calls;
+	psmch_spec_t *spec; /* helper thread for the -step point of a probe, or NULL */
+	double *last;       /* the last evaluated point in the order of the sequential search, or NULL */
 } hj_t;
 
-static double eval(hj_t *h, double *x) { ++h->calls; return h->f(h->n, x, h->data); }
+static double eval(hj_t *h, double *x)
+{
+	++h->calls;
+	if (h->last) memcpy(h->last, x, sizeof(double) * h->n);
+	return h->f(h->n, x, h->data);
+}
 
-/* probe each coordinate: +step, else -step, else stay (kmin.c:48-66) */
+/* probe each coordinate: +step, else -step, else stay (kmin.c:48-66).  With a helper, the -step point is evaluated
+ * concurrently and counted only if the sequential search would have evaluated it. */
 static double probe(hj_t *h, double *x, double fbest, double *step)
 {
 	int k;
 	for (k = 0; k < h->n; ++k) {
 		double v;
+		if (h->spec) {
+			const double xk = x[k];
+			x[k] = (xk + step[k]) + ((0.0 - step[k]) + (0.0 - step[k])); /* the -step point, formed exactly as below */
+			psmch_spec_submit(h->spec, x);
+			x[k] = xk;
+		}
 		x[k] += step[k];
 		v = eval(h, x);
-		if (v < fbest) { fbest = v; continue; }
+		if (v < fbest) {
+			fbest = v;
+			if (h->spec) psmch_spec_wait(h->spec); /* discard */
+			continue;
+		}
 		step[k] = 0.0 - step[k];
 		x[k] += step[k] + step[k];
-		v = eval(h, x);
+		if (h->spec) {
+			++h->calls;
+			if (h->last) memcpy(h->last, x, sizeof(double) * h->n);
+			v = psmch_spec_wait(h->spec);
+		} else {
+			v = eval(h, x);
+		}
 		if (v < fbest) fbest = v;
 		else x[k] -= step[k];
 	}
@@ -34,11 +58,17 @@ static double probe(hj_t *h, double *x, double fbest, double *step)
 
 double psmch_hooke_jeeves(psmch_func_t f, int n, double *x, void *data, double r, double eps, int max_calls)
 {
+	return psmch_hooke_jeeves_spec(f, 0, n, x, data, r, eps, max_calls, 0, 0);
+}
+
+double psmch_hooke_jeeves_spec(psmch_func_t f, psmch_spec_t *spec, int n, double *x, void *data, double r, double eps, int max_calls,
+                               double *last, int *n_calls)
+{
 	hj_t h;
 	double *y = (double*)calloc(n, sizeof(double)), *step = (double*)calloc(n, sizeof(double));
 	double fx, fy, radius = r;
 	int k, done = 0;
-	h.f = f; h.data = data; h.n = n; h.calls = 0;
+	h.f = f; h.data = data; h.n = n; h.calls = 0; h.spec = spec; h.last = last;
 	for (k = 0; k < n; ++k) {
 		step[k] = fabs(x[k]) * r;
 		if (step[k] == 0) step[k] = r;
@@ -69,5 +99,6 @@ double psmch_hooke_jeeves(psmch_func_t f, int n, double *x, void *data, double r
 		} else done = 1;
 	}
 	free(y); free(step);
+	if (n_calls) *n_calls = h.calls;
 	return fy;
 }

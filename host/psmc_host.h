@@ -114,6 +114,17 @@ double psmch_Q_fast(const psmch_model_t *m, const psmch_counts_t *c); /* same va
 /* ---- Hooke-Jeeves ---------------------------------------------------------------------------- */
 typedef double (*psmch_func_t)(int n, double *x, void *data);
 double psmch_hooke_jeeves(psmch_func_t f, int n, double *x, void *data, double r, double eps, int max_calls);
+/* helper thread that evaluates the -step point of every probe concurrently (spec.c); same search path and call count */
+typedef struct psmch_spec psmch_spec_t;
+psmch_spec_t *psmch_spec_start(psmch_func_t f, int n, void *data);
+void   psmch_spec_begin(psmch_spec_t *s);
+void   psmch_spec_end(psmch_spec_t *s);
+void   psmch_spec_submit(psmch_spec_t *s, const double *x);
+double psmch_spec_wait(psmch_spec_t *s);
+void   psmch_spec_stop(psmch_spec_t *s);
+/* last (n doubles or NULL): the last evaluated point in the order of the sequential search; n_calls: evaluations counted */
+double psmch_hooke_jeeves_spec(psmch_func_t f, psmch_spec_t *spec, int n, double *x, void *data, double r, double eps, int max_calls,
+                               double *last, int *n_calls);
 #define PSMCH_HJ_RADIUS 0.5
 #define PSMCH_HJ_EPS 1e-7
 #define PSMCH_HJ_MAXCALL 50000
@@ -150,6 +161,10 @@ typedef struct {
 	int hj_calls;
 	int borrowed;    /* ctx[0] belongs to the caller (bootstrap replicates share one context per GPU slot) */
 	int exact_mstep; /* PSMC_B200_EXACT_MSTEP: trial evaluations with scalar libm instead of libmvec */
+	int spec_mstep;  /* speculative second evaluator thread in the M-step (PSMC_B200_MSTEP_SPEC=0 disables; off for bootstrap workers) */
+	psmch_model_t model_spec; /* the helper's own model instance */
+	psmch_spec_t *spec;
+	void *spec_aux;
 	double t_estep_ms, t_mstep_ms; /* wall time of the last iteration */
 } psmch_em_t;
 

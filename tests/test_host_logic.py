@@ -137,3 +137,22 @@ def test_resampler_properties(tmp_path):
         assert abs(sum(got) - sum(lens)) <= max(lens)
         assert L.psmch_py_read_sum(h, 0) == sum(got)          # all bins are informative in this input
         L.psmch_py_read_free(h)
+
+
+@pytest.mark.parametrize("npz", ["estep_23.npz", "estep_64.npz"])
+def test_speculative_mstep_is_the_sequential_search(npz, monkeypatch):
+    """host/spec.c: the -step point of every Hooke-Jeeves probe is evaluated on a helper thread while the caller evaluates the
+    +step point.  Same search path, same counted calls, same last evaluated point, same optimum -- bit for bit."""
+    import time
+    from psmc_b200 import host
+    d = np.load(os.path.join(G, npz))
+    pat = str(d["pattern"])
+    out = {}
+    for spec in ("0", "1"):
+        monkeypatch.setenv("PSMC_B200_MSTEP_SPEC", spec)
+        t0 = time.perf_counter()
+        out[spec] = host.mstep(pat, d["params"], d["E"], A=d["A"])
+        out[spec]["t"] = time.perf_counter() - t0
+    a, b = out["0"], out["1"]
+    assert a["calls"] == b["calls"] and a["Q1"] == b["Q1"]
+    assert np.array_equal(a["params"], b["params"])

@@ -168,3 +168,20 @@ def test_emulated_adaptive_overlaps_over_iterations(oracle, emu_plain, monkeypat
             first = first or got
         # different overlaps, different chunk-to-warp assignment: same counts to rounding
         compare_stats(got, first, 1e-11, N)
+
+
+@pytest.mark.parametrize("N", [23, 64])
+def test_emulated_fp32_prewarm(oracle, emu_plain, monkeypatch, N):
+    """experimental option: the early part of every overlap in FP32 (k_prewarm); the FP64 part and the certificate make
+    the result exact all the same"""
+    from psmc_b200 import EStep
+    monkeypatch.setenv("PSMC_B200_WARM32", "2000")
+    m = make_model(oracle, N, seed=51)
+    seqs = _seqs(m, [7000, 2100, 40], seed=52)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=800) as es:
+        es.set_warm(1200)
+        got = es.run(_model(m))
+        info = es.info()
+    compare_stats(got, want, TOL, N)
+    assert info["fallbacks"] == 0 and info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
