@@ -9,6 +9,7 @@
 #include <string.h>
 #include <math.h>
 #include <time.h>
+#include <unistd.h>
 #include "psmc_host.h"
 
 static double now_ms(void)
@@ -68,7 +69,13 @@ static int init_model(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t 
 	}
 	psmch_model_update(&em->sp, em->model.params, &em->model);
 	em->exact_mstep = getenv("PSMC_B200_EXACT_MSTEP") != 0; /* scalar libm in every trial evaluation */
-	em->spec_mstep = !(getenv("PSMC_B200_MSTEP_SPEC") && atoi(getenv("PSMC_B200_MSTEP_SPEC")) == 0);
+	{	/* helper threads of the M-step (spec.c): 3 if every process on this node can have 4 cores, else 1; PSMC_B200_MSTEP_SPEC=0/1/3 overrides */
+		const char *env = getenv("PSMC_B200_MSTEP_SPEC"), *lws = getenv("LOCAL_WORLD_SIZE");
+		const long cores = sysconf(_SC_NPROCESSORS_ONLN);
+		const int procs = (lws && atoi(lws) > 0) ? atoi(lws) : 1;
+		em->spec_mstep = cores / procs >= 4 ? 3 : (cores / procs >= 2 ? 1 : 0);
+		if (env) em->spec_mstep = atoi(env) >= 3 ? 3 : (atoi(env) >= 1 ? 1 : 0);
+	}
 	em->n_seqs = sq->n_seqs;
 	return 0;
 }
@@ -129,7 +136,7 @@ void psmch_em_free(psmch_em_t *em)
 {
 	int g;
 	for (g = 0; g < em->n_gpus && !em->borrowed; ++g) psmc_b200_destroy(em->ctx[g]);
-	if (em->spec) { psmch_spec_stop(em->spec); psmch_model_free(&em->model_spec); free(em->spec_aux); }
+	for (g = 0; g < em->n_spec; ++g) { psmch_spec_stop(em->spec[g]); psmch_model_free(&em->model_spec[g]); free(em->spec_aux[g]); }
 	psmch_counts_free(&em->counts);
 	psmch_model_free(&em->model);
 	psmch_space_free(&em->sp);
@@ -200,20 +207,22 @@ int psmch_em_mstep(psmch_em_t *em, FILE *fpout)
 	memcpy(x, em->model.params, sizeof(double) * np);
 	aux.em = em; aux.m = &em->model;
 	em->Q0 = psmch_Q(&em->model, &em->counts);
-	if (em->spec_mstep && em->spec == 0) { /* first M-step: start the helper with its own model instance */
+	while (em->n_spec < em->spec_mstep) { /* first M-step: start the helpers, each with its own model instance */
+		const int j = em->n_spec;
 		aux_t *ha = (aux_t*)calloc(1, sizeof(aux_t));
-		if (ha && psmch_model_alloc(&em->model_spec, &em->sp) == 0) {
-			ha->em = em; ha->m = &em->model_spec;
-			em->spec_aux = ha;
-			em->spec = psmch_spec_start(objective, np, ha);
-			if (em->spec == 0) { psmch_model_free(&em->model_spec); free(ha); em->spec_aux = 0; em->spec_mstep = 0; }
-		} else { free(ha); em->spec_mstep = 0; }
+		if (ha == 0 || psmch_model_alloc(&em->model_spec[j], &em->sp) != 0) { free(ha); em->spec_mstep = em->n_spec >= 1 ? 1 : 0; break; }
+		ha->em = em; ha->m = &em->model_spec[j];
+		em->spec_aux[j] = ha;
+		em->spec[j] = psmch_spec_start(objective, np, ha);
+		if (em->spec[j] == 0) { psmch_model_free(&em->model_spec[j]); free(ha); em->spec_mstep = em->n_spec >= 1 ? 1 : 0; break; }
+		++em->n_spec;
 	}
 	last = (double*)malloc(sizeof(double) * np);
 	memcpy(last, x, sizeof(double) * np);
-	if (em->spec) psmch_spec_begin(em->spec);
-	em->Q1 = -psmch_hooke_jeeves_spec(objective, em->spec, np, x, &aux, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL, last, &n_calls);
-	if (em->spec) psmch_spec_end(em->spec);
+	for (k = 0; k < em->n_spec; ++k) psmch_spec_begin(em->spec[k]);
+	em->Q1 = -psmch_hooke_jeeves_spec(objective, em->spec, em->n_spec >= 3 ? 3 : (em->n_spec >= 1 ? 1 : 0), np, x, &aux, PSMCH_HJ_RADIUS,
+	                                  PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL, last, &n_calls);
+	for (k = 0; k < em->n_spec; ++k) psmch_spec_end(em->spec[k]);
 	em->hj_calls = n_calls;
 	if (fpout) fprintf(fpout, "IT\t%d\n", n_calls);
 	for (k = 0; k < np; ++k) em->model.params[k] = fabs(last[k]);

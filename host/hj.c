@@ -10,8 +10,9 @@ typedef struct {
 	psmch_func_t f;
 	void *data;
 	int n, calls;
-	psmch_spec_t *spec; /* helper thread for the -step point of a probe, or NULL */
-	double *last;       /* the last evaluated point in the order of the sequential search, or NULL */
+	psmch_spec_t **spec; /* helper threads (spec.c) or NULL */
+	int n_spec;          /* 0, 1 or 3 helpers are used */
+	double *last;        /* the last evaluated point in the order of the sequential search, or NULL */
 } hj_t;
 
 static double eval(hj_t *h, double *x)
@@ -21,54 +22,105 @@ static double eval(hj_t *h, double *x)
 	return h->f(h->n, x, h->data);
 }
 
-/* probe each coordinate: +step, else -step, else stay (kmin.c:48-66).  With a helper, the -step point is evaluated
- * concurrently and counted only if the sequential search would have evaluated it. */
+/* the sequential probe of one coordinate given the two objective values (kmin.c:48-66): +step, else -step, else stay.
+ * Returns 1 if the point moved.  Counts the calls and records the last evaluated point exactly as the sequential search
+ * would have (vb is "evaluated" only if +step failed). */
+static int settle(hj_t *h, double *x, double *fbest, double *step, int k, double va, double vb)
+{
+	x[k] += step[k];
+	++h->calls;
+	if (h->last) memcpy(h->last, x, sizeof(double) * h->n);
+	if (va < *fbest) { *fbest = va; return 1; }
+	step[k] = 0.0 - step[k];
+	x[k] += step[k] + step[k];
+	++h->calls;
+	if (h->last) memcpy(h->last, x, sizeof(double) * h->n);
+	if (vb < *fbest) { *fbest = vb; return 1; }
+	x[k] -= step[k];
+	return 0;
+}
+
+/* x with coordinate k at its -step trial value, formed exactly as the sequential code forms it */
+static void submit_minus(psmch_spec_t *sp, double *x, const double *step, int k)
+{
+	const double xk = x[k];
+	x[k] = (xk + step[k]) + ((0.0 - step[k]) + (0.0 - step[k]));
+	psmch_spec_submit(sp, x);
+	x[k] = xk;
+}
+static void submit_plus(psmch_spec_t *sp, double *x, const double *step, int k)
+{
+	const double xk = x[k];
+	x[k] = xk + step[k];
+	psmch_spec_submit(sp, x);
+	x[k] = xk;
+}
+
+/* probe each coordinate: +step, else -step, else stay (kmin.c:48-66).  Both trial points of a coordinate are known in
+ * advance, and so are those of the NEXT coordinate if this one fails in both directions (the usual case near convergence):
+ * with one helper the -step point is evaluated concurrently, with three helpers also the two points of the next
+ * coordinate.  Speculative values are used only where the sequential search would have evaluated the same point. */
 static double probe(hj_t *h, double *x, double fbest, double *step)
 {
-	int k;
-	for (k = 0; k < h->n; ++k) {
-		double v;
-		if (h->spec) {
-			const double xk = x[k];
-			x[k] = (xk + step[k]) + ((0.0 - step[k]) + (0.0 - step[k])); /* the -step point, formed exactly as below */
-			psmch_spec_submit(h->spec, x);
-			x[k] = xk;
-		}
-		x[k] += step[k];
-		v = eval(h, x);
-		if (v < fbest) {
-			fbest = v;
-			if (h->spec) psmch_spec_wait(h->spec); /* discard */
+	int k = 0;
+	while (k < h->n) {
+		double va, vb;
+		if (h->n_spec == 0) {
+			x[k] += step[k];
+			va = eval(h, x);
+			if (va < fbest) { fbest = va; ++k; continue; }
+			step[k] = 0.0 - step[k];
+			x[k] += step[k] + step[k];
+			vb = eval(h, x);
+			if (vb < fbest) fbest = vb;
+			else x[k] -= step[k];
+			++k;
 			continue;
 		}
-		step[k] = 0.0 - step[k];
-		x[k] += step[k] + step[k];
-		if (h->spec) {
-			++h->calls;
-			if (h->last) memcpy(h->last, x, sizeof(double) * h->n);
-			v = psmch_spec_wait(h->spec);
-		} else {
-			v = eval(h, x);
+		{
+			const int two = h->n_spec >= 3 && k + 1 < h->n;
+			double va2 = 0.0, vb2 = 0.0;
+			submit_minus(h->spec[0], x, step, k);
+			if (two) { /* if coordinate k fails twice, x[k] comes back through this arithmetic (not necessarily bit-identical to xk) */
+				const double xk = x[k], ns = 0.0 - step[k];
+				x[k] = ((xk + step[k]) + (ns + ns)) - ns;
+				submit_plus(h->spec[1], x, step, k + 1);
+				submit_minus(h->spec[2], x, step, k + 1);
+				x[k] = xk;
+			}
+			{ /* the caller's share: +step of coordinate k (not counted here: settle() does the book-keeping) */
+				const double xk = x[k];
+				x[k] = xk + step[k];
+				va = h->f(h->n, x, h->data);
+				x[k] = xk;
+			}
+			vb = psmch_spec_wait(h->spec[0]);
+			if (two) {
+				va2 = psmch_spec_wait(h->spec[1]);
+				vb2 = psmch_spec_wait(h->spec[2]);
+			}
+			if (settle(h, x, &fbest, step, k, va, vb) || !two) { ++k; continue; } /* moved: the next coordinate's points are stale */
+			settle(h, x, &fbest, step, k + 1, va2, vb2);
+			k += 2;
 		}
-		if (v < fbest) fbest = v;
-		else x[k] -= step[k];
 	}
 	return fbest;
 }
 
 double psmch_hooke_jeeves(psmch_func_t f, int n, double *x, void *data, double r, double eps, int max_calls)
 {
-	return psmch_hooke_jeeves_spec(f, 0, n, x, data, r, eps, max_calls, 0, 0);
+	return psmch_hooke_jeeves_spec(f, 0, 0, n, x, data, r, eps, max_calls, 0, 0);
 }
 
-double psmch_hooke_jeeves_spec(psmch_func_t f, psmch_spec_t *spec, int n, double *x, void *data, double r, double eps, int max_calls,
-                               double *last, int *n_calls)
+double psmch_hooke_jeeves_spec(psmch_func_t f, psmch_spec_t **spec, int n_spec, int n, double *x, void *data, double r, double eps,
+                               int max_calls, double *last, int *n_calls)
 {
 	hj_t h;
 	double *y = (double*)calloc(n, sizeof(double)), *step = (double*)calloc(n, sizeof(double));
 	double fx, fy, radius = r;
 	int k, done = 0;
 	h.f = f; h.data = data; h.n = n; h.calls = 0; h.spec = spec; h.last = last;
+	h.n_spec = (spec == 0 || n_spec <= 0) ? 0 : (n_spec >= 3 ? 3 : 1);
 	for (k = 0; k < n; ++k) {
 		step[k] = fabs(x[k]) * r;
 		if (step[k] == 0) step[k] = r;

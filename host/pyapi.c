@@ -202,21 +202,25 @@ int psmch_py_mstep(const char *pattern, double alpha0, double *params, const dou
 	x = (double*)malloc(sizeof(double) * sp.n_params);
 	memcpy(x, params, sizeof(double) * sp.n_params);
 	a.sp = &sp; a.m = &m; a.c = &c; a.cnt = 0; a.fast = getenv("PSMC_B200_EXACT_MSTEP") == 0;
-	{	/* PSMC_B200_MSTEP_SPEC=1: the -step point of every probe on a helper thread (spec.c), as the EM driver does */
-		const int use_spec = getenv("PSMC_B200_MSTEP_SPEC") && atoi(getenv("PSMC_B200_MSTEP_SPEC")) != 0;
-		psmch_model_t m2;
-		maux_t a2 = a;
-		psmch_spec_t *spec = 0;
+	{	/* PSMC_B200_MSTEP_SPEC=1|3: speculative trial points on helper threads (spec.c), as the EM driver does */
+		const int want = getenv("PSMC_B200_MSTEP_SPEC") ? atoi(getenv("PSMC_B200_MSTEP_SPEC")) : 0;
+		psmch_model_t m2[3];
+		maux_t a2[3];
+		psmch_spec_t *spec[3] = {0, 0, 0};
 		double *last = (double*)malloc(sizeof(double) * sp.n_params);
-		int n_calls = 0, i;
-		if (use_spec && psmch_model_alloc(&m2, &sp) == 0) {
-			a2.m = &m2;
-			spec = psmch_spec_start(mobjective, sp.n_params, &a2);
-			if (spec) psmch_spec_begin(spec);
+		int n_calls = 0, i, ns = 0;
+		for (i = 0; i < (want >= 3 ? 3 : (want >= 1 ? 1 : 0)); ++i) {
+			if (psmch_model_alloc(&m2[i], &sp) != 0) break;
+			a2[i] = a; a2[i].m = &m2[i];
+			spec[i] = psmch_spec_start(mobjective, sp.n_params, &a2[i]);
+			if (spec[i] == 0) { psmch_model_free(&m2[i]); break; }
+			psmch_spec_begin(spec[i]);
+			++ns;
 		}
 		memcpy(last, x, sizeof(double) * sp.n_params);
-		res[1] = -psmch_hooke_jeeves_spec(mobjective, spec, sp.n_params, x, &a, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL, last, &n_calls);
-		if (spec) { psmch_spec_end(spec); psmch_spec_stop(spec); psmch_model_free(&m2); }
+		res[1] = -psmch_hooke_jeeves_spec(mobjective, spec, ns >= 3 ? 3 : (ns >= 1 ? 1 : 0), sp.n_params, x, &a, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS,
+		                                  PSMCH_HJ_MAXCALL, last, &n_calls);
+		for (i = 0; i < ns; ++i) { psmch_spec_end(spec[i]); psmch_spec_stop(spec[i]); psmch_model_free(&m2[i]); }
 		res[2] = n_calls;
 		for (i = 0; i < sp.n_params; ++i) m.params[i] = last[i] < 0 ? -last[i] : last[i]; /* the last evaluated point (em.c:61-67) */
 		free(last);
