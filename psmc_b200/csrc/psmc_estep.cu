@@ -459,12 +459,25 @@ __device__ __forceinline__ void prefsuf2(const double (&x)[SPL], const double (&
 // T[c] is stored column-major (column j = 64 consecutive doubles), mantissas only; Tex[c][j] holds
 // the power-of-two exponent of column j.
 // ------------------------------------------------------------------------------------------------
+// Is the operator of sub-chunk s used by the boundary chains (k_chain_subs) under the flag picture `flags`?  Its parent
+// chunk must be flagged; and the sub-chunk at the far end of a chunk (the last one going forward, dir 0; the first one
+// going backward, dir 1) only carries the vector into the NEXT chunk of the run, so it is needed only if that chunk is
+// flagged as well (one operator in eight otherwise computed for nothing).  flags has guard entries at -1 and n.
+__device__ __forceinline__ bool op_needed(const int32_t *__restrict__ flags, const int32_t *__restrict__ parent,
+                                          const int32_t *__restrict__ chunk_sub0, int s, int dir)
+{
+	const int p = parent[s];
+	if (!flags[p]) return false;
+	if (dir == 0) return !(chunk_sub0[p + 1] - 1 == s) || flags[p + 1] != 0;
+	return !(chunk_sub0[p] == s) || flags[p - 1] != 0;
+}
+
 template <int SPL, int G, int COLS>
 __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ chunks, const int32_t *__restrict__ k1_list,
                                                       const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                       double *__restrict__ T, int32_t *__restrict__ Tex, int N,
                                                       const int32_t *__restrict__ flag, int sel, const int32_t *__restrict__ skip,
-                                                      int n_items)
+                                                      int n_items, const int32_t *__restrict__ chunk_sub0, int dir)
 {
 	constexpr int NP = SPL * G;
 	// sel 0: chunk list (transfer mode), one block row per listed chunk.  sel 3: repair rounds of the warm-up mode: `chunks`
@@ -474,7 +487,7 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
 	// operators are already there (computed ahead of time from the previous E-step's failures, see launch_warm).
 	for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
 	const int c = sel == 0 ? k1_list[item] : item;
-	if (sel == 3 && (!flag[k1_list[c]] || (skip && skip[k1_list[c]]))) continue;
+	if (sel == 3 && (!op_needed(flag, k1_list, chunk_sub0, c, dir) || (skip && op_needed(skip, k1_list, chunk_sub0, c, dir)))) continue;
 	const Chunk ch = chunks[c];
 	const int gl = threadIdx.x % G;
 	const int col = blockIdx.y * COLS + threadIdx.x / G;
@@ -2908,7 +2921,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	if (c->n_k1 > 0) {
 		constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 		dim3 grid((unsigned)c->n_k1, NP / COLS);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), grid, COLS * G1, st, c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr, c->n_k1);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), grid, COLS * G1, st, c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr, c->n_k1, nullptr, 0);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[1], st);
@@ -2971,7 +2984,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	const int32_t *pred = c->predict ? c->d_pred[c->pred_cur] + 1 : nullptr, *pred_b = c->predict ? c->d_pred_b[c->pred_cur] + 1 : nullptr;
 	int32_t *pred_next = c->d_pred[c->pred_cur ^ 1] + 1, *pred_next_b = c->d_pred_b[c->pred_cur ^ 1] + 1;
 	auto side_k1f = [&]() {
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, c->stream2, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr, c->n_sub);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, c->stream2, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr, c->n_sub, c->d_chunk_sub0, 0);
 		cudaEventRecord(c->ev_k1f, c->stream2);
 	};
 	auto side_warm = [&]() {
@@ -2990,13 +3003,13 @@ static int launch_warm(psmc_b200_ctx *c)
 		if (c->predict) side_k1f();
 	}
 	if (c->predict) {
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr, c->n_sub_b);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1);
 		cudaEventRecord(c->ev_k1b, c->stream2);
 		cudaStreamWaitEvent(st, c->ev_k1f, 0);
 	}
 	for (int r = 0; r < c->repair_rounds; ++r) {
 		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr, adf ? c->d_warm_f : nullptr, c->warm_len, c->d_tight_f);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub, c->d_chunk_sub0, 0);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_forward_repair<NP>(c);
 		LAUNCH((k_fold), c->n_chunks, 128, st, c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
@@ -3009,7 +3022,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
 	for (int r = 0; r < c->repair_rounds; ++r) {
 		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr, adb ? c->d_warm_b : nullptr, cap_b, c->d_tight_b);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
 		LAUNCH((k_fold), c->n_chunks_b, 128, st, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
