@@ -1550,7 +1550,10 @@ __device__ __forceinline__ void backward_chunk(const Chunk &ch, bool valid, cons
 // ------------------------------------------------------------------------------------------------
 template <int SPL, int G>
 struct BackwardRun {
-	static constexpr int NP = SPL * G, PF = 4;
+#ifndef PSMC_BWD_PF
+#define PSMC_BWD_PF 4
+#endif
+	static constexpr int NP = SPL * G, PF = PSMC_BWD_PF;
 	const Chunk &ch;
 	const LaneModel<SPL> &M;
 	const bool valid;
@@ -1648,9 +1651,9 @@ struct BackwardRun {
 		const int trips = (warp_trips(valid ? ch.len : 0) + PF - 1) / PF * PF;
 		for (int t = 0; t < trips; t += PF) {
 			step<0>(t, b);
-			step<1>(t + 1, b);
-			step<2>(t + 2, b);
-			step<3>(t + 3, b);
+			if (PF > 1) step<(PF > 1 ? 1 : 0)>(t + 1, b);
+			if (PF > 2) step<(PF > 2 ? 2 : 0)>(t + 2, b);
+			if (PF > 3) step<(PF > 3 ? 3 : 0)>(t + 3, b);
 		}
 		if (valid) {
 			double *po = part_c + s0;

@@ -36,6 +36,20 @@ def test_estep_matches_oracle_ragged(oracle, N, chunk_len):
     compare_stats(got, want, TOL, N)
 
 
+def test_generation1_kernels_still_match(oracle, monkeypatch):
+    """PSMC_B200_GEN=1: the Kogge-Stone kernels (the backward fallback at 128 padded states) through the fast path"""
+    from psmc_b200 import EStep
+    monkeypatch.setenv("PSMC_B200_GEN", "1")
+    N = 64
+    m = make_model(oracle, N, seed=13)
+    seqs = _seqs(m, [40000, 9000, 77], seed=14)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=2000) as es:
+        es.set_warm(3000)
+        got = es.run(_model(m))
+    compare_stats(got, want, TOL, N)
+
+
 def test_chunking_is_exact(oracle):
     """the chunk plan must not change the result (it does for the reference's splitfa, which cuts the likelihood)"""
     from psmc_b200 import EStep
