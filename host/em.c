@@ -51,7 +51,8 @@ static int init_model(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t 
 		em->sp.inp_ti = (double*)malloc(sizeof(double) * (em->sp.n + 1));
 		memcpy(em->sp.inp_ti, o->inp_ti, sizeof(double) * (em->sp.n + 1));
 	}
-	if (psmch_model_alloc(&em->model, &em->sp) < 0 || psmch_counts_alloc(&em->counts, em->sp.n + 1, 0) < 0) return -1;
+	em->exact_qd = o->exact_qd || (getenv("PSMC_B200_EXACT_QD") && atoi(getenv("PSMC_B200_EXACT_QD")) != 0);
+	if (psmch_model_alloc(&em->model, &em->sp) < 0 || psmch_counts_alloc(&em->counts, em->sp.n + 1, em->exact_qd) < 0) return -1;
 	em->post_sigma = (double*)calloc(em->sp.n + 1, sizeof(double));
 	/* initial parameters (core.c:32-49) */
 	if (o->inp_pa) {
@@ -128,6 +129,10 @@ int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq,
 			fprintf(stderr, "psmc: GPU E-step unavailable on device %d: %s\n", o->devices[g], psmc_b200_last_error());
 			return -1;
 		}
+		if (em->exact_qd && psmc_b200_set_dense(em->ctx[g], 1) != 0) {
+			fprintf(stderr, "psmc: --exact-qd: %s\n", psmc_b200_last_error());
+			return -1;
+		}
 	}
 	return 0;
 }
@@ -171,6 +176,15 @@ static int estep_all(psmch_em_t *em)
 		if (rc) return rc;
 	}
 	em->counts.LL = sv.LL;
+	if (em->exact_qd && em->counts.A) { /* hmm_expect's dense A summed over all sequences (khmm.c:346-352), for hmm_Q0 only */
+		double *tmp = (double*)malloc(sizeof(double) * (size_t)N * N);
+		memset(em->counts.A, 0, sizeof(double) * (size_t)N * N);
+		for (g = 0; g < em->n_gpus; ++g) {
+			if ((rc = psmc_b200_dense_counts(em->ctx[g], tmp)) != 0) { free(tmp); return rc; }
+			for (i = 0; i < N * N; ++i) em->counts.A[i] += tmp[i];
+		}
+		free(tmp);
+	}
 	return 0;
 }
 

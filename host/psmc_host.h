@@ -146,6 +146,7 @@ typedef struct {
 	int n_replicates;    /* --replicates R  R bootstrap replicates in this process (implies -b) [0] */
 	int split_len;       /* --split[=T]  apply the splitfa rule with trunk size T bins first [off; 500000] */
 	int slots;           /* --slots K  concurrent replicates per GPU [2] */
+	int exact_qd;        /* --exact-qd  dense transition counts for hmm_Q0 (khmm.c:336-340): the QD line as the original prints it */
 } psmch_opts_t;
 
 typedef struct {
@@ -159,6 +160,7 @@ typedef struct {
 	int *seq_owner; /* per sequence: which context holds it */
 	int64_t n_seqs;
 	int hj_calls;
+	int exact_qd;    /* dense counts fetched after every E-step (counts.A) */
 	int borrowed;    /* ctx[0] belongs to the caller (bootstrap replicates share one context per GPU slot) */
 	int exact_mstep; /* PSMC_B200_EXACT_MSTEP: trial evaluations with scalar libm instead of libmvec */
 	int spec_mstep;  /* speculative evaluator threads in the M-step: 0, 1 or 3 (PSMC_B200_MSTEP_SPEC; 0 for bootstrap workers) */

@@ -156,6 +156,14 @@ int  psmc_b200_decode(psmc_b200_ctx *ctx, const psmc_b200_model *model, int32_t 
  * E-step is silently redone with the transfer-matrix path (counted in psmc_b200_info::fallbacks). */
 int  psmc_b200_set_warm(psmc_b200_ctx *ctx, int32_t warm_len, double eps);
 
+/* Dense transition counts (option): hmm_expect's A[N][N] (khmm.c:305-316 summed over sequences as hmm_add_expect does,
+ * khmm.c:346-352).  Nothing on the EM path needs them -- the M-step works on the five O(N) marginals -- except the
+ * constant offset hmm_Q0 (khmm.c:336-340) of the printed QD line.  psmc_b200_set_dense(ctx, 1) makes every following
+ * E-step also spill the backward rows (8N more bytes per bin: allocated here); psmc_b200_dense_counts then forms the
+ * N x N matrix (row-major, caller-owned) of the LAST E-step.  At most 64 states. */
+int  psmc_b200_set_dense(psmc_b200_ctx *ctx, int32_t on);
+int  psmc_b200_dense_counts(psmc_b200_ctx *ctx, double *A);
+
 int  psmc_b200_get_info(const psmc_b200_ctx *ctx, psmc_b200_info *info);
 
 #ifdef __cplusplus

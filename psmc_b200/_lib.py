@@ -63,6 +63,8 @@ SYMBOLS = {
     "psmc_b200_unpack_stats": (C.c_int, [C.c_int32, _dp, C.c_int64, C.POINTER(CStats)]),
     "psmc_b200_decode": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.c_int32, _ip, _dp, _dp, _dp, _dp]),
     "psmc_b200_set_warm": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
+    "psmc_b200_set_dense": (C.c_int, [C.c_void_p, C.c_int32]),
+    "psmc_b200_dense_counts": (C.c_int, [C.c_void_p, _dp]),
     "psmc_b200_get_info": (C.c_int, [C.c_void_p, C.POINTER(CInfo)]),
 }
 

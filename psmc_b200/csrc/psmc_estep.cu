@@ -1562,6 +1562,7 @@ struct BackwardRun {
 	const double *__restrict__ frow, *__restrict__ srow; // row of bin ulast
 	double *__restrict__ bsave_c;
 	const int usave;
+	double *__restrict__ grow; // dense-count option: g_u = e_{x_u} b_u of every transition goes to ghat (this is the row of bin ulast), or nullptr
 	DualScan<G> ds;
 	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
 	double nf[PF][SPL], ns[PF];
@@ -1569,9 +1570,11 @@ struct BackwardRun {
 	int xu;
 
 	__device__ __forceinline__ BackwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_, const uint32_t *__restrict__ obs_,
-	                                       const double *__restrict__ fhat, const double *__restrict__ sc, double *__restrict__ bsave_c_, int usave_)
+	                                       const double *__restrict__ fhat, const double *__restrict__ sc, double *__restrict__ bsave_c_, int usave_,
+	                                       double *__restrict__ ghat)
 	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), ulast(ch_.u0 + ch_.len - 1), obs(obs_),
-	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_), usave(usave_)
+	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_), usave(usave_),
+	      grow(ghat ? ghat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL : nullptr)
 	{
 	}
 
@@ -1609,6 +1612,7 @@ struct BackwardRun {
 		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
 		prefsuf2<SPL, G>(fm, M.W, M.U, ds, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
 		if (trans) {
+			if (grow) store_vec<SPL>(grow - (size_t)t * NP, g);
 			const double inv = fast_rcp(sm);
 			const double w0 = (xm == 0) ? 1.0 : 0.0, w1 = (xm == 1) ? 1.0 : 0.0;
 #pragma unroll
@@ -1675,9 +1679,9 @@ template <int SPL, int G>
 __device__ __forceinline__ void backward_chunk2(const Chunk &ch, bool valid, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
                                                 const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
                                                 const double *__restrict__ sc, double *__restrict__ part_c,
-                                                double *__restrict__ bsave_c = nullptr, int usave = -1)
+                                                double *__restrict__ bsave_c = nullptr, int usave = -1, double *__restrict__ ghat = nullptr)
 {
-	BackwardRun<SPL, G> r(ch, valid, M, gl, obs, fhat, sc, bsave_c, usave);
+	BackwardRun<SPL, G> r(ch, valid, M, gl, obs, fhat, sc, bsave_c, usave, ghat);
 	r.run(b, part_c);
 }
 
@@ -1844,7 +1848,8 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
                                                   const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                   const double *__restrict__ bdir, int publish, const double *__restrict__ fhat,
                                                   const double *__restrict__ sc, double *__restrict__ part,
-                                                  double *__restrict__ bexact, double *__restrict__ bsave_next, int warm_next)
+                                                  double *__restrict__ bexact, double *__restrict__ bsave_next, int warm_next,
+                                                  double *__restrict__ ghat)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
@@ -1868,7 +1873,7 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 	const int usave = (ch.flags & CH_FIRST) ? -1 : min(ch.u0 - 1 + warm_next, ulast);
 	if constexpr (VER == 2)
 		backward_chunk2<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
-		                        bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
+		                        bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave, ghat);
 	else
 		backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
 		                       bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
@@ -1923,7 +1928,8 @@ __global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict
                                                          const int32_t *__restrict__ flag_b, const double *__restrict__ bsub,
                                                          const double *__restrict__ fhat, const double *__restrict__ sc,
                                                          double *__restrict__ partsub, double *__restrict__ bwarm,
-                                                         double *__restrict__ bexact, unsigned long long *__restrict__ stat)
+                                                         double *__restrict__ bexact, unsigned long long *__restrict__ stat,
+                                                         double *__restrict__ ghat)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_sub);
@@ -1938,7 +1944,7 @@ __global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict
 	load_vec<SPL>(bsub + (size_t)s * NP + s0, beta);                                                           // exact direction at the sub-chunk's last bin (k_chain_subs)
 	publish_direction<SPL, G>(beta, bwarm + (size_t)pc * NP, gl, valid && chunk_sub0[pc + 1] - 1 == s);       // the chunk boundary agrees by construction from now on
 	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
-	if constexpr (VER == 2) backward_chunk2<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP);
+	if constexpr (VER == 2) backward_chunk2<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP, nullptr, -1, ghat);
 	else backward_chunk<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP);
 	if (gl == 0 && valid) atomicAdd(&stat[3], 1ull);
 	// the first sub-chunk of a chunk ends at the boundary to chunk pc-1: publish the direction computed here
@@ -1972,6 +1978,77 @@ __global__ void __launch_bounds__(128) k_certify(const Chunk *__restrict__ chunk
 		if (!(m <= eps)) atomicAdd(&cert[0], 1ull);
 		atomicMax(&cert[1 + dir], (unsigned long long)__double_as_longlong(m));
 	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense transition counts (option): A[k][l] = a[k][l] * C[k][l] with C = sum_u f_{u-1}[k] g_u[l] over the transitions
+// (khmm.c:313-316), needed only for the constant offset hmm_Q0 of the printed QD line (khmm.c:336-340).  The backward
+// kernel stores the rows g_u next to the forward spill; C is then a tall-skinny product F^T G: one block per backward
+// chunk accumulates its NP x NP partial in registers (16 x 16 threads, a (NP/16)^2 tile each), rows staged through
+// shared memory in slabs of 32 bins; a fixed-order reduction over the chunks follows (deterministic, weighted by the
+// multiplicity of the chunk's record).  The pairing (row of bin u-1, row of bin u) never crosses a record: u >= max(u0, 1).
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256) k_dense_chunk(const Chunk *__restrict__ chunks, const double *__restrict__ fhat,
+                                                     const double *__restrict__ ghat, double *__restrict__ cpart)
+{
+	constexpr int TL = NP / 16, SLAB = 32;
+	__shared__ double sf[SLAB][NP], sg[SLAB][NP];
+	const Chunk ch = chunks[blockIdx.x];
+	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+	double acc[TL][TL];
+#pragma unroll
+	for (int i = 0; i < TL; ++i)
+#pragma unroll
+		for (int j = 0; j < TL; ++j) acc[i][j] = 0.0;
+	const int ulo = max(ch.u0, 1), uhi = ch.u0 + ch.len; // transitions into bins [ulo, uhi)
+	for (int ub = ulo; ub < uhi; ub += SLAB) {
+		const int nb = min(SLAB, uhi - ub);
+		for (int idx = threadIdx.x; idx < nb * NP; idx += 256) {
+			const int r = idx / NP, k = idx % NP;
+			const size_t row = (size_t)ch.gb0 + (size_t)(ub + r - ch.u0);
+			sf[r][k] = fhat[(row - 1) * NP + k];
+			sg[r][k] = ghat[row * NP + k];
+		}
+		__syncthreads();
+		for (int r = 0; r < nb; ++r) {
+			double fv[TL], gv[TL];
+#pragma unroll
+			for (int i = 0; i < TL; ++i) fv[i] = sf[r][ty * TL + i];
+#pragma unroll
+			for (int j = 0; j < TL; ++j) gv[j] = sg[r][tx * TL + j];
+#pragma unroll
+			for (int i = 0; i < TL; ++i)
+#pragma unroll
+				for (int j = 0; j < TL; ++j) acc[i][j] = fma(fv[i], gv[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+	double *out = cpart + (size_t)blockIdx.x * NP * NP;
+#pragma unroll
+	for (int i = 0; i < TL; ++i)
+#pragma unroll
+		for (int j = 0; j < TL; ++j) out[(size_t)(ty * TL + i) * NP + tx * TL + j] = acc[i][j];
+}
+
+// C[e] = sum_c w[c] * cpart[c][e] in a fixed order; one block per entry e of the NP x NP matrix
+__global__ void __launch_bounds__(256) k_dense_reduce(const double *__restrict__ cpart, int n_chunks, int n_entries,
+                                                      const double *__restrict__ w, double *__restrict__ out)
+{
+	__shared__ double sh[256];
+	const int e = blockIdx.x;
+	double acc = 0.0;
+	for (int c = threadIdx.x; c < n_chunks; c += 256) {
+		const double v = cpart[(size_t)c * n_entries + e];
+		acc += w ? w[c] * v : v;
+	}
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	for (int d = 128; d > 0; d >>= 1) {
+		if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[e] = sh[0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2165,6 +2242,10 @@ struct psmc_b200_ctx {
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
 	int side_order = 0;         // PSMC_B200_SIDE_ORDER, see launch_warm
+	bool dense = false;         // psmc_b200_set_dense: the backward pass also stores the rows g_u for psmc_b200_dense_counts
+	bool dense_valid = false;   // ghat holds the rows of the last E-step
+	double *d_ghat = nullptr, *d_cpart = nullptr, *d_cdense = nullptr;
+	int cap_cpart = 0;
 	int warm32 = 0, warm32_b = 0; // bins of FP32 pre-warm-up in front of the FP64 overlaps (PSMC_B200_WARM32 / _WARM32_BWD; 0 = none)
 	double *d_pre_f = nullptr, *d_pre_b = nullptr; // its results: start vectors of the forward / backward overlaps
 	bool adapt = false;         // adaptive per-boundary overlaps (PSMC_B200_ADAPT=1; measured on B200: no gain -- the kernels' duration is set by
@@ -2260,6 +2341,7 @@ static void free_ctx(psmc_b200_ctx *c)
 	cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_cert);
 	if (c->h_cert) cudaFreeHost(c->h_cert);
 	cudaFree(c->d_stats);
+	cudaFree(c->d_ghat); cudaFree(c->d_cpart); cudaFree(c->d_cdense);
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
 	if (c->h_model) cudaFreeHost(c->h_model);
 	if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -2846,7 +2928,7 @@ template <int NP>
 static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const double *bdir, int publish, double *bsave_next)
 {
 	cudaStream_t st = c->stream;
-#define BWD(G_, V_) LAUNCH((k_backward<NP / G_, G_, V_>), blocks_for(n, G_), 128, st, chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot)
+#define BWD(G_, V_) LAUNCH((k_backward<NP / G_, G_, V_>), blocks_for(n, G_), 128, st, chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot, (c->dense && V_ == 2) ? c->d_ghat : nullptr)
 	// (forcing 4 resident blocks per SM with __launch_bounds__(128, 4) was measured: the spills cost more than the occupancy gives)
 	if constexpr (Gen2<NP>::BWD_OK) {
 		if (c->gen == 2) {
@@ -2877,7 +2959,7 @@ template <int NP>
 static void run_backward_repair(psmc_b200_ctx *c)
 {
 	cudaStream_t st = c->stream;
-#define BWR(G_, V_) LAUNCH((k_backward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub_b, G_), 128, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4)
+#define BWR(G_, V_) LAUNCH((k_backward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub_b, G_), 128, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4, (c->dense && V_ == 2) ? c->d_ghat : nullptr)
 	if constexpr (Gen2<NP>::BWD_OK) {
 		if (c->gen == 2) {
 			BWR(Gen2<NP>::G_BWD, 2);
@@ -3080,6 +3162,7 @@ extern "C" int psmc_b200_estep_launch(psmc_b200_ctx *c, const psmc_b200_model *m
 	rc = launch_dispatch(c, true);
 	if (rc) return rc;
 	c->launched = true;
+	c->dense_valid = c->dense;
 	return 0;
 }
 
@@ -3297,6 +3380,67 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
 	if (s_out) CUDA_TRY(cudaMemcpyAsync(s_out, c->d_sc + c->seq_gb0[seq_id], sizeof(double) * (size_t)Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	if (model) collect_times(c, false);
+	return 0;
+}
+
+// ---- dense transition counts (option) ----
+extern "C" int psmc_b200_set_dense(psmc_b200_ctx *c, int32_t on)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (on && (c->NP > 64 || c->gen != 2))
+		return set_err(PSMC_B200_EINVAL, "dense counts need the generation-2 backward kernels (at most 64 states)");
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	if (on && !c->d_ghat) {
+		const size_t bytes = (size_t)std::max<int64_t>(c->total_bins, 1) * c->NP * sizeof(double);
+		CUDA_TRY(cudaMalloc((void **)&c->d_ghat, bytes), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMemsetAsync(c->d_ghat, 0, bytes, c->stream), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMalloc((void **)&c->d_cdense, sizeof(double) * (size_t)c->NP * c->NP), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+		c->bytes_total += (int64_t)bytes;
+	}
+	c->dense = on != 0;
+	c->dense_valid = false;
+	return 0;
+}
+
+template <int NP>
+static void launch_dense(psmc_b200_ctx *c)
+{
+	LAUNCH((k_dense_chunk<NP>), c->n_chunks_b, 256, c->stream, c->d_chunks_b, c->d_fhat, c->d_ghat, c->d_cpart);
+	LAUNCH((k_dense_reduce), NP * NP, 256, c->stream, c->d_cpart, c->n_chunks_b, NP * NP, c->weighted ? c->d_cw_b : nullptr, c->d_cdense);
+}
+
+extern "C" int psmc_b200_dense_counts(psmc_b200_ctx *c, double *A)
+{
+	if (!c || !A) return set_err(PSMC_B200_EINVAL, "NULL argument");
+	if (!c->dense || !c->dense_valid) return set_err(PSMC_B200_EINVAL, "no dense rows: call psmc_b200_set_dense(ctx, 1) before the E-step");
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	int rc = sync_and_certify(c);
+	if (rc) return rc;
+	const int NP = c->NP, N = c->N;
+	if (c->n_chunks_b > c->cap_cpart) {
+		cudaFree(c->d_cpart);
+		c->d_cpart = nullptr;
+		c->cap_cpart = 0;
+		CUDA_TRY(cudaMalloc((void **)&c->d_cpart, sizeof(double) * (size_t)std::max(c->n_chunks_b, 1) * NP * NP), PSMC_B200_ECUDA);
+		c->cap_cpart = c->n_chunks_b;
+	}
+	std::vector<double> C((size_t)NP * NP, 0.0);
+	if (c->n_chunks_b > 0) {
+		if (NP == 32) launch_dense<32>(c);
+		else launch_dense<64>(c);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+		CUDA_TRY(cudaMemcpyAsync(C.data(), c->d_cdense, sizeof(double) * (size_t)NP * NP, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	}
+	// A[k][l] = sum over records of ( HMM_TINY + sum_u f_{u-1}[k] a[k][l] e[l] b_u[l] )   (khmm.c:305-316, 346-352)
+	const double *hm = c->h_model, tiny = HMM_TINY_ * (double)c->n_seq_eff;
+	for (int k = 0; k < N; ++k)
+		for (int l = 0; l < N; ++l) {
+			const double a = l < k ? hm[M_U * NP + k] * hm[M_V * NP + l] : (l > k ? hm[M_W * NP + k] * hm[M_Z * NP + l] : hm[M_D * NP + k]);
+			A[(size_t)k * N + l] = tiny + a * C[(size_t)k * NP + l];
+		}
 	return 0;
 }
 

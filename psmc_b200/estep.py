@@ -167,6 +167,16 @@ class EStep:
             raise ValueError("mult must have one entry per record given at construction (%d)" % self.n_seqs)
         check(self.lib, self.lib.psmc_b200_set_multiplicity(self.h, m.ctypes.data_as(C.POINTER(C.c_int32))))
 
+    def set_dense(self, on=True):
+        """also spill the backward rows in every following E-step (needed by dense_counts)"""
+        check(self.lib, self.lib.psmc_b200_set_dense(self.h, 1 if on else 0))
+
+    def dense_counts(self):
+        """hmm_expect's dense A[N][N] of the last E-step (khmm.c:305-316), summed over the sequences"""
+        A = np.zeros((self.N, self.N))
+        check(self.lib, self.lib.psmc_b200_dense_counts(self.h, _d(A)))
+        return A
+
     def set_warm(self, warm_len=-1, eps=0.0):
         """warm-up overlap in bins (0 = exact transfer-matrix path only) and certificate tolerance"""
         check(self.lib, self.lib.psmc_b200_set_warm(self.h, warm_len, eps))

@@ -43,6 +43,22 @@ def test_64_states_ragged_contigs_em_matches_reference(tmp_path):
     compare_rounds(got2, got, {"*": (1e-6, 1e-6), "LK": (1e-7, 1e-6), "TR": (5e-5, 2e-6), "MT": (5e-5, 2e-6), "MM": (5e-5, 2e-6), "RS": (1e-3, 3e-6), "PA": (1e-3, 3e-6), "RI": (1e-3, 2e-7)})
 
 
+def test_exact_qd_matches_the_reference_qd_lines(tmp_path):
+    """--exact-qd: dense transition counts on the GPU give hmm_Q0 its original offset (khmm.c:336-340), so the QD lines --
+    format-checked only otherwise -- agree with the reference numerically; nothing else may change"""
+    args = ["-N4", "-t15", "-r5", "-p", "4+25*2+4+6", os.path.join(G, "small64.psmcfa.gz")]
+    plain, _ = run(args, tmp_path, "plain.psmc")
+    exact, _ = run(args + ["--exact-qd"], tmp_path, "exact.psmc")
+    want = parse(os.path.join(G, "small64.psmc"))
+    assert [l for l in plain if not l.startswith("QD")] == [l for l in exact if not l.startswith("QD")]
+    qd_g = [[float(x) for x in fields(l)[1] if x != "->"] for l in exact if l.startswith("QD")]
+    qd_w = [[float(x) for x in fields(l)[1] if x != "->"] for l in want if l.startswith("QD")]
+    assert len(qd_g) == len(qd_w) > 1
+    for a, b in zip(qd_g, qd_w):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 2e-5 * abs(y) + 2e-6, (a, b)
+
+
 def test_first_round_is_tight(tmp_path):
     """round 1 (one E-step + one M-step from identical start values) before trajectories can drift"""
     got, _ = run(["-N1", "-t5", "-r1", "-p", "4+5*3+4", os.path.join(G, "c1.psmcfa.gz")], tmp_path)

@@ -80,6 +80,23 @@ def test_estep_dense_entry_and_structure_check(oracle):
         assert ei.value.code == -4
 
 
+def test_dense_counts_match_oracle(oracle):
+    """option: hmm_expect's dense A[N][N] (khmm.c:305-316) from the spilled backward rows and a tall-skinny product"""
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=61)
+    seqs = _seqs(m, [30000, 7000, 1], seed=62)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=2000) as es:
+        es.set_warm(3000)
+        es.set_dense(True)
+        got = es.run(_model(m))
+        A = es.dense_counts()
+    compare_stats(got, want, TOL, N)
+    scale = np.maximum(np.abs(want["A"]), 1e-9 * np.abs(want["A"]).max())
+    assert np.max(np.abs(A - want["A"]) / scale) < TOL
+
+
 def test_missing_only_and_all_hom(oracle):
     from psmc_b200 import EStep
     N = 23

@@ -185,3 +185,23 @@ def test_emulated_fp32_prewarm(oracle, emu_plain, monkeypatch, N):
         info = es.info()
     compare_stats(got, want, TOL, N)
     assert info["fallbacks"] == 0 and info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
+
+
+@pytest.mark.parametrize("N,mult", [(23, None), (64, None), (64, [2, 0, 1])])
+def test_emulated_dense_counts(oracle, emu_plain, N, mult):
+    """option: hmm_expect's dense A[N][N] (khmm.c:305-316) from the spilled backward rows and a tall-skinny product"""
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=61)
+    seqs = _seqs(m, [900, 340, 1], seed=62)
+    expanded = seqs if mult is None else [s for s, k in zip(seqs, mult) for _ in range(k)]
+    want = oracle_stats(oracle, m, expanded)
+    with EStep(seqs, N, chunk_len=150) as es:
+        es.set_warm(300)
+        es.set_dense(True)
+        if mult is not None:
+            es.set_multiplicity(mult)
+        got = es.run(_model(m))
+        A = es.dense_counts()
+    compare_stats(got, want, TOL, N)
+    scale = np.maximum(np.abs(want["A"]), 1e-9 * np.abs(want["A"]).max())
+    assert np.max(np.abs(A - want["A"]) / scale) < TOL
