@@ -1,0 +1,56 @@
+"""The drop-in `psmc` binary end to end on the CPU: host/psmc is linked against libpsmc_b200.so by name, so pointing the
+loader at tests/emu's build of the same C ABI (the CUDA source executed by the SIMT emulation) runs the whole program --
+CLI, .psmcfa reader, GPU-side orchestration, kernels' source, M-step, printer -- without a GPU, against the golden files
+written by the unmodified reference.  Test infrastructure only (the product has no CPU path); `-m gpu` repeats it for real."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from psmc_text import compare_rounds, fields, parse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+PSMC = os.path.join(ROOT, "host", "psmc")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+TOL = {"*": (1e-6, 1e-6), "LK": (1e-7, 1e-6), "TR": (5e-5, 2e-6), "MT": (5e-5, 2e-6), "MM": (5e-5, 2e-6), "RS": (1e-3, 3e-6),
+       "PA": (1e-3, 3e-6), "RI": (1e-3, 2e-7)}
+
+
+@pytest.fixture(scope="module")
+def emu_env(tmp_path_factory):
+    if not os.path.exists(PSMC):
+        pytest.skip("host/psmc not built")
+    subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
+    d = tmp_path_factory.mktemp("emulib")
+    shutil.copy(os.path.join(EMU_DIR, "libpsmc_b200_emu.so"), str(d / "libpsmc_b200.so"))
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = str(d) + os.pathsep + env.get("LD_LIBRARY_PATH", "")   # searched before the binary's RUNPATH
+    env["PSMC_EMU_SMS"] = "2"
+    return env
+
+
+def run(args, env, out):
+    r = subprocess.run([PSMC] + args + ["-o", out], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    return parse(out)
+
+
+def test_emulated_cli_config1_matches_reference(emu_env, tmp_path):
+    got = run(["-N5", "-t5", "-r1", "-p", "4+5*3+4", os.path.join(G, "c1.psmcfa.gz")], emu_env, str(tmp_path / "c1.psmc"))
+    compare_rounds(got, parse(os.path.join(G, "c1.psmc")), TOL)
+
+
+def test_emulated_cli_64_states_exact_qd(emu_env, tmp_path):
+    """64 states, ragged contigs, --exact-qd: every line including QD against the reference's output"""
+    args = ["-N4", "-t15", "-r5", "-p", "4+25*2+4+6", "--exact-qd", os.path.join(G, "small64.psmcfa.gz")]
+    got = run(args, emu_env, str(tmp_path / "s64.psmc"))
+    want = parse(os.path.join(G, "small64.psmc"))
+    compare_rounds(got, want, TOL)
+    qd_g = [[float(x) for x in fields(l)[1] if x != "->"] for l in got if l.startswith("QD")]
+    qd_w = [[float(x) for x in fields(l)[1] if x != "->"] for l in want if l.startswith("QD")]
+    assert len(qd_g) == len(qd_w) > 1
+    for a, b in zip(qd_g, qd_w):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 2e-5 * abs(y) + 2e-6, (a, b)
