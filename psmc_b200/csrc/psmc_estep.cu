@@ -1993,7 +1993,7 @@ __global__ void __launch_bounds__(256) k_dense_chunk(const Chunk *__restrict__ c
                                                      const double *__restrict__ ghat, double *__restrict__ cpart)
 {
 	constexpr int TL = NP / 16, SLAB = 32;
-	__shared__ double sf[SLAB][NP], sg[SLAB][NP];
+	__shared__ __align__(16) double sf[SLAB][NP], sg[SLAB][NP];
 	const Chunk ch = chunks[blockIdx.x];
 	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 	double acc[TL][TL];
@@ -2014,9 +2014,12 @@ __global__ void __launch_bounds__(256) k_dense_chunk(const Chunk *__restrict__ c
 		for (int r = 0; r < nb; ++r) {
 			double fv[TL], gv[TL];
 #pragma unroll
-			for (int i = 0; i < TL; ++i) fv[i] = sf[r][ty * TL + i];
-#pragma unroll
-			for (int j = 0; j < TL; ++j) gv[j] = sg[r][tx * TL + j];
+			for (int i = 0; i < TL; i += 2) { // 128-bit shared loads (TL is 2 or 4, the tiles are 16-byte aligned)
+				const double2 a = *reinterpret_cast<const double2 *>(&sf[r][ty * TL + i]);
+				const double2 b = *reinterpret_cast<const double2 *>(&sg[r][tx * TL + i]);
+				fv[i] = a.x; fv[i + 1] = a.y;
+				gv[i] = b.x; gv[i + 1] = b.y;
+			}
 #pragma unroll
 			for (int i = 0; i < TL; ++i)
 #pragma unroll

@@ -25,6 +25,7 @@
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static thread_local /* a block lives on one host thread */
 
 struct dim3 {
