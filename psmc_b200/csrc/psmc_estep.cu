@@ -914,7 +914,8 @@ struct ForwardRun {
 	int u_warm;  // the vector of bin u_warm - 1 goes to fwarm_c  (u0 after a warm-up, or never)
 	int u_boost; // boosts of bins >= u_boost enter the log-likelihood
 	int kq, ubase, wlast, tpend, mystart;
-	uint32_t word, wnext, wnext2;
+	uint32_t wa, wb, wna, wnb; // packed observation words of the current block (word ia and the one after it) / of the next block (ina)
+	int ia, ina;
 	double *prow, *psc; // where the row / scale factor of the bin finished by the next store-phase step go (advance one bin per step)
 
 	__device__ __forceinline__ ForwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_,
@@ -940,17 +941,27 @@ struct ForwardRun {
 		tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
 	}
 
+	// A block = the steps [t, tstop) between two multiples of 16 (or up to a late start / the end of the phase).  Makes the
+	// words prefetched for a block starting at t current and fetches those of the block starting at tstop (indices clamped
+	// to the sequence, so idle groups read legal words too; the loads have a whole block to complete).
+	__device__ __forceinline__ int begin_block(int t, int tend)
+	{
+		const int tstop = min(min(tend, tpend), (t & ~15) + 16);
+		wa = wna; wb = wnb; ia = ina;
+		ina = (ubase + tstop) >> 4;
+		wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast));
+		wnb = __ldg(obs + ch.ow0 + min(max(ina + 1, 0), wlast));
+		return tstop;
+	}
+
 	// bin u = ubase + t is formed from the current vector (bin u-1); BOOK: finish bin u-1 (sum, reciprocal, stores) alongside
 	template <bool BOOK>
 	__device__ __forceinline__ void step(int t)
 	{
 		const int u = ubase + t;
-		if ((u & 15) == 0) { // next packed word; fetched TWO words ahead, so that nothing waits for the load (indices clamped
-			word = wnext;    // to the sequence: idle groups read legal words too)
-			wnext = wnext2;
-			wnext2 = __ldg(obs + ch.ow0 + min(max((u >> 4) + 2, 0), wlast));
-		}
-		const int x = (word >> ((u & 15) * 2)) & 3;
+		// the (at most two) packed words of this block of <= 16 bins were fetched during the previous block (begin_block):
+		// no load and no address arithmetic in here
+		const int x = ((((u >> 4) == ia) ? wa : wb) >> ((u & 15) * 2)) & 3;
 		double c0, c1;
 		emis_coef(x, c0, c1);
 		c0 *= qc;
@@ -1021,10 +1032,9 @@ struct ForwardRun {
 		const int tB = warp_min_i(valid ? trips - (uend - max(u0, ubeg)) : trips); // first step in which some group forms a bin it stores
 		ubase = uend - trips;
 		mystart = valid ? trips - mytrips : INT_MAX;
-		// (as if bin ubase-1 had just been processed: the first step shifts if ubase starts a word)
-		word = __ldg(obs + ch.ow0 + min(max((ubase - 1) >> 4, 0), wlast));
-		wnext = __ldg(obs + ch.ow0 + min(max(((ubase - 1) >> 4) + 1, 0), wlast));
-		wnext2 = __ldg(obs + ch.ow0 + min(max(((ubase - 1) >> 4) + 2, 0), wlast));
+		ina = ubase >> 4; // words of the first block (begin_block makes them current)
+		wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast));
+		wnb = __ldg(obs + ch.ow0 + min(max(ina + 1, 0), wlast));
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) g[i] = f[i];
 		ps = local_sum<SPL>(g);
@@ -1035,7 +1045,7 @@ struct ForwardRun {
 		int t = 0;
 		while (t < tB) { // warm-up phase, in blocks of at most 16 bins: late starts and the boost decision sit between blocks
 			if (t == tpend) start_due(t, f, inv_before);
-			const int tstop = min(min(tB, tpend), (t & ~15) + 16);
+			const int tstop = begin_block(t, tB);
 			qc = (gsum<G>(ps) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
 			for (; t < tstop; ++t) step<false>(t);
 		}
@@ -1047,7 +1057,7 @@ struct ForwardRun {
 		}
 		while (t < trips) { // store phase
 			if (t == tpend) start_due(t, f, inv_before);
-			const int tstop = min(trips, tpend);
+			const int tstop = begin_block(t, trips);
 			for (; t < tstop; ++t) step<true>(t);
 		}
 		if (mytrips == 0) { // nothing formed in the loop (a one-bin chunk at the start of a sequence): the start vector is the last bin
@@ -1762,11 +1772,10 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 		const int mystart = mytrips > 0 ? trips - mytrips : INT_MAX;
 		int tpend = warp_min_i(mystart);
 		const int wlast = (ch.Lseq - 1) >> 4, ufirst = ulast + trips;
-		// packed words: `word` holds the word of the bin being processed, `wprev` the one below it; indices are clamped to
-		// the sequence so that idle groups read legal words too (initialised as if bin ufirst+1 had just been processed)
-		uint32_t word = __ldg(obs + ch.ow0 + min(max((ufirst + 1) >> 4, 0), wlast));
-		uint32_t wprev = __ldg(obs + ch.ow0 + min(max(((ufirst + 1) >> 4) - 1, 0), wlast));
-		uint32_t wprev2 = __ldg(obs + ch.ow0 + min(max(((ufirst + 1) >> 4) - 2, 0), wlast)); // two words ahead: nothing waits for the load
+		// packed words: the (at most two) words of a block of <= 16 bins are fetched during the previous block, so the inner
+		// loop has no load and no address arithmetic; indices are clamped to the sequence (idle groups read legal words too)
+		int ina = ufirst >> 4, ia;
+		uint32_t wa, wb, wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast)), wnb = __ldg(obs + ch.ow0 + min(max(ina - 1, 0), wlast));
 		double q = 1.0, bc[SPL];
 #pragma unroll
 		for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
@@ -1780,15 +1789,14 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 				tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
 			}
 			const int tstop = min(min(trips, tpend), (t & ~15) + 16);
+			wa = wna; wb = wnb; ia = ina;
+			ina = (ufirst - tstop) >> 4; // the next block starts at step tstop
+			wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast));
+			wnb = __ldg(obs + ch.ow0 + min(max(ina - 1, 0), wlast));
 			q = (gsum<G>(local_sum<SPL>(bc)) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
 			for (; t < tstop; ++t) {
 				const int u = ufirst - t; // bin whose emission enters; the step yields the direction of bin u-1
-				if ((u & 15) == 15) {
-					word = wprev;
-					wprev = wprev2;
-					wprev2 = __ldg(obs + ch.ow0 + min(max((u >> 4) - 2, 0), wlast));
-				}
-				const int x = (word >> ((u & 15) * 2)) & 3;
+				const int x = ((((u >> 4) == ia) ? wa : wb) >> ((u & 15) * 2)) & 3;
 				double g[SPL], c0, c1;
 				emis_coef(x, c0, c1);
 				c0 *= q;
