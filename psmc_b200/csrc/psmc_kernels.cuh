@@ -1,0 +1,2122 @@
+// psmc_kernels.cuh -- device code of the B200 (sm_100a) E-step: lane-group primitives, the chunk kernels of both
+// generations, transfer operators, boundary chains, certificate, reductions, decode, dense counts.
+// Included by psmc_estep.cu only (which holds the C ABI and the host orchestration); see the header comment there and
+// DESIGN.md for the algorithm.  Reference being replaced: khmm.c:145-324 (hmm_forward / hmm_backward / hmm_lk / hmm_expect)
+// and aux.c:150-201 (posterior decoding) of lh3/psmc -- nothing here is translated from it.
+#pragma once
+// ------------------------------------------------------------------------------------------------
+// device-side layout
+// ------------------------------------------------------------------------------------------------
+struct Chunk {
+	int32_t seq;     // sequence id
+	int32_t flags;   // bit0: first chunk of its sequence, bit1: last chunk of its sequence
+	int32_t u0;      // first bin of the chunk, sequence-local
+	int32_t len;     // bins in the chunk (>= 1)
+	int64_t gb0;     // global bin index of u0 (rows of fhat / entries of sc)
+	int64_t ow0;     // first packed-observation word of the SEQUENCE (16 bins per 32-bit word)
+	int32_t Lseq;    // length of the sequence
+	int32_t pad_;
+};
+#define CH_FIRST 1
+#define CH_LAST 2
+
+// model arrays on the device, each NP doubles, contiguous: a0 e0 e1 U V W Z D
+enum { M_A0 = 0, M_E0, M_E1, M_U, M_V, M_W, M_Z, M_D, M_COUNT };
+// statistics rows: E0 E1 RL CL RU CU AD
+enum { S_E0 = 0, S_E1, S_RL, S_CL, S_RU, S_CU, S_AD, S_COUNT };
+
+// ------------------------------------------------------------------------------------------------
+// lane-group primitives: a vector of NP = G*SPL states is held by G consecutive lanes, SPL states
+// per lane (state = gl*SPL + i).  G is a power of two <= 32.
+// ------------------------------------------------------------------------------------------------
+// Kogge-Stone scans over the lanes of a group.  A step is "x += (source lane inside my group) ? shuffled x : 0";
+// written as an FMA with a per-lane 0/1 mask it costs 2 SHFL + 1 DFMA (the obvious if/select form compiles to
+// 2 SHFL + DADD + 2 FSEL + moves and made the chunk kernels issue-bound: 231 instructions per bin, ncu).
+template <int G>
+struct ScanMasks {
+	static constexpr int STEPS = (G == 32 ? 5 : G == 16 ? 4 : G == 8 ? 3 : G == 4 ? 2 : G == 2 ? 1 : 0);
+	double up[STEPS + 1], dn[STEPS + 1]; // [k]: distance 2^k; [STEPS] is unused padding for G == 1
+	__device__ __forceinline__ void init(int gl)
+	{
+#pragma unroll
+		for (int k = 0; k < STEPS; ++k) {
+			up[k] = (gl >= (1 << k)) ? 1.0 : 0.0;
+			dn[k] = (gl + (1 << k) < G) ? 1.0 : 0.0;
+		}
+		up[STEPS] = dn[STEPS] = 0.0;
+	}
+	// keep the masks in registers: without this ptxas re-derives every mask from a predicate in every iteration
+	// (ISETP + FSEL + MOV per scan stage); only for kernels with registers to spare
+	__device__ __forceinline__ void pin()
+	{
+#pragma unroll
+		for (int k = 0; k < STEPS; ++k) {
+			PIN_REG(up[k]);
+			PIN_REG(dn[k]);
+		}
+	}
+};
+template <int G>
+__device__ __forceinline__ double gscan_up(double t, const ScanMasks<G> &m) // exclusive prefix over the lanes of a group
+{
+	if (G == 1) return 0.0;
+	double x = __shfl_up_sync(FULLMASK, t, 1, G) * m.up[0];
+#pragma unroll
+	for (int k = 0; k < ScanMasks<G>::STEPS; ++k) x = fma(__shfl_up_sync(FULLMASK, x, 1 << k, G), m.up[k], x);
+	return x;
+}
+template <int G>
+__device__ __forceinline__ double gscan_down(double t, const ScanMasks<G> &m) // exclusive suffix over the lanes of a group
+{
+	if (G == 1) return 0.0;
+	double x = __shfl_down_sync(FULLMASK, t, 1, G) * m.dn[0];
+#pragma unroll
+	for (int k = 0; k < ScanMasks<G>::STEPS; ++k) x = fma(__shfl_down_sync(FULLMASK, x, 1 << k, G), m.dn[k], x);
+	return x;
+}
+template <int G>
+__device__ __forceinline__ double gsum(double t) // all-reduce over the lanes of a group (same bits in every lane)
+{
+#pragma unroll
+	for (int d = G >> 1; d > 0; d >>= 1) t += __shfl_xor_sync(FULLMASK, t, d, G);
+	return t;
+}
+// reciprocal of a positive normal double: hardware seed (20 bits) + two Newton steps (2^-80 before rounding, ~1 ulp;
+// the IEEE division drags a slow path and a range check into the loop)
+__device__ __forceinline__ double fast_rcp(double s)
+{
+	double r;
+#ifndef PSMC_SIMT_EMU
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+#else
+	r = simt_emu::rcp_seed(s);
+#endif
+	double e = fma(-s, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-s, r, 1.0);
+	return fma(r, e, r);
+}
+template <int G>
+__device__ __forceinline__ int gmax_i(int t)
+{
+#pragma unroll
+	for (int d = G >> 1; d > 0; d >>= 1) t = max(t, __shfl_xor_sync(FULLMASK, t, d, G));
+	return t;
+}
+
+// out[i] = D[i] x[i] + pc[i] * sum_{j<i} pm[j] x[j] + sc[i] * sum_{j>i} sm[j] x[j]   (indices over the whole group)
+//   forward  (A^T f): pm = W, pc = Z, sm = U, sc = V
+//   backward (A g)  : pm = V, pc = U, sm = Z, sc = W
+template <int SPL, int G>
+__device__ __forceinline__ void semisep(const double (&x)[SPL], const double (&pm)[SPL], const double (&pc)[SPL],
+                                        const double (&sm)[SPL], const double (&sc)[SPL], const double (&D)[SPL],
+                                        const ScanMasks<G> &mk, double (&out)[SPL])
+{
+	double tp = 0.0, ts = 0.0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		tp = fma(x[i], pm[i], tp);
+		ts = fma(x[i], sm[i], ts);
+	}
+	double p = gscan_up<G>(tp, mk), s = gscan_down<G>(ts, mk);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		out[i] = fma(pc[i], p, D[i] * x[i]);
+		p = fma(x[i], pm[i], p);
+	}
+#pragma unroll
+	for (int i = SPL - 1; i >= 0; --i) {
+		out[i] = fma(sc[i], s, out[i]);
+		s = fma(x[i], sm[i], s);
+	}
+}
+
+// exclusive prefix P[i] = sum_{j<i} pm[j] x[j] and exclusive suffix S[i] = sum_{j>i} sm[j] x[j]
+template <int SPL, int G>
+__device__ __forceinline__ void prefsuf(const double (&x)[SPL], const double (&pm)[SPL], const double (&sm)[SPL],
+                                        const ScanMasks<G> &mk, double (&P)[SPL], double (&S)[SPL])
+{
+	double tp = 0.0, ts = 0.0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		tp = fma(x[i], pm[i], tp);
+		ts = fma(x[i], sm[i], ts);
+	}
+	double p = gscan_up<G>(tp, mk), s = gscan_down<G>(ts, mk);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		P[i] = p;
+		p = fma(x[i], pm[i], p);
+	}
+#pragma unroll
+	for (int i = SPL - 1; i >= 0; --i) {
+		S[i] = s;
+		s = fma(x[i], sm[i], s);
+	}
+}
+
+template <int SPL>
+__device__ __forceinline__ void load_vec(const double *__restrict__ p, double (&v)[SPL])
+{
+	if (SPL == 1) {
+		v[0] = __ldg(p);
+	} else {
+#pragma unroll
+		for (int i = 0; i < SPL; i += 2) {
+			double2 t = __ldg(reinterpret_cast<const double2 *>(p + i));
+			v[i] = t.x;
+			v[i + 1] = t.y;
+		}
+	}
+}
+template <int SPL>
+__device__ __forceinline__ void store_vec(double *__restrict__ p, const double (&v)[SPL])
+{
+	if (SPL == 1) {
+		p[0] = v[0];
+	} else {
+#pragma unroll
+		for (int i = 0; i < SPL; i += 2) *reinterpret_cast<double2 *>(p + i) = make_double2(v[i], v[i + 1]);
+	}
+}
+
+__device__ __forceinline__ int obs_at(const uint32_t *__restrict__ obs, int64_t ow0, int u)
+{
+	return (__ldg(obs + ow0 + (u >> 4)) >> ((u & 15) * 2)) & 3;
+}
+
+// Loop bounds of a warp-per-chunk kernel come from a per-thread load; broadcasting them from lane 0 lets ptxas
+// prove they are warp-uniform, otherwise every shuffle in the loop is wrapped in WARPSYNC/ENDCOLLECTIVE (3x the
+// instruction count, measured with ncu on B200).
+__device__ __forceinline__ Chunk uniform_chunk(Chunk ch)
+{
+	ch.seq = __shfl_sync(FULLMASK, ch.seq, 0);
+	ch.flags = __shfl_sync(FULLMASK, ch.flags, 0);
+	ch.u0 = __shfl_sync(FULLMASK, ch.u0, 0);
+	ch.len = __shfl_sync(FULLMASK, ch.len, 0);
+	ch.Lseq = __shfl_sync(FULLMASK, ch.Lseq, 0);
+	return ch;
+}
+
+// exact power-of-two rescale helpers: k = floor(log2(x)) for a normal positive x
+__device__ __forceinline__ int exponent_of(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
+__device__ __forceinline__ double pow2i(int k) { return __hiloint2double((1023 + k) << 20, 0); } // |k| < 1022
+
+// ================================================================================================
+// Second-generation lane-group primitives (the chunk kernels are bound by the LATENCY of the per-bin dependency
+// chain at one or two warps per scheduler, not by issue slots or bandwidth; measured with ncu on B200):
+//   * DualScan<G>: exclusive prefix of one value AND exclusive suffix of another over the G lanes of a group in ONE
+//     (G = 8) or TWO (G = 16) shuffle rounds instead of 1 + log2 G Kogge-Stone rounds.  With xor-partners, the lane
+//     pair (l, l ^ m) needs exactly one value from each other: the lower lane's prefix term goes up, the upper lane's
+//     suffix term goes down, so one 64-bit shuffle serves both scans.
+//   * local prefix/suffix sums as trees, and everything that does not depend on the shuffled values moved in front
+//     of them: after the shuffles a state costs two FMAs.
+// ================================================================================================
+template <int G>
+struct DualScan;
+
+template <>
+struct DualScan<8> {
+	bool h0, h1, h2;
+	double u0, u1, u2, d0, d1, d2; // u_b = 1 iff bit b of my lane is set: the partners that differ first in bit b are BELOW me
+	__device__ __forceinline__ void init(int gl)
+	{
+		h0 = (gl & 1) != 0; h1 = (gl & 2) != 0; h2 = (gl & 4) != 0;
+		u0 = h0 ? 1.0 : 0.0; u1 = h1 ? 1.0 : 0.0; u2 = h2 ? 1.0 : 0.0;
+		d0 = 1.0 - u0; d1 = 1.0 - u1; d2 = 1.0 - u2;
+		PIN_REG(u0); PIN_REG(u1); PIN_REG(u2); PIN_REG(d0); PIN_REG(d1); PIN_REG(d2);
+	}
+	// P = sum_{j<gl} tp_j,  S = sum_{j>gl} ts_j
+	__device__ __forceinline__ void run(double tp, double ts, double &P, double &S) const
+	{
+		// a partner above me needs my prefix term and sends its suffix term; a partner below me the other way round
+		const double s0 = h0 ? ts : tp, s1 = h1 ? ts : tp, s2 = h2 ? ts : tp;
+		const double r1 = __shfl_xor_sync(FULLMASK, s0, 1, 8);
+		const double r2 = __shfl_xor_sync(FULLMASK, s1, 2, 8), r3 = __shfl_xor_sync(FULLMASK, s1, 3, 8);
+		const double r4 = __shfl_xor_sync(FULLMASK, s2, 4, 8), r5 = __shfl_xor_sync(FULLMASK, s2, 5, 8);
+		const double r6 = __shfl_xor_sync(FULLMASK, s2, 6, 8), r7 = __shfl_xor_sync(FULLMASK, s2, 7, 8);
+		const double q1 = r2 + r3, q2 = (r4 + r5) + (r6 + r7);
+		P = fma(u2, q2, fma(u1, q1, u0 * r1));
+		S = fma(d2, q2, fma(d1, q1, d0 * r1));
+	}
+};
+
+template <>
+struct DualScan<16> {
+	bool h2, h3;
+	double u0, u1, u2, u3, d0, d1, d2, d3;
+	__device__ __forceinline__ void init(int gl)
+	{
+		h2 = (gl & 4) != 0; h3 = (gl & 8) != 0;
+		u0 = (gl & 1) ? 1.0 : 0.0; u1 = (gl & 2) ? 1.0 : 0.0; u2 = h2 ? 1.0 : 0.0; u3 = h3 ? 1.0 : 0.0;
+		d0 = 1.0 - u0; d1 = 1.0 - u1; d2 = 1.0 - u2; d3 = 1.0 - u3;
+		PIN_REG(u0); PIN_REG(u1); PIN_REG(u2); PIN_REG(u3); PIN_REG(d0); PIN_REG(d1); PIN_REG(d2); PIN_REG(d3);
+	}
+	__device__ __forceinline__ void run(double tp, double ts, double &P, double &S) const
+	{
+		// round 1, inside quads of lanes: both terms travel, because the quad totals are needed as well
+		const double p1 = __shfl_xor_sync(FULLMASK, tp, 1, 16), s1 = __shfl_xor_sync(FULLMASK, ts, 1, 16);
+		const double p2 = __shfl_xor_sync(FULLMASK, tp, 2, 16), s2 = __shfl_xor_sync(FULLMASK, ts, 2, 16);
+		const double p3 = __shfl_xor_sync(FULLMASK, tp, 3, 16), s3 = __shfl_xor_sync(FULLMASK, ts, 3, 16);
+		const double qp = p2 + p3, qs = s2 + s3;
+		const double Pq = fma(u1, qp, u0 * p1), Sq = fma(d1, qs, d0 * s1);
+		const double Tp = (tp + p1) + qp, Ts = (ts + s1) + qs;
+		// round 2, between quads: one value per partner quad, as in DualScan<8>
+		const double t2 = h2 ? Ts : Tp, t3 = h3 ? Ts : Tp;
+		const double r4 = __shfl_xor_sync(FULLMASK, t2, 4, 16);
+		const double r8 = __shfl_xor_sync(FULLMASK, t3, 8, 16), r12 = __shfl_xor_sync(FULLMASK, t3, 12, 16);
+		const double q3 = r8 + r12;
+		P = fma(u3, q3, fma(u2, r4, Pq));
+		S = fma(d3, q3, fma(d2, r4, Sq));
+	}
+};
+
+// exclusive prefix sums of a[0..SPL) inside a lane (lp[i] = a[0] + .. + a[i-1]) and the total, as a tree: the total
+// is log2 SPL additions deep
+template <int SPL>
+__device__ __forceinline__ void local_prefix(const double (&a)[SPL], double (&lp)[SPL], double &tot)
+{
+	if (SPL == 1) {
+		lp[0] = 0.0;
+		tot = a[0];
+	} else if (SPL == 2) {
+		lp[0] = 0.0;
+		lp[1] = a[0];
+		tot = a[0] + a[1];
+	} else if (SPL == 4) {
+		const double p01 = a[0] + a[1], p23 = a[2] + a[3];
+		lp[0] = 0.0; lp[1] = a[0]; lp[2] = p01; lp[3] = p01 + a[2];
+		tot = p01 + p23;
+	} else if (SPL == 8) {
+		const double p01 = a[0] + a[1], p23 = a[2] + a[3], p45 = a[4] + a[5], p67 = a[6] + a[7];
+		const double q03 = p01 + p23, q47 = p45 + p67, q05 = q03 + p45;
+		lp[0] = 0.0; lp[1] = a[0]; lp[2] = p01; lp[3] = p01 + a[2];
+		lp[4] = q03; lp[5] = q03 + a[4]; lp[6] = q05; lp[7] = q05 + a[6];
+		tot = q03 + q47;
+	} else {
+		double t = 0.0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			lp[i] = t;
+			t += a[i];
+		}
+		tot = t;
+	}
+}
+template <int SPL>
+__device__ __forceinline__ void local_suffix(const double (&c)[SPL], double (&ls)[SPL], double &tot)
+{
+	double r[SPL], lr[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) r[i] = c[SPL - 1 - i];
+	local_prefix<SPL>(r, lr, tot);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) ls[i] = lr[SPL - 1 - i];
+}
+template <int SPL>
+__device__ __forceinline__ double local_sum(const double (&a)[SPL])
+{
+	if (SPL == 4) return (a[0] + a[1]) + (a[2] + a[3]);
+	if (SPL == 8) return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+	double t = 0.0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) t += a[i];
+	return t;
+}
+
+// out[i] = D[i] x[i] + pc[i] * sum_{j<i} pm[j] x[j] + sc[i] * sum_{j>i} sm[j] x[j]  (same contract as semisep)
+template <int SPL, int G>
+__device__ __forceinline__ void semisep2(const double (&x)[SPL], const double (&pm)[SPL], const double (&pc)[SPL],
+                                         const double (&sm)[SPL], const double (&sc)[SPL], const double (&D)[SPL],
+                                         const DualScan<G> &ds, double (&out)[SPL])
+{
+	double a[SPL], c[SPL], lp[SPL], ls[SPL], tp, ts, P, S;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		a[i] = x[i] * pm[i];
+		c[i] = x[i] * sm[i];
+	}
+	local_prefix<SPL>(a, lp, tp);
+	local_suffix<SPL>(c, ls, ts);
+	ds.run(tp, ts, P, S);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		double base = D[i] * x[i]; // independent of the shuffles (lp[0] and ls[SPL-1] are zero)
+		if (i > 0) base = fma(pc[i], lp[i], base);
+		if (i < SPL - 1) base = fma(sc[i], ls[i], base);
+		out[i] = fma(sc[i], S, fma(pc[i], P, base));
+	}
+}
+// full exclusive prefix P[i] = sum_{j<i} pm[j] x[j] and suffix S[i] = sum_{j>i} sm[j] x[j] (same contract as prefsuf)
+template <int SPL, int G>
+__device__ __forceinline__ void prefsuf2(const double (&x)[SPL], const double (&pm)[SPL], const double (&sm)[SPL],
+                                         const DualScan<G> &ds, double (&P)[SPL], double (&S)[SPL])
+{
+	double a[SPL], c[SPL], lp[SPL], ls[SPL], tp, ts, p, s;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		a[i] = x[i] * pm[i];
+		c[i] = x[i] * sm[i];
+	}
+	local_prefix<SPL>(a, lp, tp);
+	local_suffix<SPL>(c, ls, ts);
+	ds.run(tp, ts, p, s);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		P[i] = p + lp[i];
+		S[i] = s + ls[i];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: transfer operators.  grid = (n_k1_chunks, NP / COLS), block = COLS * G threads; the lane group
+// of column j pushes the unit vector e_j through every bin of the chunk.
+// T[c] is stored column-major (column j = 64 consecutive doubles), mantissas only; Tex[c][j] holds
+// the power-of-two exponent of column j.
+// ------------------------------------------------------------------------------------------------
+// Is the operator of sub-chunk s used by the boundary chains (k_chain_subs) under the flag picture `flags`?  Its parent
+// chunk must be flagged; and the sub-chunk at the far end of a chunk (the last one going forward, dir 0; the first one
+// going backward, dir 1) only carries the vector into the NEXT chunk of the run, so it is needed only if that chunk is
+// flagged as well (one operator in eight otherwise computed for nothing).  flags has guard entries at -1 and n.
+__device__ __forceinline__ bool op_needed(const int32_t *__restrict__ flags, const int32_t *__restrict__ parent,
+                                          const int32_t *__restrict__ chunk_sub0, int s, int dir)
+{
+	const int p = parent[s];
+	if (!flags[p]) return false;
+	if (dir == 0) return !(chunk_sub0[p + 1] - 1 == s) || flags[p + 1] != 0;
+	return !(chunk_sub0[p] == s) || flags[p - 1] != 0;
+}
+
+template <int SPL, int G, int COLS>
+__global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ chunks, const int32_t *__restrict__ k1_list,
+                                                      const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                      double *__restrict__ T, int32_t *__restrict__ Tex, int N,
+                                                      const int32_t *__restrict__ flag, int sel, const int32_t *__restrict__ skip,
+                                                      int n_items, const int32_t *__restrict__ chunk_sub0, int dir)
+{
+	constexpr int NP = SPL * G;
+	// sel 0: chunk list (transfer mode), one block row per listed chunk.  sel 3: repair rounds of the warm-up mode: `chunks`
+	// is the SUB-chunk table; the block rows stride over it and work on the sub-chunks whose parent chunk is flagged (flag has
+	// guard entries at -1 and n) -- a few hundred of ~19 000, so a block row per sub-chunk would spend 0.1 ms per launch on
+	// scheduling empty blocks (measured).  k1_list = parent chunk of every sub-chunk in this mode; `skip` marks parents whose
+	// operators are already there (computed ahead of time from the previous E-step's failures, see launch_warm).
+	for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+	const int c = sel == 0 ? k1_list[item] : item;
+	if (sel == 3 && (!op_needed(flag, k1_list, chunk_sub0, c, dir) || (skip && op_needed(skip, k1_list, chunk_sub0, c, dir)))) continue;
+	const Chunk ch = chunks[c];
+	const int gl = threadIdx.x % G;
+	const int col = blockIdx.y * COLS + threadIdx.x / G;
+	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], f[SPL];
+	const int s0 = gl * SPL;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = model[M_U * NP + s0 + i];
+		cV[i] = model[M_V * NP + s0 + i];
+		cW[i] = model[M_W * NP + s0 + i];
+		cZ[i] = model[M_Z * NP + s0 + i];
+		cD[i] = model[M_D * NP + s0 + i];
+		e0[i] = model[M_E0 * NP + s0 + i];
+		f[i] = (s0 + i == col && col < N) ? 1.0 : 0.0;
+	}
+	int ex = 0;
+	const int uend = ch.u0 + ch.len;
+	uint32_t word = 0;
+	DualScan<G> ds;
+	ds.init(gl);
+	for (int u = ch.u0; u < uend; ++u) {
+		if (u == ch.u0 || (u & 15) == 0) word = __ldg(obs + ch.ow0 + (u >> 4));
+		const int x = (word >> ((u & 15) * 2)) & 3;
+		double out[SPL];
+		if (u == 0) { // first bin of the sequence: emission only (khmm.c:171-174 has no transition there)
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) out[i] = f[i];
+		} else {
+			semisep2<SPL, G>(f, cW, cZ, cU, cV, cD, ds, out);
+		}
+		if (x == 0) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = out[i] * e0[i];
+		} else if (x == 1) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = out[i] * (1.0 - e0[i]);
+		} else {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = out[i];
+		}
+		if (((u - ch.u0) & 15) == 15 || u == uend - 1) { // exact power-of-two rescale of the column
+			double t = 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) t += f[i];
+			t = gsum<G>(t);
+			if (t > 1e-290 && t < 1e290) {
+				const int k = exponent_of(t);
+				const double sc = pow2i(-k);
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) f[i] *= sc;
+				ex += k;
+			}
+		}
+	}
+	double *Tc = T + (size_t)c * NP * NP + (size_t)col * NP + s0;
+	store_vec<SPL>(Tc, f);
+	if (gl == 0) Tex[(size_t)c * NP + col] = ex;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: boundary chains.  One block per (sequence, direction); blockDim = NP.
+//   dir 0: vstart[c+1] = normalise( T_c * vstart[c] ), starting from a0 at the first chunk.
+//   dir 1: bend[c] = T_{c+1}^T * bend[c+1], starting from ones at the last chunk (direction only).
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+	// NP threads, NP in {32,64,128}
+	v = gsum<32>(v);
+	if (NP > 32) {
+		__syncthreads();
+		if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+		__syncthreads();
+		double t = 0.0;
+#pragma unroll
+		for (int w = 0; w < NP / 32; ++w) t += red[w];
+		v = t;
+	}
+	return v;
+}
+template <int NP>
+__device__ __forceinline__ int block_max_i(int v, int *red)
+{
+	v = gmax_i<32>(v);
+	if (NP > 32) {
+		__syncthreads();
+		if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+		__syncthreads();
+		int t = INT_MIN;
+#pragma unroll
+		for (int w = 0; w < NP / 32; ++w) t = max(t, red[w]);
+		v = t;
+	}
+	return v;
+}
+
+// v <- normalise(T_c v): thread i holds v[i]; returns the new v[i]  (column-major mantissas + per-column exponents)
+template <int NP>
+__device__ __forceinline__ double chain_fwd_step(const double *__restrict__ Tc, const int32_t *__restrict__ Texc, double v,
+                                                 double *vec, double *red, int *redi)
+{
+	const int i = threadIdx.x;
+	const int ex = Texc[i];
+	int e = (v > 0.0) ? ex + ilogb(v) : INT_MIN;
+	const int emax = block_max_i<NP>(e, redi);
+	__syncthreads();
+	vec[i] = (v > 0.0) ? scalbn(v, ex - emax) : 0.0;
+	__syncthreads();
+	double acc = 0.0;
+#pragma unroll 8
+	for (int j = 0; j < NP; ++j) acc = fma(__ldg(Tc + (size_t)j * NP + i), vec[j], acc);
+	const double tot = block_sum<NP>(acc, red);
+	return acc / tot;
+}
+// b <- T_c^T b (direction only, rescaled so that the largest entry is ~1)
+template <int NP>
+__device__ __forceinline__ double chain_bwd_step(const double *__restrict__ Tc, const int32_t *__restrict__ Texc, double b,
+                                                 double *vec, int *redi)
+{
+	const int i = threadIdx.x;
+	const double *col = Tc + (size_t)i * NP; // column i of T_c
+	__syncthreads();
+	vec[i] = b;
+	__syncthreads();
+	double d = 0.0;
+#pragma unroll 8
+	for (int j = 0; j < NP; ++j) d = fma(__ldg(col + j), vec[j], d);
+	const int ex = Texc[i];
+	int e = (d > 0.0) ? ex + ilogb(d) : INT_MIN;
+	const int emax = block_max_i<NP>(e, redi);
+	return (d > 0.0) ? scalbn(d, ex - emax) : 0.0;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(NP) k_chain(const int32_t *__restrict__ seq_c0, const int32_t *__restrict__ seq_nc,
+                                              const double *__restrict__ T, const int32_t *__restrict__ Tex,
+                                              const double *__restrict__ model, double *__restrict__ vstart,
+                                              double *__restrict__ bend, int n_seqs)
+{
+	__shared__ double vec[NP];
+	__shared__ double red[4];
+	__shared__ int redi[4];
+	const int seq = blockIdx.x % n_seqs, dir = blockIdx.x / n_seqs;
+	const int c0 = seq_c0[seq], nc = seq_nc[seq];
+	const int i = threadIdx.x;
+	if (nc <= 1) return;
+	if (dir == 0) {
+		double v = model[M_A0 * NP + i];
+		for (int c = c0; c < c0 + nc - 1; ++c) {
+			v = chain_fwd_step<NP>(T + (size_t)c * NP * NP, Tex + (size_t)c * NP, v, vec, red, redi);
+			vstart[(size_t)(c + 1) * NP + i] = v;
+		}
+	} else {
+		double b = 1.0;
+		for (int c = c0 + nc - 2; c >= c0; --c) {
+			b = chain_bwd_step<NP>(T + (size_t)(c + 1) * NP * NP, Tex + (size_t)(c + 1) * NP, b, vec, redi);
+			bend[(size_t)c * NP + i] = b;
+		}
+	}
+}
+
+// Repair rounds of the warm-up mode.  Flagged chunks are repaired at SUB-chunk granularity (every chunk is pre-split
+// into pieces of ~1.5k bins) so that the latency-bound pieces of a repair (transfer operators, recompute) are short.
+// One block per chunk; only the HEAD of a run of failed boundaries works and walks the sub-chunks of its run.
+//   dir 0 (forward): head = flag[c] && !flag[c-1]; the exact vector in front of the run is the last stored vector of
+//          chunk c-1; vsub[s] (start vector of every sub-chunk of the run) follows through the sub-chunk operators.
+//   dir 1 (backward): head = flag[c] && !flag[c+1]; the exact direction at the end of chunk c is bexact[c];
+//          bsub[s] = direction of b at the last bin of sub-chunk s.
+template <int NP>
+__global__ void __launch_bounds__(NP) k_chain_subs(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
+                                                   const int32_t *__restrict__ chunk_sub0, const int32_t *__restrict__ flag, int dir,
+                                                   const double *__restrict__ T, const int32_t *__restrict__ Tex,
+                                                   const double *__restrict__ fhat, const double *__restrict__ bexact,
+                                                   double *__restrict__ vsub, double *__restrict__ bsub)
+{
+	__shared__ double vec[NP];
+	__shared__ double red[4];
+	__shared__ int redi[4];
+	const int c = blockIdx.x, i = threadIdx.x;
+	if (dir == 0) {
+		if (!flag[c] || flag[c - 1]) return;
+		int s = chunk_sub0[c];
+		double v = fhat[((size_t)subs[s].gb0 - 1) * NP + i];
+		vsub[(size_t)s * NP + i] = v;
+		while (s + 1 < n_sub && flag[parent[s + 1]]) {
+			v = chain_fwd_step<NP>(T + (size_t)s * NP * NP, Tex + (size_t)s * NP, v, vec, red, redi);
+			++s;
+			vsub[(size_t)s * NP + i] = v;
+		}
+	} else {
+		if (!flag[c] || flag[c + 1]) return;
+		int s = chunk_sub0[c + 1] - 1;
+		double b = bexact[(size_t)c * NP + i];
+		bsub[(size_t)s * NP + i] = b;
+		while (s - 1 >= 0 && flag[parent[s - 1]]) {
+			b = chain_bwd_step<NP>(T + (size_t)s * NP * NP, Tex + (size_t)s * NP, b, vec, redi);
+			--s;
+			bsub[(size_t)s * NP + i] = b;
+		}
+	}
+}
+
+// after a repair round: fold the per-sub-chunk results of every flagged chunk back into the per-chunk arrays
+// (dir 0: log-likelihood partials; dir 1: expected-count partials).  One block per chunk.
+__global__ void __launch_bounds__(128) k_fold(const int32_t *__restrict__ chunk_sub0, const int32_t *__restrict__ flag, int dir, int NP,
+                                              const double *__restrict__ llsub, double *__restrict__ llpart,
+                                              const double *__restrict__ partsub, double *__restrict__ part)
+{
+	const int c = blockIdx.x;
+	if (!flag[c]) return;
+	const int s0 = chunk_sub0[c], s1 = chunk_sub0[c + 1];
+	if (dir == 0) {
+		if (threadIdx.x == 0) {
+			double t = 0.0;
+			for (int s = s0; s < s1; ++s) t += llsub[s];
+			llpart[c] = t;
+		}
+	} else {
+		const int n = S_COUNT * NP;
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+			double t = 0.0;
+			for (int s = s0; s < s1; ++s) t += partsub[(size_t)s * n + j];
+			part[(size_t)c * n + j] = t;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-lane model constants of a warp that holds one state vector (G = 32 lanes x SPL states).
+// ------------------------------------------------------------------------------------------------
+// emission of symbol x in a state with hom-emission e0: x = 0 -> e0, x = 1 -> 1 - e0 (bit-identical to the host's
+// e[1][k] = 1.0 - e[0][k], core.c:125), x = 2 (missing) -> 1 (khmm.c:21); branch-free: em = c1 * e0 + c0
+__device__ __forceinline__ void emis_coef(int x, double &c0, double &c1)
+{
+	c0 = (x == 0) ? 0.0 : 1.0;
+	c1 = (x == 0) ? 1.0 : ((x == 1) ? -1.0 : 0.0);
+}
+
+template <int SPL>
+struct LaneModel {
+	double U[SPL], V[SPL], W[SPL], Z[SPL], D[SPL], e0[SPL];
+	__device__ __forceinline__ void load(const double *__restrict__ model, int s0, int NP)
+	{
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			U[i] = model[M_U * NP + s0 + i];
+			V[i] = model[M_V * NP + s0 + i];
+			W[i] = model[M_W * NP + s0 + i];
+			Z[i] = model[M_Z * NP + s0 + i];
+			D[i] = model[M_D * NP + s0 + i];
+			e0[i] = model[M_E0 * NP + s0 + i];
+		}
+	}
+};
+
+// Hilbert projective mismatch max_i(x_i/y_i) / min_i(x_i/y_i) - 1 of two vectors held like state vectors
+// (states >= N ignored); 1e300 if their supports differ.  Same value in every lane.
+template <int SPL>
+__device__ __forceinline__ double warp_mismatch(const double (&x)[SPL], const double (&y)[SPL], int s0, int N)
+{
+	double mx = 0.0, mn = 1e300;
+	bool bad = false;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		if (s0 + i < N) {
+			if ((x[i] > 0.0) != (y[i] > 0.0)) bad = true;
+			else if (x[i] > 0.0) {
+				const double r = x[i] / y[i];
+				mx = fmax(mx, r);
+				mn = fmin(mn, r);
+			}
+		}
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		mx = fmax(mx, __shfl_xor_sync(FULLMASK, mx, d));
+		mn = fmin(mn, __shfl_xor_sync(FULLMASK, mn, d));
+	}
+	bad = __any_sync(FULLMASK, bad);
+	return (!bad && mn < 1e300 && mn > 0.0) ? mx / mn - 1.0 : 1e300;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Work assignment of the chunk kernels: a state vector is held by a GROUP of G consecutive lanes (SPL = NP/G
+// states per lane), so a warp runs 32/G chunks side by side in lock step.  Narrow groups make the scans
+// work-efficient (log2 G shuffle rounds shared by 32/G chunks) and give the FP64 pipe independent work.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+struct GroupId {
+	int c, gl;
+	bool valid;
+	__device__ __forceinline__ GroupId(int n_chunks)
+	{
+		const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+		gl = lane % G;
+		c = warp * (32 / G) + lane / G;
+		valid = c < n_chunks;
+		if (!valid) c = n_chunks - 1; // idle groups shadow a real chunk so that every address they form stays legal
+	}
+};
+
+// trip count of a lock-step loop: the largest count of the warp's groups, identical in every lane (and provably so
+// for ptxas, which otherwise wraps every shuffle of the loop in WARPSYNC/ENDCOLLECTIVE)
+__device__ __forceinline__ int warp_trips(int n)
+{
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) n = max(n, __shfl_xor_sync(FULLMASK, n, d));
+	return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward over bins [ubeg, u0+len) of chunk ch by one lane group, starting from f (the normalised forward
+// vector of bin ubeg-1, or a0 when ubeg == 0).  Bins >= u0 are stored (f_u, s_u) and enter the
+// log-likelihood; bins < u0 are warm-up.  If fwarm_c != nullptr the vector reached at bin u0-1 is saved
+// there.  On return f is the vector of the chunk's last bin.  (khmm.c:171-185 with O(N) transitions.)
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G>
+__device__ __forceinline__ double forward_chunk(const Chunk &ch, bool valid, int ubeg, const LaneModel<SPL> &M, double (&f)[SPL],
+                                                int gl, const uint32_t *__restrict__ obs, double *__restrict__ fhat,
+                                                double *__restrict__ sc, double *__restrict__ fwarm_c)
+{
+	// The recursion carries g_u = (M_u g_{u-1}) * rho_u with the ONE-STEP-DELAYED scale rho_u = 1 / sum(g_{u-1}).
+	// Then sum(g_u) = s_u exactly (the reference's scale factor, khmm.c:183-184) and f_u = g_u / s_u, while the
+	// reduction and the division that produce rho_{u+1} overlap the next transition instead of sitting on the
+	// dependency chain (the chain per bin is scan + combine only).  On entry f is normalised (rho = 1).
+	constexpr int NP = SPL * G;
+	const int s0 = gl * SPL;
+	double ll = 0.0, prod = 1.0;
+	const int uend = ch.u0 + ch.len;
+	const int trips = warp_trips(valid ? uend - ubeg : 0);
+	uint32_t word = 0;
+	double g[SPL], rho = 1.0;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) g[i] = f[i];
+	ScanMasks<G> mk;
+	mk.init(gl);
+	mk.pin();
+	for (int t = 0; t < trips; ++t) {
+		const int u = ubeg + t;
+		const bool act = valid && u < uend;
+		const int uo = act ? u : uend - 1; // idle groups keep reading a legal word
+		if (t == 0 || (uo & 15) == 0) word = __ldg(obs + ch.ow0 + (uo >> 4));
+		const int x = (word >> ((uo & 15) * 2)) & 3;
+		double out[SPL];
+		semisep<SPL, G>(g, M.W, M.Z, M.U, M.V, M.D, mk, out);
+		double tsum = 0.0, c0, c1;
+		emis_coef(x, c0, c1);
+		c0 *= rho;
+		c1 *= rho;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			out[i] = ((u == 0) ? g[i] : out[i]) * fma(c1, M.e0[i], c0); // first bin of a sequence: no transition (khmm.c:171-174)
+			tsum += out[i];
+		}
+		const double s = gsum<G>(tsum); // = s_u
+		const double inv = fast_rcp(s);
+		if (act) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) g[i] = out[i];
+			rho = inv;
+			if (u >= ch.u0) {
+				double fn[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) fn[i] = out[i] * inv;
+				store_vec<SPL>(fhat + ((size_t)ch.gb0 + (u - ch.u0)) * NP + s0, fn);
+				if (gl == 0) sc[ch.gb0 + (u - ch.u0)] = s;
+				prod *= s; // running product with reset, as hmm_lk (khmm.c:251-258)
+				if (prod < 1e-100 || prod > 1e100) {
+					ll += log(prod);
+					prod = 1.0;
+				}
+			} else if (u == ch.u0 - 1 && fwarm_c) {
+				double fn[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) fn[i] = out[i] * inv;
+				store_vec<SPL>(fwarm_c + s0, fn);
+			}
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) f[i] = g[i] * rho; // normalised vector of the last bin
+	return ll + log(prod);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second-generation forward over a chunk (same contract as forward_chunk).  Differences, all about latency:
+//   * the recursion carries an UNNORMALISED vector g_u = q_u * diag(e_{x_u}) A^T g_{u-1}; q_u is 1 or an exact power
+//     of two that is switched on when the sum has dropped below 2^-200 -- nothing on the per-bin dependency chain
+//     depends on a reduction any more.  With S_u = sum(g_u): s_u = S_u / (q_u S_{u-1}) (the reference's scale factor,
+//     khmm.c:183-184), f_u = g_u / S_u, and sum_u log s_u telescopes to log S_last - log S_before - log2(prod q) ln 2.
+//   * during the warm-up overlap nothing else is computed; in the store phase the reduction, the reciprocal and the
+//     stores of bin u-1 are issued together with the scan of bin u (software pipelining by one bin), so that their
+//     shuffle latency hides behind the scan's.
+//   * the lane groups of a warp are aligned at the END of their chunks, so that all of them are in the same phase.
+// ------------------------------------------------------------------------------------------------
+#ifndef PSMC_BOOST_BITS
+#define PSMC_BOOST_BITS 200 /* the emulation tests also build with a small value so that boosts happen every few bins */
+#endif
+#define PSMC_BOOST_LOW pow2i(-PSMC_BOOST_BITS)
+#define PSMC_BOOST_UP pow2i(PSMC_BOOST_BITS)
+__device__ __forceinline__ int warp_min_i(int n)
+{
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) n = min(n, __shfl_xor_sync(FULLMASK, n, d));
+	return n;
+}
+template <int SPL, int G>
+struct ForwardRun {
+	static constexpr int NP = SPL * G;
+	const Chunk &ch;
+	const LaneModel<SPL> &M;
+	const bool valid;
+	const int gl, s0, u0, uend;
+	const uint32_t *__restrict__ obs;
+	double *__restrict__ fhat, *__restrict__ sc, *__restrict__ fwarm_c;
+	DualScan<G> ds;
+	double g[SPL], ps, inv_prev, qc, rq_cur, Sstart;
+	// `valid`, "has this group started" and "is there a warm-up vector to publish" are folded into bin indices the
+	// loop compares u with (one ISETP each; a bool that lives across the loop gets re-derived from threadIdx in every
+	// iteration once registers are tight -- measured):
+	int u_store; // bins u-1 >= u_store are stored                (u0, or never for an idle shadow group)
+	int u_first; // Sstart = S of the bin before bin u_first      (u0, or never)
+	int u_warm;  // the vector of bin u_warm - 1 goes to fwarm_c  (u0 after a warm-up, or never)
+	int u_boost; // boosts of bins >= u_boost enter the log-likelihood
+	int kq, ubase, wlast, tpend, mystart;
+	uint32_t wa, wb, wna, wnb; // packed observation words of the current block (word ia and the one after it) / of the next block (ina)
+	int ia, ina;
+	double *prow, *psc; // where the row / scale factor of the bin finished by the next store-phase step go (advance one bin per step)
+
+	__device__ __forceinline__ ForwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_,
+	                                      const uint32_t *__restrict__ obs_, double *__restrict__ fhat_, double *__restrict__ sc_,
+	                                      double *__restrict__ fwarm_c_)
+	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), u0(ch_.u0), uend(ch_.u0 + ch_.len), obs(obs_),
+	      fhat(fhat_), sc(sc_), fwarm_c(fwarm_c_)
+	{
+	}
+
+	// A group whose chunk needs fewer steps than the longest one of its warp starts late: until then it computes on
+	// whatever its registers hold (no per-step select keeps it idle) and picks up its real start vector here.
+	__device__ __forceinline__ void start_due(int t, const double (&f)[SPL], double inv_before)
+	{
+		if (mystart == t) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) g[i] = f[i];
+			ps = local_sum<SPL>(g);
+			inv_prev = inv_before;
+			rq_cur = 1.0;
+			qc = 1.0;
+		}
+		tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
+	}
+
+	// A block = the steps [t, tstop) between two multiples of 16 (or up to a late start / the end of the phase).  Makes the
+	// words prefetched for a block starting at t current and fetches those of the block starting at tstop (indices clamped
+	// to the sequence, so idle groups read legal words too; the loads have a whole block to complete).
+	__device__ __forceinline__ int begin_block(int t, int tend)
+	{
+		const int tstop = min(min(tend, tpend), (t & ~15) + 16);
+		wa = wna; wb = wnb; ia = ina;
+		ina = (ubase + tstop) >> 4;
+		wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast));
+		wnb = __ldg(obs + ch.ow0 + min(max(ina + 1, 0), wlast));
+		return tstop;
+	}
+
+	// bin u = ubase + t is formed from the current vector (bin u-1); BOOK: finish bin u-1 (sum, reciprocal, stores) alongside
+	template <bool BOOK>
+	__device__ __forceinline__ void step(int t)
+	{
+		const int u = ubase + t;
+		// the (at most two) packed words of this block of <= 16 bins were fetched during the previous block (begin_block):
+		// no load and no address arithmetic in here
+		const int x = ((((u >> 4) == ia) ? wa : wb) >> ((u & 15) * 2)) & 3;
+		double c0, c1;
+		emis_coef(x, c0, c1);
+		c0 *= qc;
+		c1 *= qc;
+		double out[SPL];
+		semisep2<SPL, G>(g, M.W, M.Z, M.U, M.V, M.D, ds, out);
+		if (BOOK) { // (written after the scan so that the scheduler issues the scan's shuffles first and this reduction in their shadow)
+			const double S1 = gsum<G>(ps); // = S_{u-1}
+			const double inv1 = fast_rcp(S1);
+			const bool st_f = u - 1 >= u_store, st_w = u == u_warm;
+			if (st_f || st_w) {
+				double fn[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) fn[i] = g[i] * inv1;
+				store_vec<SPL>(st_f ? prow : fwarm_c + s0, fn);
+			}
+			if (st_f && gl == 0) *psc = S1 * inv_prev * rq_cur;
+			prow += NP;
+			psc += 1;
+			if (u == u_first) Sstart = S1;
+			const bool boosted = qc != 1.0;
+			rq_cur = boosted ? PSMC_BOOST_LOW : 1.0;
+			if (boosted && u >= u_boost) kq += PSMC_BOOST_BITS;
+			inv_prev = inv1;
+			qc = (S1 < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0; // acts on the NEXT bin: off the dependency chain
+		} else {
+			qc = 1.0; // (the warm-up phase decides once per block of 16 bins, see run)
+		}
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = out[i] * fma(c1, M.e0[i], c0);
+		ps = local_sum<SPL>(g);
+	}
+
+	__device__ __forceinline__ double run(int ubeg_in, double (&f)[SPL])
+	{
+		int ubeg = ubeg_in;
+		const bool warmed = ubeg_in < u0;
+		wlast = (ch.Lseq - 1) >> 4;
+		ds.init(gl);
+		Sstart = 1.0;
+		kq = 0;
+		double inv_before = 1.0; // 1 / S of the bin before the start vector's bin (only the first bin of a sequence needs it)
+		const double S_init = gsum<G>(local_sum<SPL>(f)); // (every lane of the warp takes part)
+		bool have_start = false;
+		if (ubeg_in == 0) {
+			// first bin of a sequence: emission only, no transition (khmm.c:171-174); f is a0 here.  Done in front of the loop
+			// so that the loop body has no special case: the start vector becomes bin 0 (unnormalised) and bin 1 is formed first.
+			const int x = __ldg(obs + ch.ow0) & 3;
+			double c0, c1;
+			emis_coef(x, c0, c1);
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] *= fma(c1, M.e0[i], c0);
+			inv_before = fast_rcp(S_init);
+			if (u0 == 0) {
+				Sstart = S_init;
+				have_start = true;
+			}
+			ubeg = 1;
+		}
+		// from here on: f = vector of bin ubeg-1, the group forms bins ubeg .. uend-1 and is aligned with the other groups at the END
+		const int never = INT_MAX / 2;
+		u_store = valid ? u0 : never;
+		u_first = (valid && !have_start) ? u0 : never;
+		u_warm = (valid && warmed && fwarm_c != nullptr) ? u0 : never;
+		u_boost = valid ? max(u0, ubeg) : never;
+		const int mytrips = valid ? uend - ubeg : 0;
+		const int trips = warp_trips(mytrips);
+		const int tB = warp_min_i(valid ? trips - (uend - max(u0, ubeg)) : trips); // first step in which some group forms a bin it stores
+		ubase = uend - trips;
+		mystart = valid ? trips - mytrips : INT_MAX;
+		ina = ubase >> 4; // words of the first block (begin_block makes them current)
+		wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast));
+		wnb = __ldg(obs + ch.ow0 + min(max(ina + 1, 0), wlast));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = f[i];
+		ps = local_sum<SPL>(g);
+		inv_prev = inv_before;
+		rq_cur = 1.0;
+		qc = 1.0;
+		tpend = warp_min_i(mystart);
+		int t = 0;
+		while (t < tB) { // warm-up phase, in blocks of at most 16 bins: late starts and the boost decision sit between blocks
+			if (t == tpend) start_due(t, f, inv_before);
+			const int tstop = begin_block(t, tB);
+			qc = (gsum<G>(ps) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+			for (; t < tstop; ++t) step<false>(t);
+		}
+		qc = 1.0;
+		{ // integer arithmetic: for idle groups the address lies outside the buffers until their first stored bin (never dereferenced)
+			const long long row0 = (long long)ch.gb0 + ((long long)ubase + t - 1 - u0);
+			prow = (double *)((char *)fhat + (row0 * NP + s0) * (long long)sizeof(double));
+			psc = (double *)((char *)sc + row0 * (long long)sizeof(double));
+		}
+		while (t < trips) { // store phase
+			if (t == tpend) start_due(t, f, inv_before);
+			const int tstop = begin_block(t, trips);
+			for (; t < tstop; ++t) step<true>(t);
+		}
+		if (mytrips == 0) { // nothing formed in the loop (a one-bin chunk at the start of a sequence): the start vector is the last bin
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) g[i] = f[i];
+			ps = local_sum<SPL>(g);
+			inv_prev = inv_before;
+			rq_cur = 1.0;
+		}
+		// finish the last bin
+		const double S1 = gsum<G>(ps), inv1 = fast_rcp(S1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) f[i] = g[i] * inv1;
+		if (valid) {
+			store_vec<SPL>(fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + s0, f);
+			if (gl == 0) sc[ch.gb0 + (ch.len - 1)] = S1 * inv_prev * rq_cur;
+		}
+		return (log(S1) - log(Sstart)) - (double)kq * 0.69314718055994530942;
+	}
+};
+
+template <int SPL, int G>
+__device__ __forceinline__ double forward_chunk2(const Chunk &ch, bool valid, int ubeg, const LaneModel<SPL> &M, double (&f)[SPL],
+                                                 int gl, const uint32_t *__restrict__ obs, double *__restrict__ fhat,
+                                                 double *__restrict__ sc, double *__restrict__ fwarm_c)
+{
+	ForwardRun<SPL, G> r(ch, valid, M, gl, obs, fhat, sc, fwarm_c);
+	return r.run(ubeg, f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 pre-warm-up.  An overlap only has to deliver a start vector that is exact to 1e-12 AFTER its last few thousand
+// bins; what happens in its early part is forgotten geometrically.  So the early part runs in FP32 (one SHFL per
+// value instead of two, FFMA at full rate and 4 cycles of latency instead of DFMA at half rate and 9) in its own short
+// kernel, and the FP64 overlap of the forward / backward warm-up kernel starts from its result instead of from the
+// stationary vector.  FP32 leaves a relative error of ~1e-6 in the vector; the FP64 part contracts it like any other
+// start error (the certificate decides, as always).  8-lane groups only (NP <= 64).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DualScan8T { // DualScan<8> in the scalar type T
+	bool h0, h1, h2;
+	T u0, u1, u2, d0, d1, d2;
+	__device__ __forceinline__ void init(int gl)
+	{
+		h0 = (gl & 1) != 0; h1 = (gl & 2) != 0; h2 = (gl & 4) != 0;
+		u0 = h0 ? T(1) : T(0); u1 = h1 ? T(1) : T(0); u2 = h2 ? T(1) : T(0);
+		d0 = T(1) - u0; d1 = T(1) - u1; d2 = T(1) - u2;
+	}
+	__device__ __forceinline__ void run(T tp, T ts, T &P, T &S) const
+	{
+		const T s0 = h0 ? ts : tp, s1 = h1 ? ts : tp, s2 = h2 ? ts : tp;
+		const T r1 = __shfl_xor_sync(FULLMASK, s0, 1, 8);
+		const T r2 = __shfl_xor_sync(FULLMASK, s1, 2, 8), r3 = __shfl_xor_sync(FULLMASK, s1, 3, 8);
+		const T r4 = __shfl_xor_sync(FULLMASK, s2, 4, 8), r5 = __shfl_xor_sync(FULLMASK, s2, 5, 8);
+		const T r6 = __shfl_xor_sync(FULLMASK, s2, 6, 8), r7 = __shfl_xor_sync(FULLMASK, s2, 7, 8);
+		const T q1 = r2 + r3, q2 = (r4 + r5) + (r6 + r7);
+		P = fma(u2, q2, fma(u1, q1, u0 * r1));
+		S = fma(d2, q2, fma(d1, q1, d0 * r1));
+	}
+};
+template <typename T, int SPL>
+__device__ __forceinline__ void local_prefix_t(const T (&a)[SPL], T (&lp)[SPL], T &tot)
+{
+	T t = T(0);
+	if (SPL == 8) {
+		const T p01 = a[0] + a[1], p23 = a[2] + a[3], p45 = a[4] + a[5], p67 = a[6] + a[7];
+		const T q03 = p01 + p23, q47 = p45 + p67, q05 = q03 + p45;
+		lp[0] = T(0); lp[1] = a[0]; lp[2] = p01; lp[3] = p01 + a[2];
+		lp[4] = q03; lp[5] = q03 + a[4]; lp[6] = q05; lp[7] = q05 + a[6];
+		tot = q03 + q47;
+		return;
+	}
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		lp[i] = t;
+		t += a[i];
+	}
+	tot = t;
+}
+template <typename T, int SPL>
+__device__ __forceinline__ T local_sum_t(const T (&a)[SPL])
+{
+	T t = T(0);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) t += a[i];
+	return t;
+}
+template <typename T>
+__device__ __forceinline__ T gsum8_t(T t)
+{
+#pragma unroll
+	for (int d = 4; d > 0; d >>= 1) t += __shfl_xor_sync(FULLMASK, t, d, 8);
+	return t;
+}
+// out[i] = D[i] x[i] + pc[i] * sum_{j<i} pm[j] x[j] + sc[i] * sum_{j>i} sm[j] x[j]  (semisep2 in the scalar type T, 8 lanes)
+template <typename T, int SPL>
+__device__ __forceinline__ void semisep2_t(const T (&x)[SPL], const T (&pm)[SPL], const T (&pc)[SPL], const T (&sm)[SPL],
+                                           const T (&sc)[SPL], const T (&D)[SPL], const DualScan8T<T> &ds, T (&out)[SPL])
+{
+	T a[SPL], c[SPL], r[SPL], lp[SPL], lr[SPL], tp, ts, P, S;
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		a[i] = x[i] * pm[i];
+		c[i] = x[i] * sm[i];
+		r[SPL - 1 - i] = c[i];
+	}
+	local_prefix_t<T, SPL>(a, lp, tp);
+	local_prefix_t<T, SPL>(r, lr, ts); // suffix sums = prefix sums of the reversed array
+	ds.run(tp, ts, P, S);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		T base = D[i] * x[i];
+		if (i > 0) base = fma(pc[i], lp[i], base);
+		if (i < SPL - 1) base = fma(sc[i], lr[SPL - 1 - i], base);
+		out[i] = fma(sc[i], S, fma(pc[i], P, base));
+	}
+}
+
+// DIR 0: for every forward chunk whose FP64 overlap [u0 - warm64, u0) does not reach the start of its sequence, the forward
+//        vector of bin u0 - warm64 - 1 from warm32 bins further left (sum-normalised, as doubles) -> start[c].
+// DIR 1: for every backward chunk whose FP64 overlap (ulast, ulast + warm64] does not reach the end of its sequence, the
+//        direction of b at bin ulast + warm64 from warm32 bins further right -> start[c].
+// Same loop structure as the FP64 warm-up (groups aligned at the end, late starts between 16-bin blocks, boosts).
+template <int SPL, int DIR>
+__global__ void __launch_bounds__(128) k_prewarm(const Chunk *__restrict__ chunks, int n_chunks, const uint32_t *__restrict__ obs,
+                                                 const double *__restrict__ model, int warm64, int warm32, double *__restrict__ start)
+{
+	typedef float T;
+	constexpr int G = 8, NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	T cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], v[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = (T)model[M_U * NP + s0 + i];
+		cV[i] = (T)model[M_V * NP + s0 + i];
+		cW[i] = (T)model[M_W * NP + s0 + i];
+		cZ[i] = (T)model[M_Z * NP + s0 + i];
+		cD[i] = (T)model[M_D * NP + s0 + i];
+		e0[i] = (T)model[M_E0 * NP + s0 + i];
+		v[i] = DIR == 0 ? (T)model[M_A0 * NP + s0 + i] : T(1);
+	}
+	const int ulast = ch.u0 + ch.len - 1;
+	// bins processed: DIR 0: ua .. ub ascending (ub = u0 - warm64 - 1);  DIR 1: ua .. ub descending (ub = ulast + warm64 + 1)
+	bool need;
+	int ua, ub;
+	if (DIR == 0) {
+		need = id.valid && !(ch.flags & CH_FIRST) && ch.u0 - warm64 > 0;
+		ub = ch.u0 - warm64 - 1;
+		ua = max(0, ub - warm32 + 1);
+	} else {
+		need = id.valid && !(ch.flags & CH_LAST) && ulast + warm64 < ch.Lseq - 1;
+		ub = ulast + warm64 + 1;
+		ua = min(ch.Lseq - 1, ub + warm32 - 1);
+	}
+	const int mytrips = need ? (DIR == 0 ? ub - ua + 1 : ua - ub + 1) : 0;
+	const int trips = warp_trips(mytrips);
+	const int mystart = mytrips > 0 ? trips - mytrips : INT_MAX;
+	int tpend = warp_min_i(mystart);
+	const int wlast = (ch.Lseq - 1) >> 4;
+	const int ufirst = DIR == 0 ? ub - trips + 1 : ub + trips - 1; // bin of step 0 (may lie outside the sequence: clamped words)
+	const int uprev = DIR == 0 ? ufirst - 1 : ufirst + 1;          // as if this bin had just been processed
+	uint32_t word = __ldg(obs + ch.ow0 + min(max(uprev >> 4, 0), wlast));
+	uint32_t wnext = __ldg(obs + ch.ow0 + min(max((uprev >> 4) + (DIR == 0 ? 1 : -1), 0), wlast));
+	DualScan8T<T> ds;
+	ds.init(gl);
+	T g[SPL], q = T(1);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) g[i] = v[i];
+	int t = 0;
+	while (t < trips) {
+		if (t == tpend) { // warp-uniform, rare
+			if (mystart == t) {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) g[i] = v[i];
+			}
+			tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
+		}
+		const int tstop = min(min(trips, tpend), (t & ~15) + 16);
+		q = (gsum8_t<T>(local_sum_t<T, SPL>(g)) < T(9.094947e-13)) ? T(1.0995116e12) : T(1); // 2^-40 / 2^40
+		for (; t < tstop; ++t) {
+			const int u = DIR == 0 ? ufirst + t : ufirst - t;
+			if ((u & 15) == (DIR == 0 ? 0 : 15)) {
+				word = wnext;
+				wnext = __ldg(obs + ch.ow0 + min(max((u >> 4) + (DIR == 0 ? 1 : -1), 0), wlast));
+			}
+			const int x = (word >> ((u & 15) * 2)) & 3;
+			const T c0 = (x == 0 ? T(0) : T(1)) * q, c1 = (x == 0 ? T(1) : (x == 1 ? T(-1) : T(0))) * q;
+			q = T(1);
+			T out[SPL];
+			if (DIR == 0) {
+				semisep2_t<T, SPL>(g, cW, cZ, cU, cV, cD, ds, out);
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) g[i] = out[i] * fma(c1, e0[i], c0);
+			} else {
+				T h[SPL];
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) h[i] = fma(c1, e0[i], c0) * g[i];
+				semisep2_t<T, SPL>(h, cV, cU, cZ, cW, cD, ds, g);
+			}
+		}
+	}
+	const T tot = gsum8_t<T>(local_sum_t<T, SPL>(g));
+	if (need) {
+		const double inv = 1.0 / (double)tot;
+		double o[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) o[i] = fmax((double)g[i] * inv, 1e-300); // (a flushed component restarts positive)
+		store_vec<SPL>(start + (size_t)c * NP + s0, o);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: forward.  One lane group per chunk.
+//   warm == 0 : the exact start vector comes from the boundary chain (vstart, transfer mode).
+//   warm  > 0 : the group starts `warm` bins to the LEFT of its chunk from the stationary vector, runs
+//               the same recursion without storing (the HMM forgets its start geometrically) and saves
+//               the vector it reached at the bin before its chunk (fwarm[c]) for the certificate.
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G, int VER>
+__global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
+                                                 const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                 const double *__restrict__ vstart, int warm, int use_prev, double *__restrict__ fhat,
+                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm,
+                                                 const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of,
+                                                 const double *__restrict__ pre_start)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	// pre_start: start vectors of the overlaps from the FP32 pre-warm-up (k_prewarm), nullptr = stationary start.
+	// order: chunks sorted by their number of steps, so that the groups of a warp finish together (adaptive overlaps);
+	// warm_of: this chunk's own overlap (nullptr: `warm` for every chunk)
+	const int c = order ? order[id.c] : id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0, NP);
+	double f[SPL];
+	int ubeg = ch.u0;
+	if ((ch.flags & CH_FIRST) || warm > 0) {
+		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - (warm_of ? min(warm_of[c], warm) : warm));
+		if (use_prev && ubeg > 0) {
+			// warm start: the vector the PREVIOUS E-step stored for bin ubeg-1 (the parameters moved only a little since;
+			// any positive vector is a legal start -- the certificate decides -- so a stale or concurrently rewritten row is harmless)
+			const double *row = fhat + ((size_t)ch.gb0 - (size_t)(ch.u0 - ubeg) - 1) * NP + s0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = fmax(row[i], 1e-300);
+		} else if (pre_start && ubeg > 0) {
+			load_vec<SPL>(pre_start + (size_t)c * NP + s0, f);
+		} else {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
+		}
+	} else {
+		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
+	}
+	double ll;
+	if constexpr (VER == 2) ll = forward_chunk2<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
+	else ll = forward_chunk<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
+	if (gl == 0 && id.valid) llpart[c] = ll;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adaptive overlaps.  How many bins of warm-up a boundary needs is a property of the data around it (het-poor,
+// low-TMRCA tracts mix slowly) and varies by an order of magnitude between boundaries; the mismatch the certificate
+// measures anyway tells, per boundary, whether the overlap of this E-step was ample (mismatch at the rounding floor),
+// tight, or too short.  Additive-decrease / multiplicative-increase on that signal: shrink by 1/8 while the mismatch
+// stays at the floor, grow by 1/2 as soon as it leaves the safe band (the boundary still passes at 1e-12, or is
+// repaired).  All on the device, inside the mark kernels of the first repair round; the next E-step reads the new lengths.
+// ------------------------------------------------------------------------------------------------
+// w: the overlap used in this E-step; tight: the longest overlap seen so far whose mismatch was NOT at the floor (memory,
+// so that a boundary approaches its need from above once instead of probing it again and again).
+__device__ __forceinline__ int adapt_overlap(int w, double mismatch, int w_max, int32_t *tight)
+{
+	const int w_min = 1536;
+	int t = *tight;
+	if (!(mismatch <= 2e-14)) { // off the floor (or failed): remember, and keep a safe distance from now on
+		t = max(t, w);
+		*tight = t;
+	}
+	const int floor_w = max(w_min, (t + (t >> 1)) & ~15); // 1.5 x the tightest length seen
+	if (mismatch <= 2e-14) w = max(floor_w, (w - (w >> 4)) & ~15); // 1/16 per E-step: a step multiplies the mismatch by < 10
+	else w = max(floor_w, w);
+	return max(min(w, w_max), 16);
+}
+
+// order[] = chunk indices sorted (stably) by their number of steps, longest first: every thread ranks one chunk
+// (O(n^2 / threads); n is a few thousand).  steps = (overlap unless the chunk starts / ends its sequence) + chunk length.
+__global__ void __launch_bounds__(256) k_order(const Chunk *__restrict__ chunks, int n_chunks, const int32_t *__restrict__ warm_of,
+                                               int warm_cap, int edge_flag, int32_t *__restrict__ order)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_chunks) return;
+	const int ki = ((chunks[i].flags & edge_flag) ? 0 : min(warm_of[i], warm_cap)) + chunks[i].len;
+	int rank = 0;
+	for (int j = 0; j < n_chunks; ++j) {
+		const int kj = ((chunks[j].flags & edge_flag) ? 0 : min(warm_of[j], warm_cap)) + chunks[j].len;
+		rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
+	}
+	order[rank] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3r: forward repair round (warm-up mode).  Boundary c (between chunks c-1 and c) "fails" when
+// fwarm[c] differs from the last stored vector of chunk c-1 by more than eps (Hilbert metric).
+// A warp acts only as the HEAD of a run of failed boundaries (its own fails, its left neighbour's
+// passes, so the left neighbour's stored vectors are final): it recomputes chunk c from the exact
+// vector, then keeps going through the following chunks whose boundaries also failed at kernel start
+// (nobody else touches those).  The boundary after the run is re-examined by the next round.
+// stat[0] += failed boundaries seen at kernel start, stat[1] += chunks recomputed.
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__device__ __forceinline__ double fwd_boundary_mismatch(const Chunk &ch, int c, const double *__restrict__ fhat,
+                                                        const double *__restrict__ fwarm, int s0, int N)
+{
+	constexpr int NP = SPL * 32;
+	double x[SPL], y[SPL];
+	load_vec<SPL>(fwarm + (size_t)c * NP + s0, x);
+	load_vec<SPL>(fhat + ((size_t)ch.gb0 - 1) * NP + s0, y);
+	return warp_mismatch<SPL>(x, y, s0, N);
+}
+
+// flag_f[c] = 1 iff the boundary in front of chunk c currently fails (evaluated once per round, so that the
+// repair kernel takes its decisions on a frozen picture); stat[0] += failures
+template <int SPL>
+__global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
+                                                  const double *__restrict__ fhat, const double *__restrict__ fwarm,
+                                                  int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat,
+                                                  int32_t *__restrict__ pred_next, int32_t *__restrict__ warm_of, int warm_max, int32_t *__restrict__ tight)
+{
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31;
+	const Chunk ch = chunks[c];
+	int fl = 0;
+	double m = 0.0;
+	if (!(ch.flags & CH_FIRST)) {
+		m = fwd_boundary_mismatch<SPL>(ch, c, fhat, fwarm, gl * SPL, N);
+		fl = m > eps ? 1 : 0;
+	}
+	if (gl == 0) {
+		flag_f[c] = fl;
+		if (pred_next) pred_next[c] = fl;
+		if (fl) atomicAdd(&stat[0], 1ull);
+		if (warm_of && pred_next && !(ch.flags & CH_FIRST)) warm_of[c] = adapt_overlap(warm_of[c], m, warm_max, tight + c); // first round only
+	}
+}
+
+template <int SPL, int G, int VER>
+__global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
+                                                        const int32_t *__restrict__ chunk_sub0,
+                                                        const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                        const int32_t *__restrict__ flag_f, const double *__restrict__ vsub,
+                                                        double *__restrict__ fhat, double *__restrict__ sc,
+                                                        double *__restrict__ llsub, double *__restrict__ fwarm,
+                                                        unsigned long long *__restrict__ stat)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_sub);
+	const int s = id.c, gl = id.gl, s0 = gl * SPL;
+	const int pc = parent[s];
+	const bool valid = id.valid && flag_f[pc] != 0;
+	if (!__any_sync(FULLMASK, valid)) return;
+	const Chunk ch = subs[s];
+	LaneModel<SPL> M;
+	M.load(model, s0, NP);
+	double f[SPL];
+	load_vec<SPL>(vsub + (size_t)s * NP + s0, f);                                              // exact vector of the bin before the sub-chunk (k_chain_subs)
+	if (valid && chunk_sub0[pc] == s) store_vec<SPL>(fwarm + (size_t)pc * NP + s0, f);        // the chunk boundary agrees by construction from now on
+	double ll;
+	if constexpr (VER == 2) ll = forward_chunk2<SPL, G>(ch, valid, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
+	else ll = forward_chunk<SPL, G>(ch, valid, ch.u0, M, f, gl, obs, fhat, sc, nullptr);
+	if (gl == 0 && valid) {
+		llsub[s] = ll;
+		atomicAdd(&stat[1], 1ull);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward over chunk ch by one lane group from b = b_{ulast} (reference scaling), accumulating the expected
+// counts into part_c; on return b is the vector of bin u0-1 (if u0 > 0).  (khmm.c:226-235, 310-318.)
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G>
+__device__ __forceinline__ void backward_chunk(const Chunk &ch, bool valid, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
+                                               const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
+                                               const double *__restrict__ sc, double *__restrict__ part_c,
+                                               double *__restrict__ bsave_c = nullptr, int usave = -1)
+{
+	constexpr int NP = SPL * G, PF = 4;
+	const int s0 = gl * SPL;
+	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
+	const int ulast = ch.u0 + ch.len - 1;
+	const double *frow = fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + s0; // row of bin ulast
+	const double *srow = sc + ch.gb0 + (ch.len - 1);
+	double fu[SPL], su;
+	load_vec<SPL>(frow, fu);
+	su = __ldg(srow);
+	// software prefetch ring: nf[j], ns[j] hold row (u-1-j) while bin u is processed
+	double nf[PF][SPL], ns[PF];
+#pragma unroll
+	for (int j = 0; j < PF; ++j) {
+		const int uu = ulast - 1 - j;
+		if (uu >= 0) {
+			load_vec<SPL>(frow - (size_t)(1 + j) * NP, nf[j]);
+			ns[j] = __ldg(srow - (1 + j));
+		} else {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) nf[j][i] = 0.0;
+			ns[j] = 1.0;
+		}
+	}
+	const int trips = warp_trips(valid ? ch.len : 0);
+	uint32_t word = 0;
+	ScanMasks<G> mk;
+	mk.init(gl);
+	for (int t = 0; t < trips; ++t) {
+		const int u = ulast - t;
+		const bool act = valid && u >= ch.u0;
+		const int uo = act ? u : ch.u0;
+		if (t == 0 || (uo & 15) == 15) word = __ldg(obs + ch.ow0 + (uo >> 4));
+		const int x = (word >> ((uo & 15) * 2)) & 3;
+		if (act && u == usave && bsave_c) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
+		// emission counts: bins 0..L-2 only (khmm.c:310, 317)
+		if (act && u != ch.Lseq - 1) {
+			const double w0 = (x == 0) ? su : 0.0, w1 = (x == 1) ? su : 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				const double fb = fu[i] * b[i];
+				aE0[i] = fma(fb, w0, aE0[i]);
+				aE1[i] = fma(fb, w1, aE1[i]);
+			}
+		}
+		const bool trans = act && u > 0; // no transition into the first bin of a sequence
+		// rotate the prefetch ring
+		double fm[SPL], sm = ns[0];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) fm[i] = nf[0][i];
+		if (act) {
+#pragma unroll
+			for (int j = 0; j + 1 < PF; ++j) {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) nf[j][i] = nf[j + 1][i];
+				ns[j] = ns[j + 1];
+			}
+			const int uu = u - 1 - PF;
+			if (uu >= 0) {
+				const size_t back = (size_t)(ulast - uu);
+				load_vec<SPL>(frow - back * NP, nf[PF - 1]);
+				ns[PF - 1] = __ldg(srow - back);
+			}
+		}
+		// transition u-1 -> u (khmm.c:313-318 for the counts, khmm.c:230-234 for b_{u-1})
+		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
+		emis_coef(x, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
+		prefsuf<SPL, G>(g, M.V, M.Z, mk, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
+		prefsuf<SPL, G>(fm, M.W, M.U, mk, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
+		if (trans) {
+			const double inv = fast_rcp(sm);
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				aRL[i] = fma(fm[i], Pg[i], aRL[i]);
+				aRU[i] = fma(fm[i], Sg[i], aRU[i]);
+				aAD[i] = fma(fm[i], g[i], aAD[i]);
+				aCL[i] = fma(g[i], Sf[i], aCL[i]);
+				aCU[i] = fma(g[i], Pf[i], aCU[i]);
+				const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i]));
+				b[i] = bb * inv;
+				fu[i] = fm[i];
+			}
+			su = sm;
+		}
+	}
+	if (valid) {
+		double *po = part_c + s0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			po[S_E0 * NP + i] = aE0[i];
+			po[S_E1 * NP + i] = aE1[i];
+			po[S_RL * NP + i] = aRL[i] * M.U[i];
+			po[S_CL * NP + i] = aCL[i] * M.V[i];
+			po[S_RU * NP + i] = aRU[i] * M.W[i];
+			po[S_CU * NP + i] = aCU[i] * M.Z[i];
+			po[S_AD * NP + i] = aAD[i] * M.D[i];
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second-generation backward over a chunk (same contract as backward_chunk, except for which chunk owns which
+// emission count: gamma_{u-1} = f_{u-1} (A diag(e_{x_u}) b_u) is accumulated with the TRANSITION u-1 -> u, which the
+// chunk of bin u owns -- this covers bins 0..L-2 exactly once, as khmm.c:310-318 does, and needs neither f_u nor s_u).
+// The f rows come from a ring of PF prefetched rows with static slots (the loop is unrolled PF times), the four scans
+// of a bin are two DualScans, and the scans of f_{u-1} do not depend on b, so they overlap the chain through b.
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G>
+struct BackwardRun {
+#ifndef PSMC_BWD_PF
+#define PSMC_BWD_PF 4
+#endif
+	static constexpr int NP = SPL * G, PF = PSMC_BWD_PF;
+	const Chunk &ch;
+	const LaneModel<SPL> &M;
+	const bool valid;
+	const int gl, s0, ulast;
+	const uint32_t *__restrict__ obs;
+	const double *__restrict__ frow, *__restrict__ srow; // row of bin ulast
+	double *__restrict__ bsave_c;
+	const int usave;
+	double *__restrict__ grow; // dense-count option: g_u = e_{x_u} b_u of every transition goes to ghat (this is the row of bin ulast), or nullptr
+	DualScan<G> ds;
+	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
+	double nf[PF][SPL], ns[PF];
+	uint32_t word, wprev;
+	int xu;
+
+	__device__ __forceinline__ BackwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_, const uint32_t *__restrict__ obs_,
+	                                       const double *__restrict__ fhat, const double *__restrict__ sc, double *__restrict__ bsave_c_, int usave_,
+	                                       double *__restrict__ ghat)
+	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), ulast(ch_.u0 + ch_.len - 1), obs(obs_),
+	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), bsave_c(bsave_c_), usave(usave_),
+	      grow(ghat ? ghat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL : nullptr)
+	{
+	}
+
+	template <int J>
+	__device__ __forceinline__ void step(int t, double (&b)[SPL])
+	{
+		const int u = ulast - t;
+		const bool act = valid && u >= ch.u0;
+		const bool trans = act && u > 0; // no transition into the first bin of a sequence
+		if (act && u == usave && bsave_c) store_vec<SPL>(bsave_c + s0, b); // warm start of the left neighbour's next overlap
+		// row u-1 from the ring, then refill the slot with row u-1-PF
+		double fm[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) fm[i] = nf[J][i];
+		const double sm = ns[J];
+		if (act && u - 1 - PF >= 0) {
+			const size_t back = (size_t)(t + 1 + PF);
+			load_vec<SPL>(frow - back * NP, nf[J]);
+			ns[J] = __ldg(srow - back);
+		}
+		// symbol of bin u-1 (the emission counts of this transition belong to it)
+		const int v = u - 1;
+		int xm = 2;
+		if (trans) {
+			if (t > 0 && (v & 15) == 15) {
+				word = wprev;
+				wprev = __ldg(obs + ch.ow0 + max((v >> 4) - 1, 0));
+			}
+			xm = (word >> ((v & 15) * 2)) & 3;
+		}
+		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
+		emis_coef(xu, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
+		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);  // Pg = sum_{l<k} V_l g_l, Sg = sum_{l>k} Z_l g_l
+		prefsuf2<SPL, G>(fm, M.W, M.U, ds, Pf, Sf); // Pf = sum_{k<l} W_k f_k, Sf = sum_{k>l} U_k f_k
+		if (trans) {
+			if (grow) store_vec<SPL>(grow - (size_t)t * NP, g);
+			const double inv = fast_rcp(sm);
+			const double w0 = (xm == 0) ? 1.0 : 0.0, w1 = (xm == 1) ? 1.0 : 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				aRL[i] = fma(fm[i], Pg[i], aRL[i]);
+				aRU[i] = fma(fm[i], Sg[i], aRU[i]);
+				aAD[i] = fma(fm[i], g[i], aAD[i]);
+				aCL[i] = fma(g[i], Sf[i], aCL[i]);
+				aCU[i] = fma(g[i], Pf[i], aCU[i]);
+				const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i])); // = b_{u-1} s_{u-1} (khmm.c:230-234)
+				const double gam = fm[i] * bb;                                         // posterior of bin u-1 (khmm.c:317)
+				aE0[i] = fma(gam, w0, aE0[i]);
+				aE1[i] = fma(gam, w1, aE1[i]);
+				b[i] = bb * inv;
+			}
+			xu = xm;
+		}
+	}
+
+	__device__ __forceinline__ void run(double (&b)[SPL], double *__restrict__ part_c)
+	{
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
+#pragma unroll
+		for (int j = 0; j < PF; ++j) {
+			if (ulast - 1 - j >= 0) {
+				load_vec<SPL>(frow - (size_t)(1 + j) * NP, nf[j]);
+				ns[j] = __ldg(srow - (1 + j));
+			} else {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) nf[j][i] = 0.0;
+				ns[j] = 1.0;
+			}
+		}
+		ds.init(gl);
+		xu = (__ldg(obs + ch.ow0 + (ulast >> 4)) >> ((ulast & 15) * 2)) & 3;
+		const int v0 = max(ulast - 1, 0);
+		word = __ldg(obs + ch.ow0 + (v0 >> 4));
+		wprev = __ldg(obs + ch.ow0 + max((v0 >> 4) - 1, 0));
+		const int trips = (warp_trips(valid ? ch.len : 0) + PF - 1) / PF * PF;
+		for (int t = 0; t < trips; t += PF) {
+			step<0>(t, b);
+			if (PF > 1) step<(PF > 1 ? 1 : 0)>(t + 1, b);
+			if (PF > 2) step<(PF > 2 ? 2 : 0)>(t + 2, b);
+			if (PF > 3) step<(PF > 3 ? 3 : 0)>(t + 3, b);
+		}
+		if (valid) {
+			double *po = part_c + s0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				po[S_E0 * NP + i] = aE0[i];
+				po[S_E1 * NP + i] = aE1[i];
+				po[S_RL * NP + i] = aRL[i] * M.U[i];
+				po[S_CL * NP + i] = aCL[i] * M.V[i];
+				po[S_RU * NP + i] = aRU[i] * M.W[i];
+				po[S_CU * NP + i] = aCU[i] * M.Z[i];
+				po[S_AD * NP + i] = aAD[i] * M.D[i];
+			}
+		}
+	}
+};
+
+template <int SPL, int G>
+__device__ __forceinline__ void backward_chunk2(const Chunk &ch, bool valid, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
+                                                const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
+                                                const double *__restrict__ sc, double *__restrict__ part_c,
+                                                double *__restrict__ bsave_c = nullptr, int usave = -1, double *__restrict__ ghat = nullptr)
+{
+	BackwardRun<SPL, G> r(ch, valid, M, gl, obs, fhat, sc, bsave_c, usave, ghat);
+	r.run(b, part_c);
+}
+
+// b_{ulast} in the reference's scaling from a direction beta: sum_k f[k] b[k] s = 1 (khmm.c:237 sanity identity)
+template <int SPL, int G>
+__device__ __forceinline__ void scale_boundary(const Chunk &ch, const double (&beta)[SPL], double (&b)[SPL], int gl,
+                                               const double *__restrict__ fhat, const double *__restrict__ sc)
+{
+	constexpr int NP = SPL * G;
+	double fu[SPL], dot = 0.0;
+	load_vec<SPL>(fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + gl * SPL, fu);
+	const double su = __ldg(sc + ch.gb0 + (ch.len - 1));
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) dot = fma(fu[i], beta[i], dot);
+	dot = gsum<G>(dot);
+	const double v = 1.0 / (su * dot);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
+}
+
+// sum-normalised copy of b to dst (direction of the backward vector at a chunk boundary)
+template <int SPL, int G>
+__device__ __forceinline__ void publish_direction(const double (&b)[SPL], double *__restrict__ dst, int gl, bool doit)
+{
+	double t = 0.0, nb[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) t += b[i];
+	t = 1.0 / gsum<G>(t);
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) nb[i] = b[i] * t;
+	if (doit) store_vec<SPL>(dst + gl * SPL, nb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4w: the backward warm-up on its own (needs only the observations and the model, so it runs on a second stream
+// concurrently with the forward pass): direction of b at the last bin of every chunk that does not end its sequence,
+// from `warm` bins to the right (or from the previous E-step's saved direction), sum-normalised into bwarm[c].
+template <int SPL, int G, int VER>
+__global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__ chunks, int n_chunks,
+                                                       const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev,
+                                                       const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of,
+                                                       const double *__restrict__ pre_start)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = order ? order[id.c] : id.c, gl = id.gl, s0 = gl * SPL; // (order / warm_of: adaptive overlaps, see k_forward)
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0, NP);
+	const int ulast = ch.u0 + ch.len - 1;
+	const bool is_last = (ch.flags & CH_LAST) != 0;
+	double beta[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
+	if (warm_of) warm = min(warm_of[c], warm);
+	int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
+	if (pre_start && !is_last && ulast + warm < ch.Lseq - 1) load_vec<SPL>(pre_start + (size_t)c * NP + s0, beta); // (k_prewarm, same condition)
+	if (bsave_prev && !is_last) {
+		// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin
+		// min(ulast + warm, last bin of the right neighbour) -- see usave in k_backward
+		const Chunk nx = chunks[c + 1];
+		z0 = min(ulast + warm, nx.u0 + nx.len - 1);
+		const double *row = bsave_prev + (size_t)c * NP + s0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) beta[i] = fmax(row[i], 1e-300);
+	}
+	const int trips = warp_trips(id.valid ? z0 - ulast : 0);
+	if constexpr (VER == 2) {
+		// Unnormalised recursion with a power-of-two boost when the vector has shrunk (only the direction matters); the sum
+		// that decides it is taken every 16th bin and acts on the NEXT bin, off the dependency chain.  The groups of a warp
+		// are aligned at the END (bin ulast + 1); a group with a shorter overlap starts late and until then computes on
+		// whatever its registers hold -- no per-step select.
+		DualScan<G> ds;
+		ds.init(gl);
+		const int mytrips = id.valid ? z0 - ulast : 0;
+		const int mystart = mytrips > 0 ? trips - mytrips : INT_MAX;
+		int tpend = warp_min_i(mystart);
+		const int wlast = (ch.Lseq - 1) >> 4, ufirst = ulast + trips;
+		// packed words: the (at most two) words of a block of <= 16 bins are fetched during the previous block, so the inner
+		// loop has no load and no address arithmetic; indices are clamped to the sequence (idle groups read legal words too)
+		int ina = ufirst >> 4, ia;
+		uint32_t wa, wb, wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast)), wnb = __ldg(obs + ch.ow0 + min(max(ina - 1, 0), wlast));
+		double q = 1.0, bc[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
+		int t = 0;
+		while (t < trips) { // blocks of at most 16 bins: late starts and the boost decision sit between blocks
+			if (t == tpend) { // warp-uniform, rare
+				if (mystart == t) {
+#pragma unroll
+					for (int i = 0; i < SPL; ++i) bc[i] = beta[i];
+				}
+				tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
+			}
+			const int tstop = min(min(trips, tpend), (t & ~15) + 16);
+			wa = wna; wb = wnb; ia = ina;
+			ina = (ufirst - tstop) >> 4; // the next block starts at step tstop
+			wna = __ldg(obs + ch.ow0 + min(max(ina, 0), wlast));
+			wnb = __ldg(obs + ch.ow0 + min(max(ina - 1, 0), wlast));
+			q = (gsum<G>(local_sum<SPL>(bc)) < PSMC_BOOST_LOW) ? PSMC_BOOST_UP : 1.0;
+			for (; t < tstop; ++t) {
+				const int u = ufirst - t; // bin whose emission enters; the step yields the direction of bin u-1
+				const int x = ((((u >> 4) == ia) ? wa : wb) >> ((u & 15) * 2)) & 3;
+				double g[SPL], c0, c1;
+				emis_coef(x, c0, c1);
+				c0 *= q;
+				c1 *= q;
+				q = 1.0;
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * bc[i];
+				semisep2<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, ds, bc);
+			}
+		}
+		if (mytrips > 0) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) beta[i] = bc[i];
+		}
+		publish_direction<SPL, G>(beta, bwarm + (size_t)c * NP, gl, id.valid && !is_last);
+		return;
+	}
+	uint32_t word = 0;
+	ScanMasks<G> mk;
+	mk.init(gl);
+	mk.pin();
+	for (int t = 0; t < trips; ++t) {
+		const int u = z0 - t;
+		const bool act = id.valid && u > ulast;
+		const int uo = act ? u : ulast;
+		if (t == 0 || (uo & 15) == 15) word = __ldg(obs + ch.ow0 + (uo >> 4));
+		const int x = (word >> ((uo & 15) * 2)) & 3;
+		double g[SPL], out[SPL], c0, c1;
+		emis_coef(x, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * beta[i];
+		semisep<SPL, G>(g, M.V, M.U, M.Z, M.W, M.D, mk, out);
+		double scl = 1.0;
+		if ((t & 7) == 7) { // exact power-of-two rescale, same factor in every lane of the group
+			double tt = 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) tt += out[i];
+			tt = gsum<G>(tt);
+			if (tt > 1e-290 && tt < 1e290) scl = pow2i(-exponent_of(tt));
+		}
+		if (act) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) beta[i] = out[i] * scl;
+		}
+	}
+	publish_direction<SPL, G>(beta, bwarm + (size_t)c * NP, gl, id.valid && !is_last);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: backward + expected counts.  One lane group per chunk.  Per-chunk partials: part[c][S_COUNT][NP].
+// The direction of b at the chunk's last bin is read from `bdir`: the boundary chain's bend (transfer mode) or the
+// warm-up result bwarm (fast path, K4w).  With publish != 0 the direction computed for the last bin of chunk c-1
+// goes to bexact[c-1] for the certificate; usave/bsave_next feed the optional warm start of the next E-step.
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G, int VER>
+__global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chunks, int n_chunks,
+                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                  const double *__restrict__ bdir, int publish, const double *__restrict__ fhat,
+                                                  const double *__restrict__ sc, double *__restrict__ part,
+                                                  double *__restrict__ bexact, double *__restrict__ bsave_next, int warm_next,
+                                                  double *__restrict__ ghat)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(model, s0, NP);
+	const int ulast = ch.u0 + ch.len - 1;
+	const bool is_last = (ch.flags & CH_LAST) != 0;
+	double beta[SPL], b[SPL];
+	load_vec<SPL>(bdir + (size_t)c * NP + s0, beta);
+	// (the groups of a warp differ in is_last: everything containing a shuffle runs unconditionally, then selects)
+	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
+	if (is_last) { // khmm.c:226: b_L[k] = 1/s_L
+		const double v = 1.0 / __ldg(sc + ch.gb0 + (ch.len - 1));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = v;
+	}
+	// the bin whose b the left neighbour will start its next overlap from (inside this chunk)
+	const int usave = (ch.flags & CH_FIRST) ? -1 : min(ch.u0 - 1 + warm_next, ulast);
+	if constexpr (VER == 2)
+		backward_chunk2<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
+		                        bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave, ghat);
+	else
+		backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
+		                       bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
+	// b now belongs to the last bin of chunk c-1: publish its direction for the certificate
+	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && publish && !(ch.flags & CH_FIRST));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4r: backward repair round (warm-up mode), mirror image of K3r.  Boundary c (at the END of chunk c)
+// fails when bwarm[c] differs from bexact[c].  The head of a run (its own boundary fails, the boundary at
+// the end of chunk c+1 passes or chunk c+1 ends its sequence, so bexact[c] is final) recomputes chunk c
+// from bexact[c], republishes bexact[c-1] and keeps going left while the next boundary fails.
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__device__ __forceinline__ double bwd_boundary_mismatch(int c, const double *__restrict__ bwarm, const double *__restrict__ bexact, int s0, int N)
+{
+	constexpr int NP = SPL * 32;
+	double x[SPL], y[SPL];
+	load_vec<SPL>(bwarm + (size_t)c * NP + s0, x);
+	load_vec<SPL>(bexact + (size_t)c * NP + s0, y);
+	return warp_mismatch<SPL>(x, y, s0, N);
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
+                                                  const double *__restrict__ bwarm, const double *__restrict__ bexact,
+                                                  int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat,
+                                                  int32_t *__restrict__ pred_next, int32_t *__restrict__ warm_of, int warm_max, int32_t *__restrict__ tight)
+{
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31;
+	int fl = 0;
+	double m = 0.0;
+	const bool inner = !(chunks[c].flags & CH_LAST);
+	if (inner) {
+		m = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, gl * SPL, N);
+		fl = m > eps ? 1 : 0;
+	}
+	if (gl == 0) {
+		flag_b[c] = fl;
+		if (pred_next) pred_next[c] = fl;
+		if (fl) atomicAdd(&stat[2], 1ull);
+		if (warm_of && pred_next && inner) warm_of[c] = adapt_overlap(warm_of[c], m, warm_max, tight + c); // first round only
+	}
+}
+
+template <int SPL, int G, int VER>
+__global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict__ subs, int n_sub, const int32_t *__restrict__ parent,
+                                                         const int32_t *__restrict__ chunk_sub0, const Chunk *__restrict__ chunks,
+                                                         const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                         const int32_t *__restrict__ flag_b, const double *__restrict__ bsub,
+                                                         const double *__restrict__ fhat, const double *__restrict__ sc,
+                                                         double *__restrict__ partsub, double *__restrict__ bwarm,
+                                                         double *__restrict__ bexact, unsigned long long *__restrict__ stat,
+                                                         double *__restrict__ ghat)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_sub);
+	const int s = id.c, gl = id.gl, s0 = gl * SPL;
+	const int pc = parent[s];
+	const bool valid = id.valid && flag_b[pc] != 0;
+	if (!__any_sync(FULLMASK, valid)) return;
+	const Chunk ch = subs[s];
+	LaneModel<SPL> M;
+	M.load(model, s0, NP);
+	double beta[SPL], b[SPL];
+	load_vec<SPL>(bsub + (size_t)s * NP + s0, beta);                                                           // exact direction at the sub-chunk's last bin (k_chain_subs)
+	publish_direction<SPL, G>(beta, bwarm + (size_t)pc * NP, gl, valid && chunk_sub0[pc + 1] - 1 == s);       // the chunk boundary agrees by construction from now on
+	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
+	if constexpr (VER == 2) backward_chunk2<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP, nullptr, -1, ghat);
+	else backward_chunk<SPL, G>(ch, valid, M, b, gl, obs, fhat, sc, partsub + (size_t)s * S_COUNT * NP);
+	if (gl == 0 && valid) atomicAdd(&stat[3], 1ull);
+	// the first sub-chunk of a chunk ends at the boundary to chunk pc-1: publish the direction computed here
+	publish_direction<SPL, G>(b, bexact + (size_t)(pc > 0 ? pc - 1 : 0) * NP, gl,
+	                          valid && chunk_sub0[pc] == s && !(chunks[pc].flags & CH_FIRST));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c: final certificate of the warm-up mode.  One warp per internal chunk boundary c|c+1.
+//   forward : fwarm[c+1] vs the last stored vector of chunk c;   backward: bwarm[c] vs bexact[c].
+// If every boundary agrees to eps (Hilbert projective metric), the boundary vectors are a fixed point of
+// the exact recursion and, by induction from the exactly known sequence start (forward) and sequence end
+// (backward), every chunk was computed from the exact vector (to eps).
+// cert[0] = boundaries that fail, cert[1] / cert[2] = largest forward / backward mismatch (double bits).
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_certify(const Chunk *__restrict__ chunks, int n_chunks, int N,
+                                                 const double *__restrict__ fhat, const double *__restrict__ fwarm,
+                                                 const double *__restrict__ bwarm, const double *__restrict__ bexact,
+                                                 double eps, int dir, unsigned long long *__restrict__ cert)
+{
+	// dir 0: forward boundaries of the forward plan; dir 1: backward boundaries of the backward plan
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= n_chunks) return;
+	const int gl = threadIdx.x & 31, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	if (ch.flags & CH_LAST) return;
+	const double m = dir == 0 ? fwd_boundary_mismatch<SPL>(chunks[c + 1], c + 1, fhat, fwarm, s0, N)
+	                          : bwd_boundary_mismatch<SPL>(c, bwarm, bexact, s0, N);
+	if (gl == 0) {
+		if (!(m <= eps)) atomicAdd(&cert[0], 1ull);
+		atomicMax(&cert[1 + dir], (unsigned long long)__double_as_longlong(m));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense transition counts (option): A[k][l] = a[k][l] * C[k][l] with C = sum_u f_{u-1}[k] g_u[l] over the transitions
+// (khmm.c:313-316), needed only for the constant offset hmm_Q0 of the printed QD line (khmm.c:336-340).  The backward
+// kernel stores the rows g_u next to the forward spill; C is then a tall-skinny product F^T G: one block per backward
+// chunk accumulates its NP x NP partial in registers (16 x 16 threads, a (NP/16)^2 tile each), rows staged through
+// shared memory in slabs of 32 bins; a fixed-order reduction over the chunks follows (deterministic, weighted by the
+// multiplicity of the chunk's record).  The pairing (row of bin u-1, row of bin u) never crosses a record: u >= max(u0, 1).
+// ------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256) k_dense_chunk(const Chunk *__restrict__ chunks, const double *__restrict__ fhat,
+                                                     const double *__restrict__ ghat, double *__restrict__ cpart)
+{
+	constexpr int TL = NP / 16, SLAB = 32;
+	__shared__ __align__(16) double sf[SLAB][NP], sg[SLAB][NP];
+	const Chunk ch = chunks[blockIdx.x];
+	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+	double acc[TL][TL];
+#pragma unroll
+	for (int i = 0; i < TL; ++i)
+#pragma unroll
+		for (int j = 0; j < TL; ++j) acc[i][j] = 0.0;
+	const int ulo = max(ch.u0, 1), uhi = ch.u0 + ch.len; // transitions into bins [ulo, uhi)
+	for (int ub = ulo; ub < uhi; ub += SLAB) {
+		const int nb = min(SLAB, uhi - ub);
+		for (int idx = threadIdx.x; idx < nb * NP; idx += 256) {
+			const int r = idx / NP, k = idx % NP;
+			const size_t row = (size_t)ch.gb0 + (size_t)(ub + r - ch.u0);
+			sf[r][k] = fhat[(row - 1) * NP + k];
+			sg[r][k] = ghat[row * NP + k];
+		}
+		__syncthreads();
+		for (int r = 0; r < nb; ++r) {
+			double fv[TL], gv[TL];
+#pragma unroll
+			for (int i = 0; i < TL; i += 2) { // 128-bit shared loads (TL is 2 or 4, the tiles are 16-byte aligned)
+				const double2 a = *reinterpret_cast<const double2 *>(&sf[r][ty * TL + i]);
+				const double2 b = *reinterpret_cast<const double2 *>(&sg[r][tx * TL + i]);
+				fv[i] = a.x; fv[i + 1] = a.y;
+				gv[i] = b.x; gv[i + 1] = b.y;
+			}
+#pragma unroll
+			for (int i = 0; i < TL; ++i)
+#pragma unroll
+				for (int j = 0; j < TL; ++j) acc[i][j] = fma(fv[i], gv[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+	double *out = cpart + (size_t)blockIdx.x * NP * NP;
+#pragma unroll
+	for (int i = 0; i < TL; ++i)
+#pragma unroll
+		for (int j = 0; j < TL; ++j) out[(size_t)(ty * TL + i) * NP + tx * TL + j] = acc[i][j];
+}
+
+// C[e] = sum_c w[c] * cpart[c][e] in a fixed order; one block per entry e of the NP x NP matrix
+__global__ void __launch_bounds__(256) k_dense_reduce(const double *__restrict__ cpart, int n_chunks, int n_entries,
+                                                      const double *__restrict__ w, double *__restrict__ out)
+{
+	__shared__ double sh[256];
+	const int e = blockIdx.x;
+	double acc = 0.0;
+	for (int c = threadIdx.x; c < n_chunks; c += 256) {
+		const double v = cpart[(size_t)c * n_entries + e];
+		acc += w ? w[c] * v : v;
+	}
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	for (int d = 128; d > 0; d >>= 1) {
+		if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[e] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: deterministic reduction of the per-chunk partials.
+// out layout (7*N+1 doubles): [ LL | E0(N) E1(N) | RL(N) CL(N) RU(N) CU(N) AD(N) ]
+// grid = 1 + S_COUNT*N blocks, block = 256 threads; block 0 reduces LL.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part, const double *__restrict__ llpart,
+                                                int n_chunks, int n_part, int N, int NP, double *__restrict__ out,
+                                                const double *__restrict__ w_ll, const double *__restrict__ w_part)
+{
+	// w_ll / w_part: multiplicity of the sequence every chunk belongs to (bootstrap replicates, aux.c:8-47); NULL = 1
+	__shared__ double sh[256];
+	const int o = blockIdx.x;
+	double acc = 0.0;
+	if (o == 0) {
+		for (int c = threadIdx.x; c < n_chunks; c += 256) acc += w_ll ? w_ll[c] * llpart[c] : llpart[c];
+	} else {
+		const int row = (o - 1) / N, k = (o - 1) % N;
+		const double *p = part + (size_t)row * NP + k;
+		for (int c = threadIdx.x; c < n_part; c += 256) {
+			const double v = p[(size_t)c * S_COUNT * NP];
+			acc += w_part ? w_part[c] * v : v;
+		}
+	}
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	for (int d = 128; d > 0; d >>= 1) {
+		if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[o] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: decode backward.  One warp per chunk of ONE sequence: posterior argmax / max, optional full
+// posterior and recombination probability (aux.c:167-200, khmm.c:264-293).
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(128) k_decode(const Chunk *__restrict__ chunks, int c_first, int n_chunks_seq,
+                                                const uint32_t *__restrict__ obs, const double *__restrict__ model,
+                                                const double *__restrict__ bend, const double *__restrict__ fhat,
+                                                const double *__restrict__ sc, int N, int32_t *__restrict__ best_k,
+                                                double *__restrict__ best_p, double *__restrict__ post,
+                                                double *__restrict__ p_recomb)
+{
+	constexpr int G = 32, NP = SPL * G;
+	const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (w >= n_chunks_seq) return;
+	const int c = c_first + w;
+	const int gl = threadIdx.x & 31;
+	const Chunk ch = uniform_chunk(chunks[c]);
+	const int s0 = gl * SPL;
+	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], e1[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) {
+		cU[i] = model[M_U * NP + s0 + i];
+		cV[i] = model[M_V * NP + s0 + i];
+		cW[i] = model[M_W * NP + s0 + i];
+		cZ[i] = model[M_Z * NP + s0 + i];
+		cD[i] = model[M_D * NP + s0 + i];
+		e0[i] = model[M_E0 * NP + s0 + i];
+		e1[i] = model[M_E1 * NP + s0 + i];
+	}
+	const int ulast = ch.u0 + ch.len - 1;
+	const double *frow = fhat + ((size_t)ch.gb0 + (ch.len - 1)) * NP + s0;
+	const double *srow = sc + ch.gb0 + (ch.len - 1);
+	double fu[SPL], b[SPL], su;
+	load_vec<SPL>(frow, fu);
+	su = __ldg(srow);
+	if (ch.flags & CH_LAST) {
+		const double v = 1.0 / su;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = v;
+	} else {
+		double beta[SPL], dot = 0.0;
+		load_vec<SPL>(bend + (size_t)c * NP + s0, beta);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) dot = fma(fu[i], beta[i], dot);
+		dot = gsum<G>(dot);
+		const double v = 1.0 / (su * dot);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = beta[i] * v;
+	}
+	uint32_t word = 0;
+	ScanMasks<G> mk;
+	mk.init(gl);
+	for (int u = ulast; u >= ch.u0; --u) {
+		if (u == ulast || (u & 15) == 15) word = __ldg(obs + ch.ow0 + (u >> 4));
+		const int x = (word >> ((u & 15) * 2)) & 3;
+		// posterior of bin u: gamma[k] = f*b*s (khmm.c:274); first maximum wins
+		double gmaxv = -1.0;
+		int garg = 0x7fffffff;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			const double gm = fu[i] * b[i] * su;
+			if (s0 + i < N) {
+				if (post) post[(size_t)u * N + s0 + i] = gm;
+				if (gm > gmaxv) {
+					gmaxv = gm;
+					garg = s0 + i;
+				}
+			}
+		}
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			const double ov = __shfl_xor_sync(FULLMASK, gmaxv, d);
+			const int oa = __shfl_xor_sync(FULLMASK, garg, d);
+			if (ov > gmaxv || (ov == gmaxv && oa < garg)) {
+				gmaxv = ov;
+				garg = oa;
+			}
+		}
+		if (gl == 0) {
+			best_k[u] = garg;
+			best_p[u] = gmaxv;
+		}
+		if (u == ch.Lseq - 1 && p_recomb && gl == 0) p_recomb[u] = 0.0;
+		if (u == 0) break;
+		double fm[SPL], g[SPL], out[SPL];
+		load_vec<SPL>(frow - (size_t)(ulast - (u - 1)) * NP, fm);
+		const double sm = __ldg(srow - (ulast - (u - 1)));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			const double em = (x == 0) ? e0[i] : ((x == 1) ? e1[i] : 1.0);
+			g[i] = em * b[i];
+		}
+		if (p_recomb) { // aux.c:188-193 for bin u-1: 1 - sum_l f_{u-1}[l] a[l][l] b_u[l] e_u[l]
+			double t = 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) t = fma(fm[i] * cD[i], g[i], t);
+			t = gsum<G>(t);
+			if (gl == 0) p_recomb[u - 1] = 1.0 - t;
+		}
+		semisep<SPL, G>(g, cV, cU, cZ, cW, cD, mk, out);
+		const double inv = 1.0 / sm;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			b[i] = out[i] * inv;
+			fu[i] = fm[i];
+		}
+		su = sm;
+	}
+}
+
