@@ -1,9 +1,10 @@
 // cuda_emu.h -- TEST INFRASTRUCTURE ONLY.  A host-side SIMT emulation that lets the CPU test-suite execute the
-// *source* of psmc_b200/csrc/psmc_estep.cu (kernels and host orchestration) without a GPU: one host thread per CUDA
-// thread, warp shuffles/votes through per-warp barriers, __syncthreads through a per-block barrier, the CUDA runtime
-// calls the library makes mapped onto malloc/memcpy.  It exists to catch logic errors in the kernels before GPU time
-// is spent; it is thousands of times slower than a CPU implementation would be and is built into
-// tests/emu/libpsmc_b200_emu.so, which nothing under psmc_b200/ or host/ ever loads (the product has no CPU path).
+// *source* of psmc_b200/csrc/psmc_estep.cu + psmc_kernels.cuh (kernels and host orchestration) without a GPU: every CUDA
+// thread is a cooperative fiber (all threads of a block on one host thread, a hand-rolled x86-64 context switch at every
+// warp shuffle / vote / __syncthreads), blocks of a grid run on a pool of host threads, the CUDA runtime calls the
+// library makes are mapped onto malloc/memcpy.  It exists to catch logic errors in the kernels before GPU time is spent;
+// it is thousands of times slower than a CPU implementation would be and is built into tests/emu/libpsmc_b200_emu.so,
+// which nothing under psmc_b200/ or host/ ever loads (the product has no CPU path).
 #pragma once
 #include <algorithm>
 #include <atomic>
