@@ -74,8 +74,9 @@ static int init_model(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t 
 		const char *env = getenv("PSMC_B200_MSTEP_SPEC"), *lws = getenv("LOCAL_WORLD_SIZE");
 		const long cores = sysconf(_SC_NPROCESSORS_ONLN);
 		const int procs = (lws && atoi(lws) > 0) ? atoi(lws) : 1;
-		em->spec_mstep = cores / procs >= 4 ? 3 : (cores / procs >= 2 ? 1 : 0);
-		if (env) em->spec_mstep = atoi(env) >= 3 ? 3 : (atoi(env) >= 1 ? 1 : 0);
+		const long per = cores / procs;
+		em->spec_mstep = per >= 8 ? 5 : (per >= 4 ? 3 : (per >= 2 ? 1 : 0));
+		if (env) { const int v = atoi(env); em->spec_mstep = v >= 7 ? 7 : (v >= 5 ? 5 : (v >= 3 ? 3 : (v >= 1 ? 1 : 0))); }
 	}
 	em->n_seqs = sq->n_seqs;
 	return 0;
@@ -224,17 +225,17 @@ int psmch_em_mstep(psmch_em_t *em, FILE *fpout)
 	while (em->n_spec < em->spec_mstep) { /* first M-step: start the helpers, each with its own model instance */
 		const int j = em->n_spec;
 		aux_t *ha = (aux_t*)calloc(1, sizeof(aux_t));
-		if (ha == 0 || psmch_model_alloc(&em->model_spec[j], &em->sp) != 0) { free(ha); em->spec_mstep = em->n_spec >= 1 ? 1 : 0; break; }
+		if (ha == 0 || psmch_model_alloc(&em->model_spec[j], &em->sp) != 0) { free(ha); em->spec_mstep = em->n_spec; break; }
 		ha->em = em; ha->m = &em->model_spec[j];
 		em->spec_aux[j] = ha;
 		em->spec[j] = psmch_spec_start(objective, np, ha);
-		if (em->spec[j] == 0) { psmch_model_free(&em->model_spec[j]); free(ha); em->spec_mstep = em->n_spec >= 1 ? 1 : 0; break; }
+		if (em->spec[j] == 0) { psmch_model_free(&em->model_spec[j]); free(ha); em->spec_mstep = em->n_spec; break; }
 		++em->n_spec;
 	}
 	last = (double*)malloc(sizeof(double) * np);
 	memcpy(last, x, sizeof(double) * np);
 	for (k = 0; k < em->n_spec; ++k) psmch_spec_begin(em->spec[k]);
-	em->Q1 = -psmch_hooke_jeeves_spec(objective, em->spec, em->n_spec >= 3 ? 3 : (em->n_spec >= 1 ? 1 : 0), np, x, &aux, PSMCH_HJ_RADIUS,
+	em->Q1 = -psmch_hooke_jeeves_spec(objective, em->spec, em->n_spec, np, x, &aux, PSMCH_HJ_RADIUS,
 	                                  PSMCH_HJ_EPS, PSMCH_HJ_MAXCALL, last, &n_calls);
 	for (k = 0; k < em->n_spec; ++k) psmch_spec_end(em->spec[k]);
 	em->hj_calls = n_calls;

@@ -11,7 +11,7 @@ typedef struct {
 	void *data;
 	int n, calls;
 	psmch_spec_t **spec; /* helper threads (spec.c) or NULL */
-	int n_spec;          /* 0, 1 or 3 helpers are used */
+	int n_spec;          /* 0, 1, 3, 5 or 7 helpers are used (look-ahead over 1..4 coordinates) */
 	double *last;        /* the last evaluated point in the order of the sequential search, or NULL */
 } hj_t;
 
@@ -64,8 +64,8 @@ static double probe(hj_t *h, double *x, double fbest, double *step)
 {
 	int k = 0;
 	while (k < h->n) {
-		double va, vb;
 		if (h->n_spec == 0) {
+			double va, vb;
 			x[k] += step[k];
 			va = eval(h, x);
 			if (va < fbest) { fbest = va; ++k; continue; }
@@ -77,31 +77,35 @@ static double probe(hj_t *h, double *x, double fbest, double *step)
 			++k;
 			continue;
 		}
-		{
-			const int two = h->n_spec >= 3 && k + 1 < h->n;
-			double va2 = 0.0, vb2 = 0.0;
-			submit_minus(h->spec[0], x, step, k);
-			if (two) { /* if coordinate k fails twice, x[k] comes back through this arithmetic (not necessarily bit-identical to xk) */
-				const double xk = x[k], ns = 0.0 - step[k];
-				x[k] = ((xk + step[k]) + (ns + ns)) - ns;
-				submit_plus(h->spec[1], x, step, k + 1);
-				submit_minus(h->spec[2], x, step, k + 1);
-				x[k] = xk;
+		{	/* look ahead over `depth` coordinates: helper 0 takes -step of coordinate k, helpers 2j-1 / 2j the two points of
+			 * coordinate k+j under the hypothesis that the coordinates before it fail twice (they then come back through the
+			 * sequential code's arithmetic, which is not always the identity, so the same arithmetic is applied here) */
+			enum { MAXD = 4 };
+			int depth = (h->n_spec + 1) / 2, j, moved = 0;
+			double va[MAXD], vb[MAXD], keep[MAXD] = {0.0, 0.0, 0.0, 0.0};
+			if (depth > MAXD) depth = MAXD;
+			if (depth > h->n - k) depth = h->n - k;
+			for (j = 0; j < depth; ++j) {
+				keep[j] = x[k + j];
+				if (j > 0) submit_plus(h->spec[2 * j - 1], x, step, k + j);
+				submit_minus(h->spec[2 * j], x, step, k + j);
+				if (j + 1 < depth) { /* x[k+j] as it will be after failing twice */
+					const double ns = 0.0 - step[k + j];
+					x[k + j] = ((keep[j] + step[k + j]) + (ns + ns)) - ns;
+				}
 			}
+			for (j = 0; j + 1 < depth; ++j) x[k + j] = keep[j];
 			{ /* the caller's share: +step of coordinate k (not counted here: settle() does the book-keeping) */
-				const double xk = x[k];
-				x[k] = xk + step[k];
-				va = h->f(h->n, x, h->data);
-				x[k] = xk;
+				x[k] = keep[0] + step[k];
+				va[0] = h->f(h->n, x, h->data);
+				x[k] = keep[0];
 			}
-			vb = psmch_spec_wait(h->spec[0]);
-			if (two) {
-				va2 = psmch_spec_wait(h->spec[1]);
-				vb2 = psmch_spec_wait(h->spec[2]);
+			for (j = 0; j < depth; ++j) {
+				if (j > 0) va[j] = psmch_spec_wait(h->spec[2 * j - 1]);
+				vb[j] = psmch_spec_wait(h->spec[2 * j]);
 			}
-			if (settle(h, x, &fbest, step, k, va, vb) || !two) { ++k; continue; } /* moved: the next coordinate's points are stale */
-			settle(h, x, &fbest, step, k + 1, va2, vb2);
-			k += 2;
+			for (j = 0; j < depth && !moved; ++j) moved = settle(h, x, &fbest, step, k + j, va[j], vb[j]);
+			k += j; /* the coordinates settled; the points evaluated for later ones are stale once the point has moved */
 		}
 	}
 	return fbest;
@@ -120,7 +124,7 @@ double psmch_hooke_jeeves_spec(psmch_func_t f, psmch_spec_t **spec, int n_spec, 
 	double fx, fy, radius = r;
 	int k, done = 0;
 	h.f = f; h.data = data; h.n = n; h.calls = 0; h.spec = spec; h.last = last;
-	h.n_spec = (spec == 0 || n_spec <= 0) ? 0 : (n_spec >= 3 ? 3 : 1);
+	h.n_spec = (spec == 0 || n_spec <= 0) ? 0 : (n_spec >= 7 ? 7 : (n_spec >= 5 ? 5 : (n_spec >= 3 ? 3 : 1)));
 	for (k = 0; k < n; ++k) {
 		step[k] = fabs(x[k]) * r;
 		if (step[k] == 0) step[k] = r;

@@ -123,7 +123,7 @@ void   psmch_spec_submit(psmch_spec_t *s, const double *x);
 double psmch_spec_wait(psmch_spec_t *s);
 void   psmch_spec_stop(psmch_spec_t *s);
 /* last (n doubles or NULL): the last evaluated point in the order of the sequential search; n_calls: evaluations counted */
-double psmch_hooke_jeeves_spec(psmch_func_t f, psmch_spec_t **spec, int n_spec /* 0, 1 or 3 helpers */, int n, double *x, void *data,
+double psmch_hooke_jeeves_spec(psmch_func_t f, psmch_spec_t **spec, int n_spec /* 0, 1, 3, 5 or 7 helpers */, int n, double *x, void *data,
                                double r, double eps, int max_calls, double *last, int *n_calls);
 #define PSMCH_HJ_RADIUS 0.5
 #define PSMCH_HJ_EPS 1e-7
@@ -163,11 +163,11 @@ typedef struct {
 	int exact_qd;    /* dense counts fetched after every E-step (counts.A) */
 	int borrowed;    /* ctx[0] belongs to the caller (bootstrap replicates share one context per GPU slot) */
 	int exact_mstep; /* PSMC_B200_EXACT_MSTEP: trial evaluations with scalar libm instead of libmvec */
-	int spec_mstep;  /* speculative evaluator threads in the M-step: 0, 1 or 3 (PSMC_B200_MSTEP_SPEC; 0 for bootstrap workers) */
+	int spec_mstep;  /* speculative evaluator threads in the M-step: 0, 1, 3, 5 or 7 (PSMC_B200_MSTEP_SPEC; 0 for bootstrap workers) */
 	int n_spec;      /* helpers running */
-	psmch_model_t model_spec[3]; /* the helpers' own model instances */
-	psmch_spec_t *spec[3];
-	void *spec_aux[3];
+	psmch_model_t model_spec[7]; /* the helpers' own model instances */
+	psmch_spec_t *spec[7];
+	void *spec_aux[7];
 	double t_estep_ms, t_mstep_ms; /* wall time of the last iteration */
 } psmch_em_t;
 

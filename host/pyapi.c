@@ -204,12 +204,12 @@ int psmch_py_mstep(const char *pattern, double alpha0, double *params, const dou
 	a.sp = &sp; a.m = &m; a.c = &c; a.cnt = 0; a.fast = getenv("PSMC_B200_EXACT_MSTEP") == 0;
 	{	/* PSMC_B200_MSTEP_SPEC=1|3: speculative trial points on helper threads (spec.c), as the EM driver does */
 		const int want = getenv("PSMC_B200_MSTEP_SPEC") ? atoi(getenv("PSMC_B200_MSTEP_SPEC")) : 0;
-		psmch_model_t m2[3];
-		maux_t a2[3];
-		psmch_spec_t *spec[3] = {0, 0, 0};
+		psmch_model_t m2[7];
+		maux_t a2[7];
+		psmch_spec_t *spec[7] = {0, 0, 0, 0, 0, 0, 0};
 		double *last = (double*)malloc(sizeof(double) * sp.n_params);
 		int n_calls = 0, i, ns = 0;
-		for (i = 0; i < (want >= 3 ? 3 : (want >= 1 ? 1 : 0)); ++i) {
+		for (i = 0; i < (want >= 7 ? 7 : (want >= 5 ? 5 : (want >= 3 ? 3 : (want >= 1 ? 1 : 0)))); ++i) {
 			if (psmch_model_alloc(&m2[i], &sp) != 0) break;
 			a2[i] = a; a2[i].m = &m2[i];
 			spec[i] = psmch_spec_start(mobjective, sp.n_params, &a2[i]);
@@ -218,7 +218,7 @@ int psmch_py_mstep(const char *pattern, double alpha0, double *params, const dou
 			++ns;
 		}
 		memcpy(last, x, sizeof(double) * sp.n_params);
-		res[1] = -psmch_hooke_jeeves_spec(mobjective, spec, ns >= 3 ? 3 : (ns >= 1 ? 1 : 0), sp.n_params, x, &a, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS,
+		res[1] = -psmch_hooke_jeeves_spec(mobjective, spec, ns, sp.n_params, x, &a, PSMCH_HJ_RADIUS, PSMCH_HJ_EPS,
 		                                  PSMCH_HJ_MAXCALL, last, &n_calls);
 		for (i = 0; i < ns; ++i) { psmch_spec_end(spec[i]); psmch_spec_stop(spec[i]); psmch_model_free(&m2[i]); }
 		res[2] = n_calls;
