@@ -50,6 +50,23 @@ def test_generation1_kernels_still_match(oracle, monkeypatch):
     compare_stats(got, want, TOL, N)
 
 
+def test_generations_agree_at_scale(oracle, monkeypatch):
+    """3 M bins (far beyond what the oracle does in seconds): the two independently written kernel generations, with
+    different chunk plans, overlaps and scan networks, must agree on LL and on every expected count"""
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=17)
+    seqs = _seqs(m, [1500000, 900000, 600000, 333], seed=18)
+    res = {}
+    for gen in ("1", "2"):
+        monkeypatch.setenv("PSMC_B200_GEN", gen)
+        with EStep(seqs, N) as es:
+            res[gen] = es.run(_model(m))
+            info = es.info()
+        assert info["fallbacks"] == 0 and info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
+    compare_stats(res["2"], res["1"], TOL, N)
+
+
 def test_chunking_is_exact(oracle):
     """the chunk plan must not change the result (it does for the reference's splitfa, which cuts the likelihood)"""
     from psmc_b200 import EStep
