@@ -205,3 +205,30 @@ def test_emulated_dense_counts(oracle, emu_plain, N, mult):
     compare_stats(got, want, TOL, N)
     scale = np.maximum(np.abs(want["A"]), 1e-9 * np.abs(want["A"]).max())
     assert np.max(np.abs(A - want["A"]) / scale) < TOL
+
+
+def test_emulated_dense_counts_refused_beyond_64_states(oracle, emu_plain):
+    """the dense-count option needs the generation-2 backward kernels (at most 64 states): it must say so, not misbehave"""
+    from psmc_b200 import EStep, Psmc200Error
+    N = 100
+    m = make_model(oracle, N, seed=71)
+    seqs = _seqs(m, [200], seed=72)
+    with EStep(seqs, N, chunk_len=64) as es:
+        with pytest.raises(Psmc200Error):
+            es.set_dense(True)
+        with pytest.raises(Psmc200Error):
+            es.dense_counts()
+        got = es.run(_model(m))          # the E-step itself is unaffected
+    compare_stats(got, oracle_stats(oracle, m, seqs), TOL, N)
+
+
+def test_emulated_decode_128_padded_states(oracle, emu_plain):
+    from psmc_b200 import EStep
+    N = 100
+    m = make_model(oracle, N, seed=73)
+    seqs = _seqs(m, [400, 90], seed=74)
+    with EStep(seqs, N, chunk_len=100) as es:
+        got = es.decode(_model(m), 0, full=True, want_s=True)
+    want = oracle.decode(m["a"], m["e"], m["a0"], seqs[0], full=True)
+    assert np.max(np.abs(got["post"] - want["post"])) < 1e-11
+    assert np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
