@@ -28,7 +28,7 @@ int psmch_decode(const psmch_opts_t *o, psmch_em_t *em, const psmch_seqs_t *sq, 
 		const int g = em->seq_owner[i], L = s->L, full = (o->flag & PSMCH_F_FULLDEC) && !(o->flag & PSMCH_F_PROB);
 		int32_t *bk;
 		double *bp, *post = 0, *prec = 0, *sc = 0;
-		if (L == 0) continue; /* empty records are not held by the contexts */
+		if (L == 0) { ++local[g]; continue; } /* nothing to decode; psmc_b200_decode counts the records as given to create */
 		bk = (int32_t*)malloc(sizeof(int32_t) * L);
 		bp = (double*)malloc(sizeof(double) * L);
 		if (full) { post = (double*)malloc(sizeof(double) * (size_t)L * N); prec = (double*)malloc(sizeof(double) * L); }

@@ -5,6 +5,8 @@
  *   IT line, posterior sigma     (em.c:66-74)
  * Reproduced quirks: the objective sees |x| (em.c:22); after the search the model is left at the LAST
  * EVALUATED trial point, not at the optimum (em.c:61-67 frees the optimum without copying it back). */
+#define _GNU_SOURCE
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -72,7 +74,11 @@ static int init_model(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t 
 	em->exact_mstep = getenv("PSMC_B200_EXACT_MSTEP") != 0; /* scalar libm in every trial evaluation */
 	{	/* helper threads of the M-step (spec.c): 3 if every process on this node can have 4 cores, else 1; PSMC_B200_MSTEP_SPEC=0/1/3 overrides */
 		const char *env = getenv("PSMC_B200_MSTEP_SPEC"), *lws = getenv("LOCAL_WORLD_SIZE");
-		const long cores = sysconf(_SC_NPROCESSORS_ONLN);
+		long cores = sysconf(_SC_NPROCESSORS_ONLN);
+		{	/* the cores this process may actually run on (cgroup / taskset / srun --cpus-per-task) */
+			cpu_set_t set;
+			if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0 && CPU_COUNT(&set) < cores) cores = CPU_COUNT(&set);
+		}
 		const int procs = (lws && atoi(lws) > 0) ? atoi(lws) : 1;
 		const long per = cores / procs;
 		em->spec_mstep = per >= 4 ? 3 : (per >= 2 ? 1 : 0); /* (5 or 7 helpers measured within noise of 3 on a 16-core host) */
@@ -91,6 +97,10 @@ int psmch_em_init_shared(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs
 	em->n_gpus = 1;
 	em->ctx[0] = ctx;
 	em->borrowed = 1;
+	if (em->exact_qd && psmc_b200_set_dense(ctx, 1) != 0) { /* (idempotent: the rows are allocated once per context) */
+		fprintf(stderr, "psmc: --exact-qd: %s\n", psmc_b200_last_error());
+		return -1;
+	}
 	return 0;
 }
 
@@ -98,6 +108,8 @@ int psmch_em_init(psmch_em_t *em, const psmch_opts_t *o, const psmch_seqs_t *sq,
 {
 	int g, i, rc;
 	if (init_model(em, o, sq, rnd) != 0) return -1;
+	for (i = 0, em->n_seqs = 0; i < sq->n_seqs; ++i) /* HMM_TINY terms: one per NON-EMPTY record, as the single-GPU path counts them */
+		if (sq->seqs[i].L > 0) ++em->n_seqs;
 	/* shard whole sequences over the GPUs: longest-processing-time first */
 	em->n_gpus = o->n_gpus;
 	em->seq_owner = (int*)calloc(sq->n_seqs > 0 ? sq->n_seqs : 1, sizeof(int));

@@ -10,6 +10,7 @@ int psmch_parse_pattern(const char *pattern, int *n_free, int **par_map)
 {
 	const char *p;
 	int cap = 16, ng = 0, *glen, total = 0, i, j, pos, *map;
+	long total_guard = 0;
 	if (pattern == 0) return -1;
 	for (p = pattern; *p; ++p)
 		if (!isdigit((unsigned char)*p) && *p != '*' && *p != '+') return -1; /* the reference asserts (cli.c:74) */
@@ -18,7 +19,9 @@ int psmch_parse_pattern(const char *pattern, int *n_free, int **par_map)
 	for (;;) {
 		long a = strtol(p, (char**)&p, 10), rep = 1, len = a;
 		if (*p == '*') { rep = a; ++p; len = strtol(p, (char**)&p, 10); }
-		if (ng + rep > 255) { free(glen); return -1; }                       /* stack depth assert (cli.c:81) */
+		if (rep < 0 || ng + rep > 255) { free(glen); return -1; }            /* stack depth assert (cli.c:81) */
+		if (len < 0 || len > PSMCH_MAX_INTERVALS || total_guard + rep * len > PSMCH_MAX_INTERVALS) { free(glen); return -1; } /* no int overflow, sane cap */
+		total_guard += rep * len;
 		if (ng + rep > cap) { while (ng + rep > cap) cap <<= 1; glen = (int*)realloc(glen, sizeof(int) * cap); }
 		for (i = 0; i < rep; ++i) glen[ng++] = (int)len;
 		if (*p == '+') { ++p; continue; }

@@ -24,6 +24,7 @@ extern "C" {
 #endif
 
 #define PSMCH_VERSION "0.6.5-r74-dirty" /* the version string consumers see (cli.c:13); ours is in MM B200 line */
+#define PSMCH_MAX_INTERVALS 4096 /* cap on the sum of the pattern lengths (the GPU path itself stops at 128 states) */
 #define PSMCH_N_PARAMS 3                /* theta, rho, max_t (psmc.h:12) */
 #define PSMCH_T_INF 1000.0              /* psmc.h:14 */
 #define PSMCH_TINY 1e-25                /* khmm.h:28 */

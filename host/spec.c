@@ -10,6 +10,14 @@
 #include <pthread.h>
 #include "psmc_host.h"
 
+#if defined(__x86_64__) || defined(__i386__)
+#define PSMCH_CPU_RELAX() __builtin_ia32_pause()
+#elif defined(__aarch64__)
+#define PSMCH_CPU_RELAX() __asm__ __volatile__("yield")
+#else
+#define PSMCH_CPU_RELAX() ((void)0)
+#endif
+
 struct psmch_spec {
 	psmch_func_t f;
 	void *data;
@@ -39,7 +47,7 @@ static void *helper(void *arg)
 				seen = sub;
 				__atomic_store_n(&s->done, sub, __ATOMIC_RELEASE);
 			} else {
-				__builtin_ia32_pause();
+				PSMCH_CPU_RELAX();
 			}
 		}
 	}

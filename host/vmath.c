@@ -5,7 +5,11 @@
  * the GPU is always recomputed with the scalar, bit-reproducible path. */
 #include <math.h>
 
+#if defined(__x86_64__)
 #define VCLONES __attribute__((target_clones("avx512f", "avx2,fma", "default")))
+#else
+#define VCLONES /* other hosts (aarch64: Grace): one clone, the compiler's own vector math */
+#endif
 
 VCLONES void psmch_vexp(int n, const double *x, double *y)
 {

@@ -144,6 +144,7 @@ int  psmc_b200_unpack_stats(int32_t n_states, const double *raw, int64_t n_seqs_
 /* Posterior decoding of one sequence.  Replaces aux.c:157-158 (hmm_forward/hmm_backward) plus
  * hmm_post_decode (khmm.c:264-282; aux.c:167-182) and, when post/p_recomb are non-NULL,
  * hmm_post_state (khmm.c:286-293) and the recombination probability of aux.c:188-193.
+ *   seq_id indexes the n_seqs records as given to create (empty records included; decoding one is EINVAL),
  *   best_k[L]: argmax_k f*b*s (first maximum wins), best_p[L]: its posterior,
  *   model may be NULL to reuse the forward pass of the previous estep/decode call on this context.
  *   post[L*N] (optional), p_recomb[L] (optional, 0 at the last bin), s_out[L] (optional; hmm_data_t::s, aux.c:159-164). */

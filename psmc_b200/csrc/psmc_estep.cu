@@ -1231,9 +1231,13 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
                                 double *best_p, double *post, double *p_recomb, double *s_out)
 {
 	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
-	if (seq_id < 0 || seq_id >= c->n_seqs) return set_err(PSMC_B200_EINVAL, "seq_id out of range");
+	// seq_id indexes the records AS GIVEN to create (empty records included), like psmc_b200_set_multiplicity
+	if (seq_id < 0 || seq_id >= c->n_seqs_given) return set_err(PSMC_B200_EINVAL, "seq_id out of range");
+	if (c->kept_of[seq_id] < 0) return set_err(PSMC_B200_EINVAL, "record %d is empty: nothing to decode", seq_id);
 	if (!best_k || !best_p) return set_err(PSMC_B200_EINVAL, "best_k/best_p are NULL");
-	if (c->mult[seq_id] <= 0) return set_err(PSMC_B200_EINVAL, "sequence %d has multiplicity 0 (psmc_b200_set_multiplicity)", seq_id);
+	const int given_id = seq_id;
+	seq_id = c->kept_of[seq_id];
+	if (c->mult[seq_id] <= 0) return set_err(PSMC_B200_EINVAL, "sequence %d has multiplicity 0 (psmc_b200_set_multiplicity)", given_id);
 	int rc = 0;
 	if (model) {
 		rc = check_model(c, model);

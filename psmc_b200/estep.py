@@ -145,7 +145,8 @@ class EStep:
         return buf.result()
 
     def decode(self, model, seq_id, full=False, want_s=False):
-        L = int(self.L[seq_id])
+        """seq_id indexes the records as given at construction (empty records included)"""
+        L = int(self.L[seq_id]) if 0 <= seq_id < len(self.L) else 0
         bk = np.zeros(L, dtype=np.int32); bp = np.zeros(L)
         post = np.zeros((L, self.N)) if full else None
         pr = np.zeros(L) if full else None

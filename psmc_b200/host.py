@@ -55,11 +55,12 @@ def load_host():
 def parse_pattern(pattern):
     L = load_host()
     nf = C.c_int()
-    pm = np.zeros(1024, dtype=np.int32)
-    n = L.psmch_py_pattern(pattern.encode(), C.byref(nf), pm.ctypes.data_as(_ip))
+    n = L.psmch_py_pattern(pattern.encode(), C.byref(nf), None)     # first call: sizes only
     if n < 0:
         raise ValueError("bad pattern %r" % pattern)
-    return n, nf.value, pm[: n + 1].copy()
+    pm = np.zeros(n + 1, dtype=np.int32)
+    L.psmch_py_pattern(pattern.encode(), C.byref(nf), pm.ctypes.data_as(_ip))
+    return n, nf.value, pm
 
 
 def model_from_params(pattern, params, alpha0=0.1, diverg=False, inp_ti=None):

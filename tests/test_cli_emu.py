@@ -54,3 +54,12 @@ def test_emulated_cli_64_states_exact_qd(emu_env, tmp_path):
     for a, b in zip(qd_g, qd_w):
         for x, y in zip(a, b):
             assert abs(x - y) <= 2e-5 * abs(y) + 2e-6, (a, b)
+
+
+def test_emulated_replicates_with_exact_qd(emu_env, tmp_path):
+    """--replicates together with --exact-qd: the shared bootstrap context must spill the backward rows too"""
+    args = ["-N2", "-t15", "-r5", "-p", "4+25*2+4+6", "--exact-qd", "--split=300", "--replicates", "2", "--seed", "5",
+            os.path.join(G, "small64.psmcfa.gz")]
+    got = run(args, emu_env, str(tmp_path / "rep.psmc"))
+    assert sum(1 for l in got if l.startswith("QD")) == 6          # 2 replicates x (round 0 + 2 iterations)
+    assert sum(1 for l in got if l.startswith("RD")) == 6

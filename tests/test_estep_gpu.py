@@ -219,3 +219,48 @@ def test_decode_matches_oracle(oracle, N):
             if diff.any():
                 srt = np.sort(want["post"][diff], axis=1)
                 assert np.all(srt[:, -1] - srt[:, -2] < 1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+# Parity at the benchmark regime against the UNMODIFIED reference (oracle/_ref/libpsmcref.so = khmm.c compiled as is):
+# default chunk plan (one resident wave, default overlaps, operator prediction on, default repair rounds), 64 states,
+# two consecutive E-steps on one context (the second one runs with the boundary predictions of the first).
+# ------------------------------------------------------------------------------------------------
+def _bench_contig(L, seed):
+    """a contig drawn exactly like bench.py's genome (true bottleneck history, 2 % missing data in runs)"""
+    from psmc_b200 import host, synth
+    n, nf, _ = host.parse_pattern("4+25*2+4+6")
+    hm = host.model_from_params("4+25*2+4+6", np.concatenate([[0.05, 0.0125, 15.0], synth.bottleneck_lambdas(nf)]))
+    return synth.simulate(hm["a0"], hm["model"].dense(), hm["e"], L, np.random.default_rng(seed))
+
+
+def _ref_stats(ref, m, seqs):
+    r = ref.estep(m["a"], m["e"], m["a0"], seqs)
+    A = r["A"]          # hmm_exp_t::A summed over the records; its five structured marginals (SURVEY.md 8a-0) in numpy
+    lo, up = np.tril(A, -1), np.triu(A, 1)
+    r.update(RL=lo.sum(axis=1), CL=lo.sum(axis=0), RU=up.sum(axis=1), CU=up.sum(axis=0), AD=np.diag(A).copy())
+    return r
+
+
+@pytest.mark.parametrize("L,seed", [(500000, 20260925), (2489564, 20260926)])
+def test_benchmark_regime_matches_unmodified_reference(ref, L, seed):
+    from psmc_b200 import EStep
+    N = 64
+    seq = _bench_contig(L, seed)
+    # EM's starting model (flat history, theta from the data: core.c:39) and a perturbed bottleneck model: the second
+    # E-step sees a different model than the one its boundary predictions were made with, as in EM
+    th = -np.log(1.0 - float((seq == 1).sum()) / float((seq < 2).sum()))
+    m0 = ref.update_hmm("4+25*2+4+6", np.concatenate([[th, th / 5.0, 15.0], np.ones(28)]))
+    m1 = make_model(ref, N, seed=7, theta=0.05)
+    with EStep([seq], N) as es:
+        for it, m in enumerate((m0, m1)):
+            got = es.run(_model(m))
+            info = es.info()
+            want = _ref_stats(ref, m, [seq])
+            errs = compare_stats(got, want, TOL, N)
+            print("L=%d E-step %d: chunks %d x %d, failed fwd/bwd %d/%d, fallbacks %d, worst rel err %s"
+                  % (L, it, info["n_chunks"], info["chunk_len"], info["failed_fwd"], info["failed_bwd"], info["fallbacks"],
+                     {k: "%.1e" % v for k, v in errs.items()}))
+            assert info["fallbacks"] == 0
+            assert info["warm_len"] > 0 and info["n_chunks"] > 1000     # the default plan: one resident wave, fast path
+            assert info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12

@@ -148,6 +148,25 @@ def test_emulated_decode_matches_oracle(oracle, emu_plain, N):
             assert np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
 
 
+def test_emulated_decode_counts_records_as_given(oracle, emu_plain):
+    """seq_id of psmc_b200_decode indexes the records as given to create: an empty record in front must not shift it"""
+    from psmc_b200 import EStep, Psmc200Error
+    N = 23
+    m = make_model(oracle, N, seed=23)
+    a, b = _seqs(m, [300, 411], seed=24)
+    with EStep([np.zeros(0, dtype=np.int8), a, b], N, chunk_len=100) as es:
+        mod = _model(m)
+        with pytest.raises(Psmc200Error):
+            es.decode(mod, 0)                      # empty record: nothing to decode
+        for i, s in ((1, a), (2, b)):
+            got = es.decode(mod, i, full=False)
+            want = oracle.decode(m["a"], m["e"], m["a0"], s, full=False)
+            assert len(got["best_p"]) == len(s)
+            assert np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
+        with pytest.raises(Psmc200Error):
+            es.decode(mod, 3)
+
+
 def test_emulated_adaptive_overlaps_over_iterations(oracle, emu_plain, monkeypatch):
     """per-boundary overlaps shrink while the certificate's mismatch stays at the rounding floor and grow when it does not;
     the chunks are re-sorted by their number of steps after every E-step -- the result must stay exact throughout"""
