@@ -144,18 +144,10 @@ struct psmc_b200_ctx {
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
-	int side_order = 0;         // PSMC_B200_SIDE_ORDER, see launch_warm
 	bool dense = false;         // psmc_b200_set_dense: the backward pass also stores the rows g_u for psmc_b200_dense_counts
 	bool dense_valid = false;   // ghat holds the rows of the last E-step
 	double *d_ghat = nullptr, *d_cpart = nullptr, *d_cdense = nullptr;
 	int cap_cpart = 0;
-	int warm32 = 0, warm32_b = 0; // bins of FP32 pre-warm-up in front of the FP64 overlaps (PSMC_B200_WARM32 / _WARM32_BWD; 0 = none)
-	double *d_pre_f = nullptr, *d_pre_b = nullptr; // its results: start vectors of the forward / backward overlaps
-	bool adapt = false;         // adaptive per-boundary overlaps (PSMC_B200_ADAPT=1; measured on B200: no gain -- the kernels' duration is set by
-	                            // the slowest boundaries either way and the extra failures while adapting cost more than the shorter warm-ups save)
-	int adapt_max_chunks = 16384; // (k_order ranks in O(n^2))
-	int warm_max_b = 0;         // ceiling of an adaptive backward overlap
-	int32_t *d_warm_f = nullptr, *d_warm_b = nullptr, *d_order_f = nullptr, *d_order_b = nullptr, *d_tight_f = nullptr, *d_tight_b = nullptr;
 	int gen = 2;                // kernel generation (PSMC_B200_GEN=1: the Kogge-Stone kernels)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
@@ -227,8 +219,7 @@ static void free_plan(psmc_b200_ctx *c)
 	              (void **)&c->d_chunk_sub0, (void **)&c->d_Tsub, (void **)&c->d_Texsub, (void **)&c->d_vsub, (void **)&c->d_bsub,
 	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b,
 	              (void **)&c->d_pred[0], (void **)&c->d_pred[1], (void **)&c->d_pred_b[0], (void **)&c->d_pred_b[1],
-	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b,
-	              (void **)&c->d_warm_f, (void **)&c->d_warm_b, (void **)&c->d_order_f, (void **)&c->d_order_b, (void **)&c->d_tight_f, (void **)&c->d_tight_b, (void **)&c->d_pre_f, (void **)&c->d_pre_b};
+	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b};
 	for (auto q : p) { cudaFree(*q); *q = nullptr; }
 	c->bytes_total -= c->bytes_plan;
 	c->bytes_plan = 0;
@@ -326,26 +317,6 @@ static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 
 // (Re)build both chunk plans over the sequences with multiplicity > 0 and upload them.  The packed observations,
 // the forward spill (indexed by bin) and everything else that does not depend on the plan stay where they are.
-// adaptive overlaps start from the configured lengths, in plan order
-static int reset_overlaps(psmc_b200_ctx *c)
-{
-	if (!c->d_warm_f) return 0;
-	c->warm_max_b = std::max(c->warm_len_bwd, 2 * c->warm_len);
-	std::vector<int32_t> wf((size_t)std::max(c->n_chunks, 1), c->warm_len), wb((size_t)std::max(c->n_chunks_b, 1), c->warm_len_bwd);
-	std::vector<int32_t> of((size_t)std::max(c->n_chunks, 1)), ob((size_t)std::max(c->n_chunks_b, 1));
-	for (size_t i = 0; i < of.size(); ++i) of[i] = (int32_t)i;
-	for (size_t i = 0; i < ob.size(); ++i) ob[i] = (int32_t)i;
-	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaMemcpyAsync(c->d_warm_f, wf.data(), sizeof(int32_t) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaMemcpyAsync(c->d_warm_b, wb.data(), sizeof(int32_t) * (size_t)c->n_chunks_b, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaMemcpyAsync(c->d_order_f, of.data(), sizeof(int32_t) * (size_t)c->n_chunks, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaMemcpyAsync(c->d_order_b, ob.data(), sizeof(int32_t) * (size_t)c->n_chunks_b, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaMemsetAsync(c->d_tight_f, 0, sizeof(int32_t) * (size_t)std::max(c->n_chunks, 1), c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaMemsetAsync(c->d_tight_b, 0, sizeof(int32_t) * (size_t)std::max(c->n_chunks_b, 1), c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
-	return 0;
-}
-
 static int replan(psmc_b200_ctx *c)
 {
 	const int NP = c->NP;
@@ -481,14 +452,6 @@ static int replan(psmc_b200_ctx *c)
 		alloc((void **)&c->d_bsub, sizeof(double) * (size_t)csb * NP);
 		alloc((void **)&c->d_llsub, sizeof(double) * (size_t)cs);
 		alloc((void **)&c->d_partsub, sizeof(double) * (size_t)csb * S_COUNT * NP);
-		alloc((void **)&c->d_pre_f, sizeof(double) * (size_t)cc * NP);
-		alloc((void **)&c->d_pre_b, sizeof(double) * (size_t)cb * NP);
-		alloc((void **)&c->d_warm_f, sizeof(int32_t) * (size_t)cc);
-		alloc((void **)&c->d_warm_b, sizeof(int32_t) * (size_t)cb);
-		alloc((void **)&c->d_order_f, sizeof(int32_t) * (size_t)cc);
-		alloc((void **)&c->d_order_b, sizeof(int32_t) * (size_t)cb);
-		alloc((void **)&c->d_tight_f, sizeof(int32_t) * (size_t)cc);
-		alloc((void **)&c->d_tight_b, sizeof(int32_t) * (size_t)cb);
 		alloc((void **)&c->d_cw, sizeof(double) * (size_t)cc);
 		alloc((void **)&c->d_cw_b, sizeof(double) * (size_t)cb);
 		c->bytes_total += c->bytes_plan;
@@ -516,10 +479,6 @@ static int replan(psmc_b200_ctx *c)
 	CUDA_TRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(st), PSMC_B200_ECUDA); // the host vectors above go out of scope
-	{
-		int rc = reset_overlaps(c);
-		if (rc) return rc;
-	}
 	c->have_prev = false;
 	c->fwd_valid = false;
 	c->launched = false;
@@ -566,14 +525,6 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	{
 		const char *env = getenv("PSMC_B200_GEN");
 		if (env && atoi(env) == 1) c->gen = 1;
-		env = getenv("PSMC_B200_WARM32");
-		if (env && atoi(env) >= 0) c->warm32 = c->warm32_b = atoi(env);
-		env = getenv("PSMC_B200_WARM32_BWD");
-		if (env && atoi(env) >= 0) c->warm32_b = atoi(env);
-		env = getenv("PSMC_B200_ADAPT");
-		if (env) c->adapt = atoi(env) != 0;
-		env = getenv("PSMC_B200_SIDE_ORDER");
-		if (env) c->side_order = atoi(env);
 		env = getenv("PSMC_B200_G2_FWD");
 		if (env && atoi(env) == 16) c->g2_fwd = 16;
 		env = getenv("PSMC_B200_G2_BWW");
@@ -796,18 +747,11 @@ struct Gen2 {
 	static constexpr bool BWD_OK = NP <= 64;
 };
 
-// FP32 pre-warm-up (k_prewarm): generation 2, 8-lane groups (NP <= 64), PSMC_B200_WARM32 > 0
-template <int NP>
-static bool prewarm_on(const psmc_b200_ctx *c) { return NP <= 64 && c->gen == 2 && c->g2_fwd == 8 && c->g2_bww == 8 && c->warm32 > 0 && c->d_pre_f != nullptr; }
-
 template <int NP>
 static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
-	const bool ad = c->adapt && warm > 0 && !use_prev && c->n_chunks <= c->adapt_max_chunks;
-	const bool pre = prewarm_on<NP>(c) && warm > 0 && !use_prev && !ad;
-	if (pre) LAUNCH((k_prewarm<(NP <= 64 ? NP / 8 : 8), 0>), blocks_for(c->n_chunks, 8), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, warm, c->warm32, c->d_pre_f);
-#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, ad ? c->d_order_f : nullptr, ad ? c->d_warm_f : nullptr, pre ? c->d_pre_f : nullptr)
+#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
 	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWD(16, 2);
 	else if (c->gen == 2) FWD(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8, 1);
@@ -847,10 +791,7 @@ static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const dou
 template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
-	const bool ad = c->adapt && !use_prev && c->n_chunks_b <= c->adapt_max_chunks;
-	const bool pre = prewarm_on<NP>(c) && !use_prev && !ad;
-	if (pre) LAUNCH((k_prewarm<(NP <= 64 ? NP / 8 : 8), 1>), blocks_for(c->n_chunks_b, 8), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->warm32_b, c->d_pre_b);
-#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr, ad ? c->d_order_b : nullptr, ad ? c->d_warm_b : nullptr, pre ? c->d_pre_b : nullptr)
+#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
 	if (c->gen == 2 && (c->g2_bww == 16 || NP > 64)) BWW(16, 2);
 	else if (c->gen == 2) BWW(8, 2);
 	else if (c->g_bww == 8 && NP / 8 <= 8) BWW(8, 1);
@@ -954,17 +895,14 @@ static int launch_warm(psmc_b200_ctx *c)
 	const int wpb = 4, nblk = (c->n_chunks + wpb - 1) / wpb;
 	const int hot = (c->have_prev && c->warm_hot > 0) ? 1 : 0;
 	const int wl = hot ? c->warm_hot : c->warm_len;
-	const bool adf = c->adapt && !hot && c->n_chunks <= c->adapt_max_chunks, adb = c->adapt && !hot && c->n_chunks_b <= c->adapt_max_chunks;
 	// The backward warm-up needs only observations + model: it runs on the side stream, concurrently with the forward pass;
 	// on small shards (multi-GPU) a long one would become the critical path, so it is capped at the forward kernel's length.
-	// The side stream also computes, ahead of time, the operators of the chunks that failed in the previous E-step.
-	// Order on the side stream (PSMC_B200_SIDE_ORDER): 0 = warm-up, forward operators, backward operators;
-	//                                                  1 = forward operators first (the forward repair rounds wait for them only).
+	// The side stream also computes, ahead of time, the operators of the chunks that failed in the previous E-step
+	// (after the warm-up: forward operators, then backward operators).
 	cudaEventRecord(c->ev_fork, st);
 	cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
 	const int wl_b = (c->warm_bwd_fixed || c->warm_len_bwd <= c->warm_len + c->chunk_len) ? c->warm_len_bwd : std::max(c->warm_len, c->warm_len + c->chunk_len);
-	// adaptive overlaps may grow beyond the default, up to warm_max_b (but never beyond what hides behind the forward kernel)
-	const int cap_b = adb ? std::min(c->warm_max_b, std::max(wl_b, c->warm_len + c->chunk_len)) : wl_b;
+	const int cap_b = wl_b;
 	constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 	const dim3 gridT((unsigned)std::min(c->n_sub, 8 * c->sm_count), NP / COLS); // block rows stride over the sub-chunks
 	const int nblk_b = (c->n_chunks_b + wpb - 1) / wpb;
@@ -979,24 +917,17 @@ static int launch_warm(psmc_b200_ctx *c)
 		run_backward_warm<NP>(c, c->stream2, hot ? c->warm_hot : cap_b, hot);
 		cudaEventRecord(c->ev_join, c->stream2);
 	};
-	if (c->side_order == 1) {
-		run_forward<NP>(c, wl, hot);
-		cudaEventRecord(c->ev[6], st); // forward kernel done (the repair rounds follow)
-		if (c->predict) side_k1f();
-		side_warm();
-	} else {
-		side_warm();
-		run_forward<NP>(c, wl, hot);
-		cudaEventRecord(c->ev[6], st);
-		if (c->predict) side_k1f();
-	}
+	side_warm();
+	run_forward<NP>(c, wl, hot);
+	cudaEventRecord(c->ev[6], st); // forward kernel done (the repair rounds follow)
+	if (c->predict) side_k1f();
 	if (c->predict) {
 		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1);
 		cudaEventRecord(c->ev_k1b, c->stream2);
 		cudaStreamWaitEvent(st, c->ev_k1f, 0);
 	}
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr, adf ? c->d_warm_f : nullptr, c->warm_len, c->d_tight_f);
+		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr);
 		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub, c->d_chunk_sub0, 0);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_forward_repair<NP>(c);
@@ -1009,7 +940,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	c->bsave_cur ^= 1;
 	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
 	for (int r = 0; r < c->repair_rounds; ++r) {
-		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr, adb ? c->d_warm_b : nullptr, cap_b, c->d_tight_b);
+		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr);
 		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
@@ -1019,11 +950,8 @@ static int launch_warm(psmc_b200_ctx *c)
 	LAUNCH((k_reduce), 1 + S_COUNT * c->N, 256, st, c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
 	LAUNCH((k_certify<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
 	LAUNCH((k_certify<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
-	// adaptive overlaps: sort the chunks by their new number of steps for the next E-step (two tiny launches)
-	if (adf) LAUNCH((k_order), (c->n_chunks + 255) / 256, 256, st, c->d_chunks, c->n_chunks, c->d_warm_f, c->warm_len, CH_FIRST, c->d_order_f);
-	if (adb) LAUNCH((k_order), (c->n_chunks_b + 255) / 256, 256, st, c->d_chunks_b, c->n_chunks_b, c->d_warm_b, cap_b, CH_LAST, c->d_order_b);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0) + (adf ? 1 : 0) + (adb ? 1 : 0) + ((prewarm_on<NP>(c) && !hot && !adf) ? 1 : 0) + ((prewarm_on<NP>(c) && !hot && !adb) ? 1 : 0);
+	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0);
 	c->pred_cur ^= 1;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -1357,8 +1285,6 @@ extern "C" int psmc_b200_set_warm(psmc_b200_ctx *c, int32_t warm_len, double eps
 	if (warm_len >= 0) {
 		c->warm_len = warm_len;
 		c->warm_len_bwd = warm_len + warm_len / 3;
-		int rc = reset_overlaps(c);
-		if (rc) return rc;
 	}
 	if (eps > 0) c->cert_eps = eps;
 	return 0;

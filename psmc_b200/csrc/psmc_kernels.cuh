@@ -1004,190 +1004,6 @@ __device__ __forceinline__ double forward_chunk2(const Chunk &ch, bool valid, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP32 pre-warm-up.  An overlap only has to deliver a start vector that is exact to 1e-12 AFTER its last few thousand
-// bins; what happens in its early part is forgotten geometrically.  So the early part runs in FP32 (one SHFL per
-// value instead of two, FFMA at full rate and 4 cycles of latency instead of DFMA at half rate and 9) in its own short
-// kernel, and the FP64 overlap of the forward / backward warm-up kernel starts from its result instead of from the
-// stationary vector.  FP32 leaves a relative error of ~1e-6 in the vector; the FP64 part contracts it like any other
-// start error (the certificate decides, as always).  8-lane groups only (NP <= 64).
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-struct DualScan8T { // DualScan<8> in the scalar type T
-	bool h0, h1, h2;
-	T u0, u1, u2, d0, d1, d2;
-	__device__ __forceinline__ void init(int gl)
-	{
-		h0 = (gl & 1) != 0; h1 = (gl & 2) != 0; h2 = (gl & 4) != 0;
-		u0 = h0 ? T(1) : T(0); u1 = h1 ? T(1) : T(0); u2 = h2 ? T(1) : T(0);
-		d0 = T(1) - u0; d1 = T(1) - u1; d2 = T(1) - u2;
-	}
-	__device__ __forceinline__ void run(T tp, T ts, T &P, T &S) const
-	{
-		const T s0 = h0 ? ts : tp, s1 = h1 ? ts : tp, s2 = h2 ? ts : tp;
-		const T r1 = __shfl_xor_sync(FULLMASK, s0, 1, 8);
-		const T r2 = __shfl_xor_sync(FULLMASK, s1, 2, 8), r3 = __shfl_xor_sync(FULLMASK, s1, 3, 8);
-		const T r4 = __shfl_xor_sync(FULLMASK, s2, 4, 8), r5 = __shfl_xor_sync(FULLMASK, s2, 5, 8);
-		const T r6 = __shfl_xor_sync(FULLMASK, s2, 6, 8), r7 = __shfl_xor_sync(FULLMASK, s2, 7, 8);
-		const T q1 = r2 + r3, q2 = (r4 + r5) + (r6 + r7);
-		P = fma(u2, q2, fma(u1, q1, u0 * r1));
-		S = fma(d2, q2, fma(d1, q1, d0 * r1));
-	}
-};
-template <typename T, int SPL>
-__device__ __forceinline__ void local_prefix_t(const T (&a)[SPL], T (&lp)[SPL], T &tot)
-{
-	T t = T(0);
-	if (SPL == 8) {
-		const T p01 = a[0] + a[1], p23 = a[2] + a[3], p45 = a[4] + a[5], p67 = a[6] + a[7];
-		const T q03 = p01 + p23, q47 = p45 + p67, q05 = q03 + p45;
-		lp[0] = T(0); lp[1] = a[0]; lp[2] = p01; lp[3] = p01 + a[2];
-		lp[4] = q03; lp[5] = q03 + a[4]; lp[6] = q05; lp[7] = q05 + a[6];
-		tot = q03 + q47;
-		return;
-	}
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) {
-		lp[i] = t;
-		t += a[i];
-	}
-	tot = t;
-}
-template <typename T, int SPL>
-__device__ __forceinline__ T local_sum_t(const T (&a)[SPL])
-{
-	T t = T(0);
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) t += a[i];
-	return t;
-}
-template <typename T>
-__device__ __forceinline__ T gsum8_t(T t)
-{
-#pragma unroll
-	for (int d = 4; d > 0; d >>= 1) t += __shfl_xor_sync(FULLMASK, t, d, 8);
-	return t;
-}
-// out[i] = D[i] x[i] + pc[i] * sum_{j<i} pm[j] x[j] + sc[i] * sum_{j>i} sm[j] x[j]  (semisep2 in the scalar type T, 8 lanes)
-template <typename T, int SPL>
-__device__ __forceinline__ void semisep2_t(const T (&x)[SPL], const T (&pm)[SPL], const T (&pc)[SPL], const T (&sm)[SPL],
-                                           const T (&sc)[SPL], const T (&D)[SPL], const DualScan8T<T> &ds, T (&out)[SPL])
-{
-	T a[SPL], c[SPL], r[SPL], lp[SPL], lr[SPL], tp, ts, P, S;
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) {
-		a[i] = x[i] * pm[i];
-		c[i] = x[i] * sm[i];
-		r[SPL - 1 - i] = c[i];
-	}
-	local_prefix_t<T, SPL>(a, lp, tp);
-	local_prefix_t<T, SPL>(r, lr, ts); // suffix sums = prefix sums of the reversed array
-	ds.run(tp, ts, P, S);
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) {
-		T base = D[i] * x[i];
-		if (i > 0) base = fma(pc[i], lp[i], base);
-		if (i < SPL - 1) base = fma(sc[i], lr[SPL - 1 - i], base);
-		out[i] = fma(sc[i], S, fma(pc[i], P, base));
-	}
-}
-
-// DIR 0: for every forward chunk whose FP64 overlap [u0 - warm64, u0) does not reach the start of its sequence, the forward
-//        vector of bin u0 - warm64 - 1 from warm32 bins further left (sum-normalised, as doubles) -> start[c].
-// DIR 1: for every backward chunk whose FP64 overlap (ulast, ulast + warm64] does not reach the end of its sequence, the
-//        direction of b at bin ulast + warm64 from warm32 bins further right -> start[c].
-// Same loop structure as the FP64 warm-up (groups aligned at the end, late starts between 16-bin blocks, boosts).
-template <int SPL, int DIR>
-__global__ void __launch_bounds__(128) k_prewarm(const Chunk *__restrict__ chunks, int n_chunks, const uint32_t *__restrict__ obs,
-                                                 const double *__restrict__ model, int warm64, int warm32, double *__restrict__ start)
-{
-	typedef float T;
-	constexpr int G = 8, NP = SPL * G;
-	const GroupId<G> id(n_chunks);
-	if (!__any_sync(FULLMASK, id.valid)) return;
-	const int c = id.c, gl = id.gl, s0 = gl * SPL;
-	const Chunk ch = chunks[c];
-	T cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], v[SPL];
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) {
-		cU[i] = (T)model[M_U * NP + s0 + i];
-		cV[i] = (T)model[M_V * NP + s0 + i];
-		cW[i] = (T)model[M_W * NP + s0 + i];
-		cZ[i] = (T)model[M_Z * NP + s0 + i];
-		cD[i] = (T)model[M_D * NP + s0 + i];
-		e0[i] = (T)model[M_E0 * NP + s0 + i];
-		v[i] = DIR == 0 ? (T)model[M_A0 * NP + s0 + i] : T(1);
-	}
-	const int ulast = ch.u0 + ch.len - 1;
-	// bins processed: DIR 0: ua .. ub ascending (ub = u0 - warm64 - 1);  DIR 1: ua .. ub descending (ub = ulast + warm64 + 1)
-	bool need;
-	int ua, ub;
-	if (DIR == 0) {
-		need = id.valid && !(ch.flags & CH_FIRST) && ch.u0 - warm64 > 0;
-		ub = ch.u0 - warm64 - 1;
-		ua = max(0, ub - warm32 + 1);
-	} else {
-		need = id.valid && !(ch.flags & CH_LAST) && ulast + warm64 < ch.Lseq - 1;
-		ub = ulast + warm64 + 1;
-		ua = min(ch.Lseq - 1, ub + warm32 - 1);
-	}
-	const int mytrips = need ? (DIR == 0 ? ub - ua + 1 : ua - ub + 1) : 0;
-	const int trips = warp_trips(mytrips);
-	const int mystart = mytrips > 0 ? trips - mytrips : INT_MAX;
-	int tpend = warp_min_i(mystart);
-	const int wlast = (ch.Lseq - 1) >> 4;
-	const int ufirst = DIR == 0 ? ub - trips + 1 : ub + trips - 1; // bin of step 0 (may lie outside the sequence: clamped words)
-	const int uprev = DIR == 0 ? ufirst - 1 : ufirst + 1;          // as if this bin had just been processed
-	uint32_t word = __ldg(obs + ch.ow0 + min(max(uprev >> 4, 0), wlast));
-	uint32_t wnext = __ldg(obs + ch.ow0 + min(max((uprev >> 4) + (DIR == 0 ? 1 : -1), 0), wlast));
-	DualScan8T<T> ds;
-	ds.init(gl);
-	T g[SPL], q = T(1);
-#pragma unroll
-	for (int i = 0; i < SPL; ++i) g[i] = v[i];
-	int t = 0;
-	while (t < trips) {
-		if (t == tpend) { // warp-uniform, rare
-			if (mystart == t) {
-#pragma unroll
-				for (int i = 0; i < SPL; ++i) g[i] = v[i];
-			}
-			tpend = warp_min_i(mystart > t ? mystart : INT_MAX);
-		}
-		const int tstop = min(min(trips, tpend), (t & ~15) + 16);
-		q = (gsum8_t<T>(local_sum_t<T, SPL>(g)) < T(9.094947e-13)) ? T(1.0995116e12) : T(1); // 2^-40 / 2^40
-		for (; t < tstop; ++t) {
-			const int u = DIR == 0 ? ufirst + t : ufirst - t;
-			if ((u & 15) == (DIR == 0 ? 0 : 15)) {
-				word = wnext;
-				wnext = __ldg(obs + ch.ow0 + min(max((u >> 4) + (DIR == 0 ? 1 : -1), 0), wlast));
-			}
-			const int x = (word >> ((u & 15) * 2)) & 3;
-			const T c0 = (x == 0 ? T(0) : T(1)) * q, c1 = (x == 0 ? T(1) : (x == 1 ? T(-1) : T(0))) * q;
-			q = T(1);
-			T out[SPL];
-			if (DIR == 0) {
-				semisep2_t<T, SPL>(g, cW, cZ, cU, cV, cD, ds, out);
-#pragma unroll
-				for (int i = 0; i < SPL; ++i) g[i] = out[i] * fma(c1, e0[i], c0);
-			} else {
-				T h[SPL];
-#pragma unroll
-				for (int i = 0; i < SPL; ++i) h[i] = fma(c1, e0[i], c0) * g[i];
-				semisep2_t<T, SPL>(h, cV, cU, cZ, cW, cD, ds, g);
-			}
-		}
-	}
-	const T tot = gsum8_t<T>(local_sum_t<T, SPL>(g));
-	if (need) {
-		const double inv = 1.0 / (double)tot;
-		double o[SPL];
-#pragma unroll
-		for (int i = 0; i < SPL; ++i) o[i] = fmax((double)g[i] * inv, 1e-300); // (a flushed component restarts positive)
-		store_vec<SPL>(start + (size_t)c * NP + s0, o);
-	}
-}
-
-// ------------------------------------------------------------------------------------------------
 // K3: forward.  One lane group per chunk.
 //   warm == 0 : the exact start vector comes from the boundary chain (vstart, transfer mode).
 //   warm  > 0 : the group starts `warm` bins to the LEFT of its chunk from the stationary vector, runs
@@ -1198,32 +1014,25 @@ template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                  const double *__restrict__ vstart, int warm, int use_prev, double *__restrict__ fhat,
-                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm,
-                                                 const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of,
-                                                 const double *__restrict__ pre_start)
+                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
 	if (!__any_sync(FULLMASK, id.valid)) return;
-	// pre_start: start vectors of the overlaps from the FP32 pre-warm-up (k_prewarm), nullptr = stationary start.
-	// order: chunks sorted by their number of steps, so that the groups of a warp finish together (adaptive overlaps);
-	// warm_of: this chunk's own overlap (nullptr: `warm` for every chunk)
-	const int c = order ? order[id.c] : id.c, gl = id.gl, s0 = gl * SPL;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
 	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
 	M.load(model, s0, NP);
 	double f[SPL];
 	int ubeg = ch.u0;
 	if ((ch.flags & CH_FIRST) || warm > 0) {
-		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - (warm_of ? min(warm_of[c], warm) : warm));
+		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - warm);
 		if (use_prev && ubeg > 0) {
 			// warm start: the vector the PREVIOUS E-step stored for bin ubeg-1 (the parameters moved only a little since;
 			// any positive vector is a legal start -- the certificate decides -- so a stale or concurrently rewritten row is harmless)
 			const double *row = fhat + ((size_t)ch.gb0 - (size_t)(ch.u0 - ubeg) - 1) * NP + s0;
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) f[i] = fmax(row[i], 1e-300);
-		} else if (pre_start && ubeg > 0) {
-			load_vec<SPL>(pre_start + (size_t)c * NP + s0, f);
 		} else {
 #pragma unroll
 			for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
@@ -1235,46 +1044,6 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	if constexpr (VER == 2) ll = forward_chunk2<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	else ll = forward_chunk<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	if (gl == 0 && id.valid) llpart[c] = ll;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Adaptive overlaps.  How many bins of warm-up a boundary needs is a property of the data around it (het-poor,
-// low-TMRCA tracts mix slowly) and varies by an order of magnitude between boundaries; the mismatch the certificate
-// measures anyway tells, per boundary, whether the overlap of this E-step was ample (mismatch at the rounding floor),
-// tight, or too short.  Additive-decrease / multiplicative-increase on that signal: shrink by 1/8 while the mismatch
-// stays at the floor, grow by 1/2 as soon as it leaves the safe band (the boundary still passes at 1e-12, or is
-// repaired).  All on the device, inside the mark kernels of the first repair round; the next E-step reads the new lengths.
-// ------------------------------------------------------------------------------------------------
-// w: the overlap used in this E-step; tight: the longest overlap seen so far whose mismatch was NOT at the floor (memory,
-// so that a boundary approaches its need from above once instead of probing it again and again).
-__device__ __forceinline__ int adapt_overlap(int w, double mismatch, int w_max, int32_t *tight)
-{
-	const int w_min = 1536;
-	int t = *tight;
-	if (!(mismatch <= 2e-14)) { // off the floor (or failed): remember, and keep a safe distance from now on
-		t = max(t, w);
-		*tight = t;
-	}
-	const int floor_w = max(w_min, (t + (t >> 1)) & ~15); // 1.5 x the tightest length seen
-	if (mismatch <= 2e-14) w = max(floor_w, (w - (w >> 4)) & ~15); // 1/16 per E-step: a step multiplies the mismatch by < 10
-	else w = max(floor_w, w);
-	return max(min(w, w_max), 16);
-}
-
-// order[] = chunk indices sorted (stably) by their number of steps, longest first: every thread ranks one chunk
-// (O(n^2 / threads); n is a few thousand).  steps = (overlap unless the chunk starts / ends its sequence) + chunk length.
-__global__ void __launch_bounds__(256) k_order(const Chunk *__restrict__ chunks, int n_chunks, const int32_t *__restrict__ warm_of,
-                                               int warm_cap, int edge_flag, int32_t *__restrict__ order)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_chunks) return;
-	const int ki = ((chunks[i].flags & edge_flag) ? 0 : min(warm_of[i], warm_cap)) + chunks[i].len;
-	int rank = 0;
-	for (int j = 0; j < n_chunks; ++j) {
-		const int kj = ((chunks[j].flags & edge_flag) ? 0 : min(warm_of[j], warm_cap)) + chunks[j].len;
-		rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
-	}
-	order[rank] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1303,7 +1072,7 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ fhat, const double *__restrict__ fwarm,
                                                   int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next, int32_t *__restrict__ warm_of, int warm_max, int32_t *__restrict__ tight)
+                                                  int32_t *__restrict__ pred_next)
 {
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
@@ -1319,7 +1088,6 @@ __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chun
 		flag_f[c] = fl;
 		if (pred_next) pred_next[c] = fl;
 		if (fl) atomicAdd(&stat[0], 1ull);
-		if (warm_of && pred_next && !(ch.flags & CH_FIRST)) warm_of[c] = adapt_overlap(warm_of[c], m, warm_max, tight + c); // first round only
 	}
 }
 
@@ -1647,14 +1415,12 @@ __device__ __forceinline__ void publish_direction(const double (&b)[SPL], double
 template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__ chunks, int n_chunks,
                                                        const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev,
-                                                       const int32_t *__restrict__ order, const int32_t *__restrict__ warm_of,
-                                                       const double *__restrict__ pre_start)
+                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
 	if (!__any_sync(FULLMASK, id.valid)) return;
-	const int c = order ? order[id.c] : id.c, gl = id.gl, s0 = gl * SPL; // (order / warm_of: adaptive overlaps, see k_forward)
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
 	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
 	M.load(model, s0, NP);
@@ -1663,9 +1429,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 	double beta[SPL];
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
-	if (warm_of) warm = min(warm_of[c], warm);
 	int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
-	if (pre_start && !is_last && ulast + warm < ch.Lseq - 1) load_vec<SPL>(pre_start + (size_t)c * NP + s0, beta); // (k_prewarm, same condition)
 	if (bsave_prev && !is_last) {
 		// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin
 		// min(ulast + warm, last bin of the right neighbour) -- see usave in k_backward
@@ -1824,7 +1588,7 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ bwarm, const double *__restrict__ bexact,
                                                   int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next, int32_t *__restrict__ warm_of, int warm_max, int32_t *__restrict__ tight)
+                                                  int32_t *__restrict__ pred_next)
 {
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
@@ -1840,7 +1604,6 @@ __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chun
 		flag_b[c] = fl;
 		if (pred_next) pred_next[c] = fl;
 		if (fl) atomicAdd(&stat[2], 1ull);
-		if (warm_of && pred_next && inner) warm_of[c] = adapt_overlap(warm_of[c], m, warm_max, tight + c); // first round only
 	}
 }
 

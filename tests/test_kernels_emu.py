@@ -167,45 +167,6 @@ def test_emulated_decode_counts_records_as_given(oracle, emu_plain):
             es.decode(mod, 3)
 
 
-def test_emulated_adaptive_overlaps_over_iterations(oracle, emu_plain, monkeypatch):
-    """per-boundary overlaps shrink while the certificate's mismatch stays at the rounding floor and grow when it does not;
-    the chunks are re-sorted by their number of steps after every E-step -- the result must stay exact throughout"""
-    from psmc_b200 import EStep
-    monkeypatch.setenv("PSMC_B200_ADAPT", "1")   # experimental, off by default
-    N = 64
-    m = make_model(oracle, N, seed=41)
-    seqs = _seqs(m, [5000, 1700, 900, 30], seed=42)
-    want = oracle_stats(oracle, m, seqs)
-    with EStep(seqs, N, chunk_len=400) as es:
-        es.set_warm(2500)
-        first = None
-        for it in range(7):
-            got = es.run(_model(m))
-            info = es.info()
-            compare_stats(got, want, TOL, N)
-            assert info["fallbacks"] == 0 and info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
-            first = first or got
-        # different overlaps, different chunk-to-warp assignment: same counts to rounding
-        compare_stats(got, first, 1e-11, N)
-
-
-@pytest.mark.parametrize("N", [23, 64])
-def test_emulated_fp32_prewarm(oracle, emu_plain, monkeypatch, N):
-    """experimental option: the early part of every overlap in FP32 (k_prewarm); the FP64 part and the certificate make
-    the result exact all the same"""
-    from psmc_b200 import EStep
-    monkeypatch.setenv("PSMC_B200_WARM32", "2000")
-    m = make_model(oracle, N, seed=51)
-    seqs = _seqs(m, [7000, 2100, 40], seed=52)
-    want = oracle_stats(oracle, m, seqs)
-    with EStep(seqs, N, chunk_len=800) as es:
-        es.set_warm(1200)
-        got = es.run(_model(m))
-        info = es.info()
-    compare_stats(got, want, TOL, N)
-    assert info["fallbacks"] == 0 and info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
-
-
 @pytest.mark.parametrize("N,mult", [(23, None), (64, None), (64, [2, 0, 1])])
 def test_emulated_dense_counts(oracle, emu_plain, N, mult):
     """option: hmm_expect's dense A[N][N] (khmm.c:305-316) from the spilled backward rows and a tall-skinny product"""
