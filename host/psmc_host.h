@@ -147,6 +147,8 @@ typedef struct {
 	int n_replicates;    /* --replicates R  R bootstrap replicates in this process (implies -b) [0] */
 	int split_len;       /* --split[=T]  apply the splitfa rule with trunk size T bins first [off; 500000] */
 	int slots;           /* --slots K  concurrent replicates per GPU [2] */
+	int batch;           /* --batch B  replicates sharing one launch sequence [0 = as many as fit in device memory; 1 = one at a time (the older scheme)] */
+	int batch_slots;     /* --batch-slots K  batched workers per GPU [1] */
 	int exact_qd;        /* --exact-qd  dense transition counts for hmm_Q0 (khmm.c:336-340): the QD line as the original prints it */
 } psmch_opts_t;
 

@@ -78,6 +78,11 @@ typedef struct {
 	int32_t failed_fwd, repaired_fwd, failed_bwd, repaired_bwd;
 	/* psmc_b200_set_multiplicity: bins of the sequences with multiplicity > 0, and the sum of multiplicities */
 	int64_t active_bins, n_seqs_effective;
+	/* psmc_b200_set_batch: models per E-step (1 otherwise); the backward pass's own chunk plan */
+	int32_t n_models, n_chunks_bwd, chunk_len_bwd;
+	/* repair rounds the next E-step will enqueue (adapts to how deep the repairs cascade), and how many E-steps were
+	 * redone on the fast path with more rounds after a failed certificate (before any exact fallback) */
+	int32_t repair_rounds, warm_redos;
 } psmc_b200_info;
 
 int  psmc_b200_version(void);
@@ -110,6 +115,23 @@ int  psmc_b200_upload_cat(psmc_b200_ctx *ctx, int32_t n_seqs, const int32_t *L, 
  * records only (host-side planning + a few hundred KB of tables; observations and work buffers stay in place).
  * mult == NULL restores multiplicity 1 for every record.  psmc_b200_decode refuses records with multiplicity 0. */
 int  psmc_b200_set_multiplicity(psmc_b200_ctx *ctx, const int32_t *mult);
+
+/* Batch mode: n_rep independent EM runs (bootstrap replicates, aux.c:8-47 / README:57-62) share ONE launch sequence.
+ * Model r runs over the multiset mult[r*n_seqs + i] of the resident records (NULL = every record once in every model).
+ * The drawn records of all models become the work items of the chunk plans: with a few hundred records per launch
+ * the chunks are long, so the warm-up overlaps, the certificate and the repairs that a single genome's 22 contigs
+ * need shrink to a few percent of the work.  The forward spill is reallocated to hold the
+ * drawn records of all models (psmc_b200_mem_info tells what fits); on failure the context stays usable in single mode.
+ * psmc_b200_estep_batch* take/return n_rep models/statistics; model r's statistics include the HMM_TINY terms of ITS
+ * drawn records.  psmc_b200_set_multiplicity (or set_batch with n_rep = 1) returns to single mode.  No decode and no
+ * dense counts in batch mode.  A model's result does not depend on what else is in the batch when chunk_len is fixed
+ * (same bits); with the automatic plan it agrees to the certificate's tolerance. */
+int  psmc_b200_set_batch(psmc_b200_ctx *ctx, int32_t n_rep, const int32_t *mult);
+int  psmc_b200_estep_batch(psmc_b200_ctx *ctx, int32_t n_rep, const psmc_b200_model *models, psmc_b200_stats *outs);
+int  psmc_b200_estep_batch_launch(psmc_b200_ctx *ctx, int32_t n_rep, const psmc_b200_model *models);
+int  psmc_b200_estep_batch_finish(psmc_b200_ctx *ctx, int32_t n_rep, psmc_b200_stats *outs);
+/* free / total device memory in bytes (cudaMemGetInfo), to size a batch: a model needs 8*(NP+1) bytes per drawn bin */
+int  psmc_b200_mem_info(int32_t device, int64_t *free_bytes, int64_t *total_bytes);
 
 /* One E-step: forward, backward, log-likelihood and expected counts over every sequence.
  * Replaces em.c:33-55 (hmm_pre_backward + the loop over hmm_forward / hmm_backward / hmm_lk /

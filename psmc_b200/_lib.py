@@ -36,7 +36,9 @@ class CInfo(C.Structure):
                 ("ms", C.c_float * 8), ("launches", C.c_int32),
                 ("warm_len", C.c_int32), ("fallbacks", C.c_int32), ("fwd_mismatch", C.c_double), ("bwd_mismatch", C.c_double),
                 ("failed_fwd", C.c_int32), ("repaired_fwd", C.c_int32), ("failed_bwd", C.c_int32), ("repaired_bwd", C.c_int32),
-                ("active_bins", C.c_int64), ("n_seqs_effective", C.c_int64)]
+                ("active_bins", C.c_int64), ("n_seqs_effective", C.c_int64),
+                ("n_models", C.c_int32), ("n_chunks_bwd", C.c_int32), ("chunk_len_bwd", C.c_int32),
+                ("repair_rounds", C.c_int32), ("warm_redos", C.c_int32)]
 
 
 # every symbol include/psmc_b200.h declares: name -> (restype, argtypes)
@@ -50,6 +52,11 @@ SYMBOLS = {
     "psmc_b200_upload": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.POINTER(C.c_void_p)]),
     "psmc_b200_upload_cat": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.c_void_p]),
     "psmc_b200_set_multiplicity": (C.c_int, [C.c_void_p, _ip]),
+    "psmc_b200_set_batch": (C.c_int, [C.c_void_p, C.c_int32, _ip]),
+    "psmc_b200_estep_batch": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(CModel), C.POINTER(CStats)]),
+    "psmc_b200_estep_batch_launch": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(CModel)]),
+    "psmc_b200_estep_batch_finish": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(CStats)]),
+    "psmc_b200_mem_info": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "psmc_b200_estep": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.POINTER(CStats)]),
     "psmc_b200_estep_dense": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_double, C.POINTER(CStats)]),
     "psmc_b200_factorize": (C.c_int, [C.c_int32, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp]),

@@ -141,6 +141,13 @@ struct psmc_b200_ctx {
 	double cert_eps = 1e-12;
 	bool mode_warm = false, certified = true;
 	int fallbacks = 0, repair_rounds = 3;
+	// Repairs cascade: a round fixes the runs of boundaries that failed at its start, which can move the boundary BEHIND each
+	// run (its left vector changed).  With chunks much shorter than the overlap (small inputs, many GPUs) a slow tract
+	// needs many rounds.  rounds_cur adapts: two more than the deepest round of the last E-step that still saw a failure; if
+	// the certificate fails, the E-step is first redone on the fast path with rounds_max rounds, then with exact operators.
+	int rounds_cur = 3, rounds_max = 48, warm_redos = 0;
+	bool rounds_fixed = false; // PSMC_B200_REPAIR_ROUNDS given
+	bool redoing = false;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
 	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
@@ -176,6 +183,18 @@ struct psmc_b200_ctx {
 	int chunk_len_req = 0;           // chunk length the caller / environment asked for (0 = one resident wave)
 	int sm_count = 0;
 	double *d_cw = nullptr, *d_cw_b = nullptr; // per-chunk multiplicity, forward / backward plan
+	// Batch mode (psmc_b200_set_batch): n_rep models side by side in ONE launch sequence -- bootstrap replicates, each a
+	// multiset of the resident records under its own model.  A "virtual sequence" is a (model, record) pair; the chunk
+	// plans cover the virtual sequences, chunks carry their model index, k_reduce sums per model.
+	int n_rep = 1;
+	bool batch = false;
+	std::vector<int32_t> bmult;          // batch mode: n_rep x n_seqs multiplicities (kept-record index)
+	std::vector<int64_t> rep_seq_eff;    // per model: sum of multiplicities (HMM_TINY terms)
+	std::vector<int32_t> rep_c0, rep_c0_b; // per model: first chunk in the forward / backward plan (n_rep + 1 entries)
+	int32_t *d_rep_c0 = nullptr, *d_rep_c0_b = nullptr;
+	int n_vseq = 0, cap_vseq = 0, cap_rep = 0;
+	int64_t cap_bins = 0;                // rows allocated in fhat / sc (/ ghat)
+	int cap_models = 0;                  // models d_model / h_model / d_stats / h_stats can hold
 	// Slow-mixing boundaries are a property of the data (het-poor, low-TMRCA tracts): the chunks that needed a repair in
 	// one E-step almost always need it in the next.  Their transfer operators depend on model + observations only, so they
 	// are computed AHEAD of time on the side stream, hidden behind the forward kernel (d_pred*: round-1 failures of the
@@ -219,11 +238,11 @@ static void free_plan(psmc_b200_ctx *c)
 	              (void **)&c->d_chunk_sub0, (void **)&c->d_Tsub, (void **)&c->d_Texsub, (void **)&c->d_vsub, (void **)&c->d_bsub,
 	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b,
 	              (void **)&c->d_pred[0], (void **)&c->d_pred[1], (void **)&c->d_pred_b[0], (void **)&c->d_pred_b[1],
-	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b};
+	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b, (void **)&c->d_seq_c0, (void **)&c->d_seq_nc, (void **)&c->d_rep_c0, (void **)&c->d_rep_c0_b};
 	for (auto q : p) { cudaFree(*q); *q = nullptr; }
 	c->bytes_total -= c->bytes_plan;
 	c->bytes_plan = 0;
-	c->cap_chunks = c->cap_chunks_b = c->cap_sub = c->cap_sub_b = c->cap_k1 = 0;
+	c->cap_chunks = c->cap_chunks_b = c->cap_sub = c->cap_sub_b = c->cap_k1 = c->cap_vseq = c->cap_rep = 0;
 }
 
 static void free_ctx(psmc_b200_ctx *c)
@@ -231,7 +250,7 @@ static void free_ctx(psmc_b200_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	free_plan(c);
-	cudaFree(c->d_obs); cudaFree(c->d_seq_c0); cudaFree(c->d_seq_nc);
+	cudaFree(c->d_obs);
 	cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_cert);
 	if (c->h_cert) cudaFreeHost(c->h_cert);
 	cudaFree(c->d_stats);
@@ -317,16 +336,31 @@ static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 
 // (Re)build both chunk plans over the sequences with multiplicity > 0 and upload them.  The packed observations,
 // the forward spill (indexed by bin) and everything else that does not depend on the plan stay where they are.
+struct VSeq { int32_t seq, rep, mult; int64_t gb0; };
+
 static int replan(psmc_b200_ctx *c)
 {
 	const int NP = c->NP;
+	// virtual sequences: single mode = every resident record once (records with multiplicity 0 keep their rows in the
+	// forward spill and get no chunks); batch mode = the drawn records of every model, rows packed densely
+	std::vector<VSeq> vs;
 	c->active_bins = 0; c->n_seq_eff = 0; c->weighted = false;
+	c->rep_seq_eff.assign((size_t)c->n_rep, 0);
 	int n_active = 0;
-	for (int i = 0; i < c->n_seqs; ++i) {
-		if (c->mult[i] > 0) { c->active_bins += c->L[i]; ++n_active; }
-		if (c->mult[i] != 1) c->weighted = true;
-		c->n_seq_eff += c->mult[i];
-	}
+	int64_t rows = 0;
+	for (int r = 0; r < c->n_rep; ++r)
+		for (int i = 0; i < c->n_seqs; ++i) {
+			const int32_t m = c->batch ? c->bmult[(size_t)r * c->n_seqs + i] : c->mult[i];
+			if (m > 0) { c->active_bins += c->L[i]; ++n_active; }
+			if (m != 1) c->weighted = true;
+			c->rep_seq_eff[r] += m;
+			if (c->batch && m == 0) continue;
+			vs.push_back({i, r, m, rows});
+			rows += c->L[i];
+		}
+	c->n_seq_eff = c->rep_seq_eff[0];
+	c->n_vseq = (int)vs.size();
+	c->seq_c0.assign((size_t)std::max(c->n_vseq, 1), 0); c->seq_nc.assign((size_t)std::max(c->n_vseq, 1), 0); c->seq_gb0.assign((size_t)std::max(c->n_vseq, 1), 0);
 	// The chunk kernels are latency-bound and every block lives as long as the kernel, so a plan must fit in ONE
 	// resident wave of its kernel (one block too many doubles the kernel time; more chunks only add warm-up work).
 	int chunk_len = c->chunk_len_req, chunk_len_b = c->chunk_len_req;
@@ -346,33 +380,36 @@ static int replan(psmc_b200_ctx *c)
 	std::vector<int32_t> k1;
 	std::vector<double> cw, cw_b;
 	auto build_plan = [&](int clen, bool is_main, std::vector<Chunk> &chunks, std::vector<Chunk> &subs,
-	                      std::vector<int32_t> &sub_parent, std::vector<int32_t> &chunk_sub0, std::vector<double> &w) {
-		int64_t gb = 0;
-		for (int i = 0; i < c->n_seqs; ++i) {
-			const int Li = c->L[i];
-			const int nc = c->mult[i] > 0 ? (Li + clen - 1) / clen : 0;
+	                      std::vector<int32_t> &sub_parent, std::vector<int32_t> &chunk_sub0, std::vector<double> &w, std::vector<int32_t> &rep_c0) {
+		rep_c0.assign((size_t)c->n_rep + 1, 0);
+		int next_rep = 0;
+		for (int v = 0; v < c->n_vseq; ++v) {
+			const int i = vs[v].seq, Li = c->L[i];
+			const int nc = vs[v].mult > 0 ? (Li + clen - 1) / clen : 0;
+			const int64_t gb = vs[v].gb0;
+			while (next_rep <= vs[v].rep) rep_c0[next_rep++] = (int32_t)chunks.size();
 			if (is_main) {
-				c->seq_c0[i] = (int)chunks.size();
-				c->seq_nc[i] = nc;
-				c->seq_gb0[i] = gb;
+				c->seq_c0[v] = (int)chunks.size();
+				c->seq_nc[v] = nc;
+				c->seq_gb0[v] = gb;
 			}
 			for (int k = 0; k < nc; ++k) {
 				Chunk ch;
 				const int64_t a = (int64_t)Li * k / nc, b = (int64_t)Li * (k + 1) / nc;
-				ch.seq = i;
+				ch.seq = v;
 				ch.flags = (k == 0 ? CH_FIRST : 0) | (k == nc - 1 ? CH_LAST : 0);
 				ch.u0 = (int)a;
 				ch.len = (int)(b - a);
 				ch.gb0 = gb + a;
 				ch.ow0 = c->seq_ow0[i];
 				ch.Lseq = Li;
-				ch.pad_ = 0;
+				ch.rep = vs[v].rep;
 				if (is_main && nc > 1) k1.push_back((int)chunks.size());
 				chunks.push_back(ch);
-				w.push_back((double)c->mult[i]);
+				w.push_back((double)vs[v].mult);
 			}
-			gb += Li;
 		}
+		while (next_rep <= c->n_rep) rep_c0[next_rep++] = (int32_t)chunks.size();
 		// sub-chunks (repair granularity): every chunk split into equal pieces of about sub_len bins
 		chunk_sub0.assign(chunks.size() + 1, 0);
 		for (size_t ci = 0; ci < chunks.size(); ++ci) {
@@ -395,8 +432,8 @@ static int replan(psmc_b200_ctx *c)
 	std::vector<Chunk> subs, chunks_b, subs_b;
 	std::vector<int32_t> sub_parent, chunk_sub0, sub_parent_b, chunk_sub0_b;
 	c->chunks.clear();
-	build_plan(chunk_len, true, c->chunks, subs, sub_parent, chunk_sub0, cw);
-	build_plan(chunk_len_b, false, chunks_b, subs_b, sub_parent_b, chunk_sub0_b, cw_b);
+	build_plan(chunk_len, true, c->chunks, subs, sub_parent, chunk_sub0, cw, c->rep_c0);
+	build_plan(chunk_len_b, false, chunks_b, subs_b, sub_parent_b, chunk_sub0_b, cw_b, c->rep_c0_b);
 	c->n_chunks = (int)c->chunks.size();
 	c->n_sub = (int)subs.size();
 	c->n_chunks_b = (int)chunks_b.size();
@@ -404,11 +441,35 @@ static int replan(psmc_b200_ctx *c)
 	c->n_k1 = (int)k1.size();
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream2), PSMC_B200_ECUDA);
-	if (!c->d_chunks || c->n_chunks > c->cap_chunks || c->n_chunks_b > c->cap_chunks_b || c->n_sub > c->cap_sub || c->n_sub_b > c->cap_sub_b || c->n_k1 > c->cap_k1) {
+	// forward spill: rows of every virtual sequence (grow-only; single mode needs total_bins rows, a batch the drawn records of all its models)
+	if (rows > c->cap_bins) {
+		cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_ghat);
+		c->d_fhat = nullptr; c->d_sc = nullptr; c->d_ghat = nullptr;
+		c->bytes_total -= c->bytes_forward;
+		c->bytes_forward = 0; c->cap_bins = 0;
+		// (batch mode: 1/8 head room, so that the next batch of the same size -- whose draws differ -- reuses the allocation)
+		const size_t need = (size_t)std::max<int64_t>(c->batch ? rows + rows / 8 : rows, 1);
+		cudaError_t e1 = cudaMalloc((void **)&c->d_fhat, need * NP * sizeof(double));
+		cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void **)&c->d_sc, need * sizeof(double)) : e1;
+		cudaError_t e3 = (e2 == cudaSuccess && c->dense) ? cudaMalloc((void **)&c->d_ghat, need * NP * sizeof(double)) : e2;
+		if (e3 != cudaSuccess) {
+			cudaFree(c->d_fhat); cudaFree(c->d_sc); c->d_fhat = nullptr; c->d_sc = nullptr;
+			cudaGetLastError();
+			return set_err(PSMC_B200_ECUDA, "cudaMalloc of the forward spill (%lld bins x %d states) failed: %s", (long long)rows, NP, cudaGetErrorString(e3));
+		}
+		if (c->dense) cudaMemsetAsync(c->d_ghat, 0, need * NP * sizeof(double), c->stream);
+		c->cap_bins = (int64_t)need;
+		c->bytes_forward = (int64_t)need * NP * 8 * (c->dense ? 2 : 1) + (int64_t)need * 8;
+		c->bytes_total += c->bytes_forward;
+		c->dense_valid = false;
+	}
+	if (!c->d_chunks || c->n_chunks > c->cap_chunks || c->n_chunks_b > c->cap_chunks_b || c->n_sub > c->cap_sub || c->n_sub_b > c->cap_sub_b || c->n_k1 > c->cap_k1 ||
+	    c->n_vseq > c->cap_vseq || c->n_rep > c->cap_rep) {
 		// grow-only, with head room: a replicate never needs much more than the all-sequences plan
 		free_plan(c);
 		auto room = [](int n) { return n + n / 8 + 16; };
 		const int cc = room(c->n_chunks), cb = room(c->n_chunks_b), cs = room(c->n_sub), csb = room(c->n_sub_b), ck = room(c->n_k1);
+		const int cv = room(c->n_vseq), cr = room(c->n_rep);
 		bool ok = true;
 		auto alloc = [&](void **ptr, size_t bytes) {
 			if (!ok) return;
@@ -454,9 +515,13 @@ static int replan(psmc_b200_ctx *c)
 		alloc((void **)&c->d_partsub, sizeof(double) * (size_t)csb * S_COUNT * NP);
 		alloc((void **)&c->d_cw, sizeof(double) * (size_t)cc);
 		alloc((void **)&c->d_cw_b, sizeof(double) * (size_t)cb);
+		alloc((void **)&c->d_seq_c0, sizeof(int32_t) * (size_t)cv);
+		alloc((void **)&c->d_seq_nc, sizeof(int32_t) * (size_t)cv);
+		alloc((void **)&c->d_rep_c0, sizeof(int32_t) * (size_t)(cr + 1));
+		alloc((void **)&c->d_rep_c0_b, sizeof(int32_t) * (size_t)(cr + 1));
 		c->bytes_total += c->bytes_plan;
 		if (!ok) { free_plan(c); return PSMC_B200_ECUDA; }
-		c->cap_chunks = cc; c->cap_chunks_b = cb; c->cap_sub = cs; c->cap_sub_b = csb; c->cap_k1 = ck;
+		c->cap_chunks = cc; c->cap_chunks_b = cb; c->cap_sub = cs; c->cap_sub_b = csb; c->cap_k1 = ck; c->cap_vseq = cv; c->cap_rep = cr;
 	}
 	c->bytes_transfer = (int64_t)c->n_chunks * NP * NP * 8;
 	cudaStream_t st = c->stream;
@@ -468,7 +533,7 @@ static int replan(psmc_b200_ctx *c)
 	UP(c->d_chunks, c->chunks); UP(c->d_sub, subs); UP(c->d_sub_parent, sub_parent); UP(c->d_chunk_sub0, chunk_sub0);
 	UP(c->d_chunks_b, chunks_b); UP(c->d_sub_b, subs_b); UP(c->d_sub_parent_b, sub_parent_b); UP(c->d_chunk_sub0_b, chunk_sub0_b);
 	UP(c->d_k1, k1); UP(c->d_cw, cw); UP(c->d_cw_b, cw_b);
-	UP(c->d_seq_c0, c->seq_c0); UP(c->d_seq_nc, c->seq_nc);
+	UP(c->d_seq_c0, c->seq_c0); UP(c->d_seq_nc, c->seq_nc); UP(c->d_rep_c0, c->rep_c0); UP(c->d_rep_c0_b, c->rep_c0_b);
 #undef UP
 	CUDA_TRY(cudaMemsetAsync(c->d_flag_b, 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaMemsetAsync(c->d_flag, 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), st), PSMC_B200_ECUDA);
@@ -483,6 +548,25 @@ static int replan(psmc_b200_ctx *c)
 	c->fwd_valid = false;
 	c->launched = false;
 	++c->replans;
+	return 0;
+}
+
+// model blocks and statistics vectors for n models (device + pinned staging), grow-only
+static int ensure_models(psmc_b200_ctx *c, int n)
+{
+	if (n <= c->cap_models) return 0;
+	const size_t mb = sizeof(double) * M_COUNT * c->NP * (size_t)n, sb = sizeof(double) * (size_t)(S_COUNT * c->N + 1) * (size_t)n;
+	if (c->stream) CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	cudaFree(c->d_model); cudaFree(c->d_stats);
+	if (c->h_model) cudaFreeHost(c->h_model);
+	if (c->h_stats) cudaFreeHost(c->h_stats);
+	c->d_model = c->d_stats = c->h_model = c->h_stats = nullptr;
+	c->cap_models = 0;
+	CUDA_TRY(cudaMalloc((void **)&c->d_model, mb), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMalloc((void **)&c->d_stats, sb), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMallocHost((void **)&c->h_model, mb), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaMallocHost((void **)&c->h_stats, sb), PSMC_B200_ECUDA);
+	c->cap_models = n;
 	return 0;
 }
 
@@ -567,7 +651,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		env = getenv("PSMC_B200_WARM_HOT");
 		if (env && atoi(env) >= 0) c->warm_hot = atoi(env);
 		env = getenv("PSMC_B200_REPAIR_ROUNDS");
-		if (env && atoi(env) >= 0) c->repair_rounds = atoi(env);
+		if (env && atoi(env) >= 0) { c->repair_rounds = atoi(env); c->rounds_fixed = true; }
+		c->rounds_cur = c->repair_rounds;
 		env = getenv("PSMC_B200_CERT_EPS");
 		if (env && atof(env) > 0) c->cert_eps = atof(env);
 		env = getenv("PSMC_B200_SUB_LEN");
@@ -583,8 +668,6 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		words += (w + 31) / 32 * 32;
 	}
 	c->words_obs = std::max<int64_t>(words, 32);
-	c->seq_c0.resize(c->n_seqs); c->seq_nc.resize(c->n_seqs); c->seq_gb0.resize(c->n_seqs);
-	const int NP = c->NP;
 #define ALLOC(ptr, bytes)                                                                         \
 	do {                                                                                          \
 		size_t b_ = (size_t)(bytes);                                                              \
@@ -598,15 +681,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		c->bytes_total += (int64_t)b_;                                                            \
 	} while (0)
 	c->bytes_obs = c->words_obs * 4;
-	c->bytes_forward = c->total_bins * NP * 8 + c->total_bins * 8;
 	ALLOC(c->d_obs, c->bytes_obs);
-	ALLOC(c->d_seq_c0, sizeof(int32_t) * (size_t)c->n_seqs);
-	ALLOC(c->d_seq_nc, sizeof(int32_t) * (size_t)c->n_seqs);
-	ALLOC(c->d_model, sizeof(double) * M_COUNT * NP);
-	ALLOC(c->d_fhat, (size_t)c->total_bins * NP * 8);
-	ALLOC(c->d_sc, (size_t)c->total_bins * 8);
-	ALLOC(c->d_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1));
-	ALLOC(c->d_cert, sizeof(unsigned long long) * 8);
+	ALLOC(c->d_cert, sizeof(unsigned long long) * 16);
 #undef ALLOC
 #define CTRY(call)                                                                                \
 	do {                                                                                          \
@@ -628,16 +704,15 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		if (env && atoi(env) == 0) c->predict = false;
 	}
 	for (int i = 0; i < 8; ++i) CTRY(cudaEventCreate(&c->ev[i]));
-	CTRY(cudaMallocHost((void **)&c->h_model, sizeof(double) * M_COUNT * NP));
-	CTRY(cudaMallocHost((void **)&c->h_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1)));
-	CTRY(cudaMallocHost((void **)&c->h_cert, sizeof(unsigned long long) * 8));
+	CTRY(cudaMallocHost((void **)&c->h_cert, sizeof(unsigned long long) * 16));
 	CTRY(cudaMallocHost((void **)&c->h_obs, (size_t)c->bytes_obs));
 	pack_all(c, sp.data());
 	CTRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
 	CTRY(cudaStreamSynchronize(c->stream));
 #undef CTRY
 	{
-		int rc = replan(c);
+		int rc = ensure_models(c, 1);
+		if (rc == 0) rc = replan(c);
 		if (rc != 0) { free_ctx(c); return rc; }
 	}
 	*out = c;
@@ -654,10 +729,53 @@ extern "C" int psmc_b200_set_multiplicity(psmc_b200_ctx *c, const int32_t *mult)
 			if (mult[i] < 0) return set_err(PSMC_B200_EINVAL, "negative multiplicity");
 			if (c->kept_of[i] >= 0) m[c->kept_of[i]] = mult[i];
 		}
-	if (m == c->mult) return 0;
+	if (m == c->mult && !c->batch) return 0;
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
 	c->mult.swap(m);
+	c->batch = false;
+	c->n_rep = 1;
+	c->bmult.clear();
 	return replan(c);
+}
+
+// Batch mode: n_rep models side by side, model r over the multiset mult[r * n_seqs + i] of the resident records.
+extern "C" int psmc_b200_set_batch(psmc_b200_ctx *c, int32_t n_rep, const int32_t *mult)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (n_rep < 1 || n_rep > 4096) return set_err(PSMC_B200_EINVAL, "n_rep=%d out of range (1..4096)", n_rep);
+	if (c->dense) return set_err(PSMC_B200_EINVAL, "batch mode and dense counts (psmc_b200_set_dense) exclude each other");
+	std::vector<int32_t> m((size_t)n_rep * std::max(c->n_seqs, 1), 1);
+	if (mult)
+		for (int r = 0; r < n_rep; ++r)
+			for (int i = 0; i < c->n_seqs_given; ++i) {
+				const int32_t v = mult[(size_t)r * c->n_seqs_given + i];
+				if (v < 0) return set_err(PSMC_B200_EINVAL, "negative multiplicity");
+				if (c->kept_of[i] >= 0) m[(size_t)r * c->n_seqs + c->kept_of[i]] = v;
+			}
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	int rc = ensure_models(c, n_rep);
+	if (rc) return rc;
+	c->bmult.swap(m);
+	c->batch = true;
+	c->n_rep = n_rep;
+	rc = replan(c);
+	if (rc) { // (typically: the forward spill of so many models does not fit) -- back to single mode, still usable
+		c->batch = false; c->n_rep = 1; c->bmult.clear();
+		char keep[512];
+		snprintf(keep, sizeof(keep), "%s", g_err);
+		if (replan(c) == 0) set_err(rc, "%s", keep);
+	}
+	return rc;
+}
+
+extern "C" int psmc_b200_mem_info(int32_t device, int64_t *free_bytes, int64_t *total_bytes)
+{
+	size_t f = 0, t = 0;
+	CUDA_TRY(cudaSetDevice(device), PSMC_B200_ENODEV);
+	CUDA_TRY(cudaMemGetInfo(&f, &t), PSMC_B200_ECUDA);
+	if (free_bytes) *free_bytes = (int64_t)f;
+	if (total_bytes) *total_bytes = (int64_t)t;
+	return 0;
 }
 
 extern "C" int psmc_b200_create_cat(psmc_b200_ctx **out, int32_t n_seqs, const int32_t *L, const signed char *seqs_cat,
@@ -716,10 +834,10 @@ static int check_model(const psmc_b200_ctx *c, const psmc_b200_model *m)
 	return 0;
 }
 
-static void stage_model(psmc_b200_ctx *c, const psmc_b200_model *m)
+static void stage_model(psmc_b200_ctx *c, const psmc_b200_model *m, int r = 0)
 {
 	const int N = c->N, NP = c->NP;
-	double *h = c->h_model;
+	double *h = c->h_model + (size_t)r * M_COUNT * NP;
 	memset(h, 0, sizeof(double) * M_COUNT * NP);
 	for (int k = 0; k < N; ++k) {
 		h[M_A0 * NP + k] = m->a0[k];
@@ -855,7 +973,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	}
 	cudaEventRecord(c->ev[1], st);
 	if (c->n_k1 > 0) {
-		LAUNCH((k_chain<NP>), 2 * c->n_seqs, NP, st, c->d_seq_c0, c->d_seq_nc, c->d_T, c->d_Tex, c->d_model, c->d_vstart, c->d_bend, c->n_seqs);
+		LAUNCH((k_chain<NP>), 2 * c->n_vseq, NP, st, c->d_chunks, c->d_seq_c0, c->d_seq_nc, c->d_T, c->d_Tex, c->d_model, c->d_vstart, c->d_bend, c->n_vseq);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[2], st);
@@ -870,7 +988,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 			++c->launches;
 		}
 		cudaEventRecord(c->ev[4], st);
-		LAUNCH((k_reduce), 1 + S_COUNT * c->N, 256, st, c->d_part, c->d_llpart, c->n_chunks, c->n_chunks, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw : nullptr);
+		LAUNCH((k_reduce), dim3(1 + S_COUNT * c->N, c->n_rep), 256, st, c->d_part, c->d_llpart, c->d_rep_c0, c->d_rep_c0, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw : nullptr);
 		++c->launches;
 		cudaEventRecord(c->ev[5], st);
 	}
@@ -888,7 +1006,11 @@ static int launch_warm(psmc_b200_ctx *c)
 {
 	constexpr int NP = 32 * SPL;
 	cudaStream_t st = c->stream;
-	cudaMemsetAsync(c->d_cert, 0, sizeof(unsigned long long) * 8, st);
+	cudaMemsetAsync(c->d_cert, 0, sizeof(unsigned long long) * 16, st);
+	const int rounds = c->rounds_cur;
+	// reach of a cascade front in chunks (see k_mark_fwd): overlap / chunk length, at least one chunk
+	const int spread_f = std::min(16, std::max(1, (c->warm_len + c->chunk_len - 1) / std::max(c->chunk_len, 1)));
+	const int spread_b = std::min(16, std::max(1, (c->warm_len_bwd + c->chunk_len_b - 1) / std::max(c->chunk_len_b, 1)));
 	cudaEventRecord(c->ev[0], st);
 	cudaEventRecord(c->ev[1], st);
 	cudaEventRecord(c->ev[2], st);
@@ -926,8 +1048,8 @@ static int launch_warm(psmc_b200_ctx *c)
 		cudaEventRecord(c->ev_k1b, c->stream2);
 		cudaStreamWaitEvent(st, c->ev_k1f, 0);
 	}
-	for (int r = 0; r < c->repair_rounds; ++r) {
-		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr);
+	for (int r = 0; r < rounds; ++r) {
+		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr, c->d_cert + 8, r == 0 ? 0 : spread_f, r);
 		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub, c->d_chunk_sub0, 0);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_forward_repair<NP>(c);
@@ -939,19 +1061,19 @@ static int launch_warm(psmc_b200_ctx *c)
 	cudaEventRecord(c->ev[7], st); // backward kernel done
 	c->bsave_cur ^= 1;
 	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
-	for (int r = 0; r < c->repair_rounds; ++r) {
-		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr);
+	for (int r = 0; r < rounds; ++r) {
+		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr, c->d_cert + 9, r == 0 ? 0 : spread_b, r);
 		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1);
 		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
 		run_backward_repair<NP>(c);
 		LAUNCH((k_fold), c->n_chunks_b, 128, st, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
 	}
 	cudaEventRecord(c->ev[4], st);
-	LAUNCH((k_reduce), 1 + S_COUNT * c->N, 256, st, c->d_part, c->d_llpart, c->n_chunks, c->n_chunks_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
+	LAUNCH((k_reduce), dim3(1 + S_COUNT * c->N, c->n_rep), 256, st, c->d_part, c->d_llpart, c->d_rep_c0, c->d_rep_c0_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
 	LAUNCH((k_certify<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
 	LAUNCH((k_certify<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 6 + 10 * c->repair_rounds + (c->predict ? 2 : 0);
+	c->launches = 6 + 10 * rounds + (c->predict ? 2 : 0);
 	c->pred_cur ^= 1;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -981,20 +1103,35 @@ static int launch_dispatch(psmc_b200_ctx *c, bool with_counts)
 	return set_err(PSMC_B200_EINVAL, "internal: bad SPL");
 }
 
-extern "C" int psmc_b200_estep_launch(psmc_b200_ctx *c, const psmc_b200_model *model)
+static int launch_models(psmc_b200_ctx *c, int n_rep, const psmc_b200_model *models)
 {
 	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
-	int rc = check_model(c, model);
-	if (rc) return rc;
+	if (n_rep != c->n_rep) return set_err(PSMC_B200_EINVAL, "%d model(s) given, the context is set up for %d (psmc_b200_set_batch)", n_rep, c->n_rep);
+	if (!models) return set_err(PSMC_B200_EINVAL, "models is NULL");
+	for (int r = 0; r < n_rep; ++r) {
+		int rc = check_model(c, models + r);
+		if (rc) return rc;
+	}
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA); // pinned staging buffer is reused
-	stage_model(c, model);
-	CUDA_TRY(cudaMemcpyAsync(c->d_model, c->h_model, sizeof(double) * M_COUNT * c->NP, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
-	rc = launch_dispatch(c, true);
+	for (int r = 0; r < n_rep; ++r) stage_model(c, models + r, r);
+	CUDA_TRY(cudaMemcpyAsync(c->d_model, c->h_model, sizeof(double) * M_COUNT * c->NP * (size_t)n_rep, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	int rc = launch_dispatch(c, true);
 	if (rc) return rc;
 	c->launched = true;
 	c->dense_valid = c->dense;
 	return 0;
+}
+
+extern "C" int psmc_b200_estep_launch(psmc_b200_ctx *c, const psmc_b200_model *model)
+{
+	if (c && c->batch) return set_err(PSMC_B200_EINVAL, "the context is in batch mode: use psmc_b200_estep_batch* (or psmc_b200_set_multiplicity to leave it)");
+	return launch_models(c, 1, model);
+}
+
+extern "C" int psmc_b200_estep_batch_launch(psmc_b200_ctx *c, int32_t n_rep, const psmc_b200_model *models)
+{
+	return launch_models(c, n_rep, models);
 }
 
 extern "C" void *psmc_b200_device_stats(psmc_b200_ctx *c) { return c ? (void *)c->d_stats : nullptr; }
@@ -1025,7 +1162,7 @@ static void collect_times(psmc_b200_ctx *c, bool with_counts)
 static int sync_and_certify(psmc_b200_ctx *c)
 {
 	const bool need = c->mode_warm && !c->certified;
-	if (need) CUDA_TRY(cudaMemcpyAsync(c->h_cert, c->d_cert, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	if (need) CUDA_TRY(cudaMemcpyAsync(c->h_cert, c->d_cert, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	if (need) {
 		c->certified = true;
@@ -1034,7 +1171,22 @@ static int sync_and_certify(psmc_b200_ctx *c)
 		memcpy(&c->mis_b, &bb, sizeof(double));
 		c->rep_fwd_fail = (long long)c->h_cert[4]; c->rep_fwd_chunks = (long long)c->h_cert[5];
 		c->rep_bwd_fail = (long long)c->h_cert[6]; c->rep_bwd_chunks = (long long)c->h_cert[7];
-		if (c->h_cert[0] > 0) {
+		const bool cert_failed = c->h_cert[0] > 0;
+		if (!c->rounds_fixed) { // the next E-step enqueues two rounds more than the deepest round that still saw a failure
+			const int deepest = (int)std::max(c->h_cert[8], c->h_cert[9]);
+			c->rounds_cur = std::min(c->rounds_max, std::max(c->repair_rounds, deepest + 2));
+		}
+		if (cert_failed && !c->redoing && !c->rounds_fixed && c->repair_rounds > 0) {
+			// the cascade was deeper than the rounds enqueued: once more on the fast path with as many rounds as allowed
+			++c->warm_redos;
+			c->redoing = true;
+			c->rounds_cur = c->rounds_max;
+			int rc = launch_dispatch(c, true);
+			if (rc == 0) rc = sync_and_certify(c);
+			c->redoing = false;
+			return rc;
+		}
+		if (cert_failed) {
 			++c->fallbacks;
 			const int keep = c->warm_len;
 			c->warm_len = 0;
@@ -1079,35 +1231,58 @@ extern "C" int psmc_b200_unpack_stats(int32_t N, const double *raw, int64_t n_se
 	return 0;
 }
 
-extern "C" int psmc_b200_estep_finish(psmc_b200_ctx *c, int64_t n_seqs_total, psmc_b200_stats *out)
+static int fetch_stats(psmc_b200_ctx *c)
 {
-	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
-	if (!c->launched) return set_err(PSMC_B200_EINVAL, "estep_finish without estep_launch");
+	if (!c->launched) return set_err(PSMC_B200_EINVAL, "estep finish/fetch without a launch");
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
-	const int n = S_COUNT * c->N + 1;
+	const size_t n = (size_t)(S_COUNT * c->N + 1) * (size_t)c->n_rep;
 	int rc = sync_and_certify(c);
 	if (rc) return rc;
 	CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	collect_times(c, true);
 	c->launched = false;
+	return 0;
+}
+
+extern "C" int psmc_b200_estep_finish(psmc_b200_ctx *c, int64_t n_seqs_total, psmc_b200_stats *out)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (c->batch) return set_err(PSMC_B200_EINVAL, "the context is in batch mode: use psmc_b200_estep_batch_finish");
+	int rc = fetch_stats(c);
+	if (rc) return rc;
 	if (n_seqs_total < 0) n_seqs_total = c->n_seq_eff;
 	return psmc_b200_unpack_stats(c->N, c->h_stats, n_seqs_total, out);
+}
+
+extern "C" int psmc_b200_estep_batch_finish(psmc_b200_ctx *c, int32_t n_rep, psmc_b200_stats *outs)
+{
+	if (!c || !outs) return set_err(PSMC_B200_EINVAL, "NULL argument");
+	if (n_rep != c->n_rep) return set_err(PSMC_B200_EINVAL, "%d result(s) asked, the context is set up for %d model(s)", n_rep, c->n_rep);
+	int rc = fetch_stats(c);
+	if (rc) return rc;
+	const int len = S_COUNT * c->N + 1;
+	for (int r = 0; r < n_rep; ++r) { // every model adds the HMM_TINY terms of ITS drawn records (khmm.c:305-308)
+		rc = psmc_b200_unpack_stats(c->N, c->h_stats + (size_t)r * len, c->rep_seq_eff[r], outs + r);
+		if (rc) return rc;
+	}
+	return 0;
+}
+
+extern "C" int psmc_b200_estep_batch(psmc_b200_ctx *c, int32_t n_rep, const psmc_b200_model *models, psmc_b200_stats *outs)
+{
+	int rc = psmc_b200_estep_batch_launch(c, n_rep, models);
+	if (rc) return rc;
+	return psmc_b200_estep_batch_finish(c, n_rep, outs);
 }
 
 extern "C" int psmc_b200_estep_fetch_raw(psmc_b200_ctx *c, double *raw)
 {
 	if (!c || !raw) return set_err(PSMC_B200_EINVAL, "NULL argument");
-	if (!c->launched) return set_err(PSMC_B200_EINVAL, "estep_fetch_raw without estep_launch");
-	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
-	const int n = S_COUNT * c->N + 1;
-	int rc = sync_and_certify(c);
+	if (c->batch) return set_err(PSMC_B200_EINVAL, "the context is in batch mode: use psmc_b200_estep_batch_finish");
+	int rc = fetch_stats(c);
 	if (rc) return rc;
-	CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
-	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
-	collect_times(c, true);
-	c->launched = false;
-	memcpy(raw, c->h_stats, sizeof(double) * n);
+	memcpy(raw, c->h_stats, sizeof(double) * (size_t)(S_COUNT * c->N + 1));
 	return 0;
 }
 
@@ -1159,6 +1334,7 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
                                 double *best_p, double *post, double *p_recomb, double *s_out)
 {
 	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (c->batch) return set_err(PSMC_B200_EINVAL, "decode needs single-model mode (psmc_b200_set_multiplicity leaves batch mode)");
 	// seq_id indexes the records AS GIVEN to create (empty records included), like psmc_b200_set_multiplicity
 	if (seq_id < 0 || seq_id >= c->n_seqs_given) return set_err(PSMC_B200_EINVAL, "seq_id out of range");
 	if (c->kept_of[seq_id] < 0) return set_err(PSMC_B200_EINVAL, "record %d is empty: nothing to decode", seq_id);
@@ -1225,13 +1401,15 @@ extern "C" int psmc_b200_set_dense(psmc_b200_ctx *c, int32_t on)
 	if (on && (c->NP > 64 || c->gen != 2))
 		return set_err(PSMC_B200_EINVAL, "dense counts need the generation-2 backward kernels (at most 64 states)");
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	if (on && c->batch) return set_err(PSMC_B200_EINVAL, "batch mode and dense counts exclude each other");
 	if (on && !c->d_ghat) {
-		const size_t bytes = (size_t)std::max<int64_t>(c->total_bins, 1) * c->NP * sizeof(double);
+		const size_t bytes = (size_t)std::max<int64_t>(c->cap_bins, 1) * c->NP * sizeof(double);
 		CUDA_TRY(cudaMalloc((void **)&c->d_ghat, bytes), PSMC_B200_ECUDA);
 		CUDA_TRY(cudaMemsetAsync(c->d_ghat, 0, bytes, c->stream), PSMC_B200_ECUDA);
-		CUDA_TRY(cudaMalloc((void **)&c->d_cdense, sizeof(double) * (size_t)c->NP * c->NP), PSMC_B200_ECUDA);
+		if (!c->d_cdense) CUDA_TRY(cudaMalloc((void **)&c->d_cdense, sizeof(double) * (size_t)c->NP * c->NP), PSMC_B200_ECUDA);
 		CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 		c->bytes_total += (int64_t)bytes;
+		c->bytes_forward += (int64_t)bytes;
 	}
 	c->dense = on != 0;
 	c->dense_valid = false;
@@ -1317,5 +1495,10 @@ extern "C" int psmc_b200_get_info(const psmc_b200_ctx *c, psmc_b200_info *info)
 	info->failed_bwd = (int32_t)c->rep_bwd_fail;
 	info->active_bins = c->active_bins;
 	info->n_seqs_effective = c->n_seq_eff;
+	info->n_models = c->n_rep;
+	info->repair_rounds = c->rounds_cur;
+	info->warm_redos = c->warm_redos;
+	info->n_chunks_bwd = c->n_chunks_b;
+	info->chunk_len_bwd = c->chunk_len_b;
 	return 0;
 }

@@ -15,13 +15,14 @@ struct Chunk {
 	int64_t gb0;     // global bin index of u0 (rows of fhat / entries of sc)
 	int64_t ow0;     // first packed-observation word of the SEQUENCE (16 bins per 32-bit word)
 	int32_t Lseq;    // length of the sequence
-	int32_t pad_;
+	int32_t rep;     // which model of the batch this chunk runs under (0 unless psmc_b200_set_batch: bootstrap replicates side by side)
 };
 #define CH_FIRST 1
 #define CH_LAST 2
 
-// model arrays on the device, each NP doubles, contiguous: a0 e0 e1 U V W Z D
+// model arrays on the device, each NP doubles, contiguous: a0 e0 e1 U V W Z D; one such block per model of the batch
 enum { M_A0 = 0, M_E0, M_E1, M_U, M_V, M_W, M_Z, M_D, M_COUNT };
+#define MODEL_OF(model, ch, NP_) ((model) + (size_t)(ch).rep * (M_COUNT * (NP_)))
 // statistics rows: E0 E1 RL CL RU CU AD
 enum { S_E0 = 0, S_E1, S_RL, S_CL, S_RU, S_CU, S_AD, S_COUNT };
 
@@ -404,18 +405,19 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
 	const int c = sel == 0 ? k1_list[item] : item;
 	if (sel == 3 && (!op_needed(flag, k1_list, chunk_sub0, c, dir) || (skip && op_needed(skip, k1_list, chunk_sub0, c, dir)))) continue;
 	const Chunk ch = chunks[c];
+	const double *__restrict__ mdl = MODEL_OF(model, ch, NP);
 	const int gl = threadIdx.x % G;
 	const int col = blockIdx.y * COLS + threadIdx.x / G;
 	double cU[SPL], cV[SPL], cW[SPL], cZ[SPL], cD[SPL], e0[SPL], f[SPL];
 	const int s0 = gl * SPL;
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) {
-		cU[i] = model[M_U * NP + s0 + i];
-		cV[i] = model[M_V * NP + s0 + i];
-		cW[i] = model[M_W * NP + s0 + i];
-		cZ[i] = model[M_Z * NP + s0 + i];
-		cD[i] = model[M_D * NP + s0 + i];
-		e0[i] = model[M_E0 * NP + s0 + i];
+		cU[i] = mdl[M_U * NP + s0 + i];
+		cV[i] = mdl[M_V * NP + s0 + i];
+		cW[i] = mdl[M_W * NP + s0 + i];
+		cZ[i] = mdl[M_Z * NP + s0 + i];
+		cD[i] = mdl[M_D * NP + s0 + i];
+		e0[i] = mdl[M_E0 * NP + s0 + i];
 		f[i] = (s0 + i == col && col < N) ? 1.0 : 0.0;
 	}
 	int ex = 0;
@@ -538,7 +540,7 @@ __device__ __forceinline__ double chain_bwd_step(const double *__restrict__ Tc, 
 }
 
 template <int NP>
-__global__ void __launch_bounds__(NP) k_chain(const int32_t *__restrict__ seq_c0, const int32_t *__restrict__ seq_nc,
+__global__ void __launch_bounds__(NP) k_chain(const Chunk *__restrict__ chunks, const int32_t *__restrict__ seq_c0, const int32_t *__restrict__ seq_nc,
                                               const double *__restrict__ T, const int32_t *__restrict__ Tex,
                                               const double *__restrict__ model, double *__restrict__ vstart,
                                               double *__restrict__ bend, int n_seqs)
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(NP) k_chain(const int32_t *__restrict__ seq_c0
 	const int i = threadIdx.x;
 	if (nc <= 1) return;
 	if (dir == 0) {
-		double v = model[M_A0 * NP + i];
+		double v = MODEL_OF(model, chunks[c0], NP)[M_A0 * NP + i];
 		for (int c = c0; c < c0 + nc - 1; ++c) {
 			v = chain_fwd_step<NP>(T + (size_t)c * NP * NP, Tex + (size_t)c * NP, v, vec, red, redi);
 			vstart[(size_t)(c + 1) * NP + i] = v;
@@ -1022,7 +1024,7 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	const int c = id.c, gl = id.gl, s0 = gl * SPL;
 	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
-	M.load(model, s0, NP);
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
 	double f[SPL];
 	int ubeg = ch.u0;
 	if ((ch.flags & CH_FIRST) || warm > 0) {
@@ -1035,7 +1037,7 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 			for (int i = 0; i < SPL; ++i) f[i] = fmax(row[i], 1e-300);
 		} else {
 #pragma unroll
-			for (int i = 0; i < SPL; ++i) f[i] = model[M_A0 * NP + s0 + i];
+			for (int i = 0; i < SPL; ++i) f[i] = MODEL_OF(model, ch, NP)[M_A0 * NP + s0 + i];
 		}
 	} else {
 		load_vec<SPL>(vstart + (size_t)c * NP + s0, f);
@@ -1072,22 +1074,28 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ fhat, const double *__restrict__ fwarm,
                                                   int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next)
+                                                  int32_t *__restrict__ pred_next, unsigned long long *__restrict__ last_round, int spread, int round)
 {
+	// spread > 0 (rounds after the first): a boundary that fails NOW fails because the repair of the previous round changed
+	// the vector to its left -- a cascade front.  The chunks behind it would fail one per round; chunk c is therefore also
+	// flagged when one of the `spread` boundaries to its left fails (spread = overlap / chunk length: the front's reach).
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31;
-	const Chunk ch = chunks[c];
-	int fl = 0;
-	double m = 0.0;
-	if (!(ch.flags & CH_FIRST)) {
-		m = fwd_boundary_mismatch<SPL>(ch, c, fhat, fwarm, gl * SPL, N);
-		fl = m > eps ? 1 : 0;
+	int fl = 0, own = 0;
+	for (int j = 0; j <= spread && c - j >= 0; ++j) {
+		const Chunk ch = chunks[c - j];
+		if (ch.flags & CH_FIRST) break; // no boundary in front of the first chunk of a sequence, and nothing reaches across it
+		const int f = fwd_boundary_mismatch<SPL>(ch, c - j, fhat, fwarm, gl * SPL, N) > eps ? 1 : 0;
+		if (j == 0) own = f;
+		fl |= f;
+		if (fl) break;
 	}
 	if (gl == 0) {
 		flag_f[c] = fl;
 		if (pred_next) pred_next[c] = fl;
-		if (fl) atomicAdd(&stat[0], 1ull);
+		if (own) atomicAdd(&stat[0], 1ull);
+		if (own) atomicMax(last_round, (unsigned long long)(round + 1)); // the deepest round that still saw a failure: the host sizes the next E-step's rounds by it
 	}
 }
 
@@ -1108,7 +1116,7 @@ __global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict_
 	if (!__any_sync(FULLMASK, valid)) return;
 	const Chunk ch = subs[s];
 	LaneModel<SPL> M;
-	M.load(model, s0, NP);
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
 	double f[SPL];
 	load_vec<SPL>(vsub + (size_t)s * NP + s0, f);                                              // exact vector of the bin before the sub-chunk (k_chain_subs)
 	if (valid && chunk_sub0[pc] == s) store_vec<SPL>(fwarm + (size_t)pc * NP + s0, f);        // the chunk boundary agrees by construction from now on
@@ -1423,7 +1431,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 	const int c = id.c, gl = id.gl, s0 = gl * SPL;
 	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
-	M.load(model, s0, NP);
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
 	const int ulast = ch.u0 + ch.len - 1;
 	const bool is_last = (ch.flags & CH_LAST) != 0;
 	double beta[SPL];
@@ -1544,7 +1552,7 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 	const int c = id.c, gl = id.gl, s0 = gl * SPL;
 	const Chunk ch = chunks[c];
 	LaneModel<SPL> M;
-	M.load(model, s0, NP);
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
 	const int ulast = ch.u0 + ch.len - 1;
 	const bool is_last = (ch.flags & CH_LAST) != 0;
 	double beta[SPL], b[SPL];
@@ -1588,22 +1596,25 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ bwarm, const double *__restrict__ bexact,
                                                   int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next)
+                                                  int32_t *__restrict__ pred_next, unsigned long long *__restrict__ last_round, int spread, int round)
 {
+	// (spread: see k_mark_fwd; the backward cascade runs to the left, so chunk c looks at the boundaries to its right)
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (c >= n_chunks) return;
 	const int gl = threadIdx.x & 31;
-	int fl = 0;
-	double m = 0.0;
-	const bool inner = !(chunks[c].flags & CH_LAST);
-	if (inner) {
-		m = bwd_boundary_mismatch<SPL>(c, bwarm, bexact, gl * SPL, N);
-		fl = m > eps ? 1 : 0;
+	int fl = 0, own = 0;
+	for (int j = 0; j <= spread && c + j < n_chunks; ++j) {
+		if (chunks[c + j].flags & CH_LAST) break; // no boundary behind the last chunk of a sequence
+		const int f = bwd_boundary_mismatch<SPL>(c + j, bwarm, bexact, gl * SPL, N) > eps ? 1 : 0;
+		if (j == 0) own = f;
+		fl |= f;
+		if (fl) break;
 	}
 	if (gl == 0) {
 		flag_b[c] = fl;
 		if (pred_next) pred_next[c] = fl;
-		if (fl) atomicAdd(&stat[2], 1ull);
+		if (own) atomicAdd(&stat[2], 1ull);
+		if (own) atomicMax(last_round, (unsigned long long)(round + 1));
 	}
 }
 
@@ -1625,7 +1636,7 @@ __global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict
 	if (!__any_sync(FULLMASK, valid)) return;
 	const Chunk ch = subs[s];
 	LaneModel<SPL> M;
-	M.load(model, s0, NP);
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
 	double beta[SPL], b[SPL];
 	load_vec<SPL>(bsub + (size_t)s * NP + s0, beta);                                                           // exact direction at the sub-chunk's last bin (k_chain_subs)
 	publish_direction<SPL, G>(beta, bwarm + (size_t)pc * NP, gl, valid && chunk_sub0[pc + 1] - 1 == s);       // the chunk boundary agrees by construction from now on
@@ -1746,19 +1757,25 @@ __global__ void __launch_bounds__(256) k_dense_reduce(const double *__restrict__
 // grid = 1 + S_COUNT*N blocks, block = 256 threads; block 0 reduces LL.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part, const double *__restrict__ llpart,
-                                                int n_chunks, int n_part, int N, int NP, double *__restrict__ out,
-                                                const double *__restrict__ w_ll, const double *__restrict__ w_part)
+                                                const int32_t *__restrict__ rep_f, const int32_t *__restrict__ rep_b, int N, int NP,
+                                                double *__restrict__ out, const double *__restrict__ w_ll, const double *__restrict__ w_part)
 {
-	// w_ll / w_part: multiplicity of the sequence every chunk belongs to (bootstrap replicates, aux.c:8-47); NULL = 1
+	// w_ll / w_part: multiplicity of the sequence every chunk belongs to (bootstrap replicates, aux.c:8-47); NULL = 1.
+	// blockIdx.y = model of the batch: its chunks are [rep_f[r], rep_f[r+1]) in the forward plan (log-likelihood partials)
+	// and [rep_b[r], rep_b[r+1]) in the backward plan (count partials); its statistics vector is out + r * (7N+1).
+	// The summation order depends only on the position of a chunk inside its own model's range, so a model gets the
+	// same bits whether it runs alone or inside a batch (same chunk plan provided).
 	__shared__ double sh[256];
-	const int o = blockIdx.x;
+	const int o = blockIdx.x, r = blockIdx.y;
 	double acc = 0.0;
 	if (o == 0) {
-		for (int c = threadIdx.x; c < n_chunks; c += 256) acc += w_ll ? w_ll[c] * llpart[c] : llpart[c];
+		const int c0 = rep_f[r], c1 = rep_f[r + 1];
+		for (int c = c0 + threadIdx.x; c < c1; c += 256) acc += w_ll ? w_ll[c] * llpart[c] : llpart[c];
 	} else {
+		const int c0 = rep_b[r], c1 = rep_b[r + 1];
 		const int row = (o - 1) / N, k = (o - 1) % N;
 		const double *p = part + (size_t)row * NP + k;
-		for (int c = threadIdx.x; c < n_part; c += 256) {
+		for (int c = c0 + threadIdx.x; c < c1; c += 256) {
 			const double v = p[(size_t)c * S_COUNT * NP];
 			acc += w_part ? w_part[c] * v : v;
 		}
@@ -1769,7 +1786,7 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part,
 		if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) out[o] = sh[0];
+	if (threadIdx.x == 0) out[(size_t)r * (S_COUNT * N + 1) + o] = sh[0];
 }
 
 // ------------------------------------------------------------------------------------------------

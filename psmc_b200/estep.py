@@ -168,6 +168,27 @@ class EStep:
             raise ValueError("mult must have one entry per record given at construction (%d)" % self.n_seqs)
         check(self.lib, self.lib.psmc_b200_set_multiplicity(self.h, m.ctypes.data_as(C.POINTER(C.c_int32))))
 
+    def set_batch(self, mults):
+        """batch mode: one model per row of mults (n_rep x n_seqs multiplicities of the resident records)"""
+        m = np.ascontiguousarray(mults, dtype=np.int32)
+        if m.ndim != 2 or m.shape[1] != self.n_seqs:
+            raise ValueError("mults must be (n_rep, %d)" % self.n_seqs)
+        check(self.lib, self.lib.psmc_b200_set_batch(self.h, m.shape[0], m.ctypes.data_as(C.POINTER(C.c_int32))))
+        self.n_rep = m.shape[0]
+
+    def run_batch(self, models):
+        """one E-step of every model of the batch; returns one result dict per model"""
+        n = len(models)
+        bufs = [_StatsBuf(self.N) for _ in range(n)]
+        cm = (CModel * n)(*[m.c_struct() for m in models])
+        cs = (CStats * n)(*[b.c for b in bufs])
+        check(self.lib, self.lib.psmc_b200_estep_batch(self.h, n, cm, cs))
+        out = []
+        for i, b in enumerate(bufs):
+            b.c = cs[i]
+            out.append(b.result())
+        return out
+
     def set_dense(self, on=True):
         """also spill the backward rows in every following E-step (needed by dense_counts)"""
         check(self.lib, self.lib.psmc_b200_set_dense(self.h, 1 if on else 0))

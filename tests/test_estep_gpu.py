@@ -262,5 +262,5 @@ def test_benchmark_regime_matches_unmodified_reference(ref, L, seed):
                   % (L, it, info["n_chunks"], info["chunk_len"], info["failed_fwd"], info["failed_bwd"], info["fallbacks"],
                      {k: "%.1e" % v for k, v in errs.items()}))
             assert info["fallbacks"] == 0
-            assert info["warm_len"] > 0 and info["n_chunks"] > 1000     # the default plan: one resident wave, fast path
+            assert info["warm_len"] > 0 and info["n_chunks"] > 900      # the default plan: one resident wave, fast path
             assert info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12

@@ -212,3 +212,81 @@ def test_emulated_decode_128_padded_states(oracle, emu_plain):
     want = oracle.decode(m["a"], m["e"], m["a0"], seqs[0], full=True)
     assert np.max(np.abs(got["post"] - want["post"])) < 1e-11
     assert np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
+
+
+@pytest.mark.parametrize("chunk_len,warm", [(150, 0), (150, 400), (0, 400)])
+def test_emulated_batch_of_models(oracle, emu_plain, chunk_len, warm):
+    """psmc_b200_set_batch: three models, each over its own multiset of the resident records, in one launch sequence;
+    every model must match the oracle on its expanded record list, and (fixed chunk length) match a run of its own bit for bit"""
+    from psmc_b200 import EStep
+    N = 23
+    ms = [make_model(oracle, N, seed=81 + r) for r in range(3)]
+    seqs = _seqs(ms[0], [700, 340, 1, 520], seed=82)
+    mults = np.array([[1, 0, 2, 1], [0, 3, 0, 1], [2, 1, 1, 0]], dtype=np.int32)
+    with EStep(seqs, N, chunk_len=chunk_len) as es:
+        es.set_warm(warm)
+        es.set_batch(mults)
+        assert es.info()["n_models"] == 3
+        got = es.run_batch([_model(m) for m in ms])
+        got2 = es.run_batch([_model(m) for m in ms])          # a second E-step of the same batch (operator predictions on)
+        info = es.info()
+        assert info["fallbacks"] == 0
+        alone = []
+        for r in range(3):
+            es.set_multiplicity(mults[r])                      # leaves batch mode
+            alone.append(es.run(_model(ms[r])))
+        with pytest.raises(Exception):
+            es.run_batch([_model(m) for m in ms])              # 3 models on a single-model context
+    for r in range(3):
+        expanded = [s for s, k in zip(seqs, mults[r]) for _ in range(k)]
+        want = oracle_stats(oracle, ms[r], expanded)
+        compare_stats(got[r], want, TOL, N)
+        compare_stats(got2[r], want, TOL, N)
+        if chunk_len > 0:
+            assert got[r]["LL"] == alone[r]["LL"]
+            for k in ("E", "RL", "CL", "RU", "CU", "AD"):
+                assert np.array_equal(got[r][k], alone[r][k]), k
+        else:
+            compare_stats(got[r], alone[r], 1e-11, N)
+
+
+def test_emulated_batch_rejects_bad_input(oracle, emu_plain):
+    from psmc_b200 import EStep, Psmc200Error
+    N = 23
+    m = make_model(oracle, N, seed=91)
+    seqs = _seqs(m, [300, 200], seed=92)
+    with EStep(seqs, N, chunk_len=100) as es:
+        with pytest.raises(Psmc200Error):
+            es.set_batch(np.array([[1, -1]], dtype=np.int32))
+        es.set_batch(np.array([[1, 1], [0, 2]], dtype=np.int32))
+        with pytest.raises(Psmc200Error):
+            es.run(_model(m))                                   # single-model call on a batch context
+        with pytest.raises(Psmc200Error):
+            es.decode(_model(m), 0)
+        with pytest.raises(Psmc200Error):
+            es.set_dense(True)
+        es.set_multiplicity(None)
+        got = es.run(_model(m))
+    compare_stats(got, oracle_stats(oracle, m, seqs), TOL, N)
+
+
+def test_emulated_deep_repair_cascade_stays_on_the_fast_path(oracle, emu_plain):
+    """chunks much shorter than the mixing length: repairs cascade over many rounds.  The number of rounds adapts and a
+    failed certificate is first retried on the fast path with more rounds; the exact transfer-operator fallback stays unused"""
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=33)
+    seqs = _seqs(m, [5000, 900], seed=34)
+    seqs[0][1500:3600] = 0            # a long homozygous tract: slow mixing across many short chunks
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=40) as es:
+        es.set_warm(60)
+        rounds = []
+        for it in range(3):
+            got = es.run(_model(m))
+            info = es.info()
+            rounds.append((info["repair_rounds"], info["warm_redos"], info["fallbacks"]))
+            compare_stats(got, want, TOL, N)
+    assert rounds[-1][2] == 0, rounds             # never the exact fallback
+    assert rounds[-1][1] == 1, rounds             # one retry on the fast path (first E-step), none afterwards
+    assert rounds[-1][0] > 3, rounds              # the cascade was deeper than the default three rounds: adapted
