@@ -8,9 +8,17 @@ objective), exactly what `psmc -N1` adds per round (em.c:27-78).  Workload = BAS
 
   python bench.py --gpus N --steps K --warmup W          own arm (torchrun for N > 1: contigs sharded over
                                                           ranks, one NCCL all-reduce of the 449-double
-                                                          statistics vector per iteration)
-  python bench.py --impl reference ...                   the reference's own CPU implementation
-                                                          (oracle/_ref) on a bounded sample, extrapolated
+                                                          statistics vector per iteration, M-step on rank 0,
+                                                          NCCL broadcast of the parameters)
+  python bench.py --impl reference ...                   the reference's own CPU implementation (oracle/_ref):
+                                                          every step times its E-step on a bounded sample on
+                                                          all host cores; value = the whole-workload rate that
+                                                          follows; plus a measured (not extrapolated) 1-core run
+                                                          of the unmodified binary on the configs[1] contig
+  python bench.py --workload bootstrap|decode            BASELINE's second metric (100-bootstrap wall time,
+                                                          configs[3]) / configs[4] (decode throughput) alone;
+                                                          the default run appends both as "bootstrap" / "decode"
+                                                          objects to its line (--no-extras skips them)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every key means.
 """
@@ -121,79 +129,139 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the UNMODIFIED reference (oracle/_ref) when present, else the oracle port
+# CPU baseline / reference arm: the UNMODIFIED reference (oracle/_ref) when present, else the oracle port.
+# Nothing in here touches the product libraries (no psmc_b200.host, no libpsmc_b200.so): the model comes from the
+# reference's own psmc_update_hmm (core.c:61-133 through oracle/ref_harness.c), the data from numpy.
 # ------------------------------------------------------------------------------------------------
+def _checker():
+    from oracle.pyoracle import Ref, Oracle
+    return (Ref(), "reference") if Ref.available() else (Oracle(), "port")
+
+
+def _true_model(chk):
+    from psmc_b200 import synth
+    n, nf, _ = chk.pattern(PATTERN)
+    return chk.update_hmm(PATTERN, np.concatenate([[TRUE_THETA, TRUE_RHO, MAX_T], synth.bottleneck_lambdas(nf)]))
+
+
 def _cpu_estep_worker(args):
-    kind, seed, nbins = args
+    seed, nbins = args
     sys.path.insert(0, ROOT)
-    from oracle.pyoracle import Oracle, Ref
-    from psmc_b200 import host, synth
-    chk = Ref() if kind == "reference" else Oracle()
-    n, nf, _ = host.parse_pattern(PATTERN)
-    params = np.concatenate([[TRUE_THETA, TRUE_RHO, MAX_T], synth.bottleneck_lambdas(nf)])
-    hm = host.model_from_params(PATTERN, params)
-    a = hm["model"].dense()
-    seq = synth.simulate(hm["a0"], a, hm["e"], nbins, np.random.default_rng(seed))
+    from psmc_b200 import synth
+    chk, _ = _checker()
+    m = _true_model(chk)
+    seq = synth.simulate(m["a0"], m["a"], m["e"], nbins, np.random.default_rng(seed))
     t0 = time.perf_counter()
-    chk.estep(a, hm["e"], hm["a0"], [seq])
+    chk.estep(m["a"], m["e"], m["a0"], [seq])
     return time.perf_counter() - t0
 
 
-def cpu_baseline(total_bins, cores, sample_bins=100000, reps=1):
-    """E-step of the reference on `cores` processes, each on its own sample contig (the contigs of a genome
-    are independent, em.c:36-55), plus the reference M-step single-threaded; extrapolated linearly in bins."""
-    import multiprocessing as mp
-    from oracle.pyoracle import Ref, Oracle
-    from psmc_b200 import host, synth
-    kind = "reference" if Ref.available() else "port"
-    chk = Ref() if kind == "reference" else Oracle()
-    t_est = []
-    ctx = mp.get_context("spawn")
-    for r in range(reps):
-        with ctx.Pool(cores) as pool:
-            t0 = time.perf_counter()
-            per = pool.map(_cpu_estep_worker, [(kind, 1000 + r * 64 + i, sample_bins) for i in range(cores)])
-            wall = time.perf_counter() - t0
-        t_est.append(max(per))
-    t_sample = min(t_est)                                   # seconds for `cores` x sample_bins bins
-    bins_per_s = cores * sample_bins / t_sample
-    # M-step of the reference: Hooke-Jeeves on the dense O(N^2) objective (em.c:15-25,65), single thread, in C
-    n, nf, _ = host.parse_pattern(PATTERN)
-    params = np.concatenate([[TRUE_THETA, TRUE_RHO, MAX_T], np.ones(nf)])
-    hm = host.model_from_params(PATTERN, params)
-    seq = synth.simulate(hm["a0"], hm["model"].dense(), hm["e"], 20000, np.random.default_rng(5))
-    t_m = reference_mstep_seconds(chk, kind, seq)
-    t_iter = total_bins / bins_per_s + t_m
-    return {"value": 1.0 / t_iter, "unit": "EM iters/s", "cores": cores, "kind": kind,
-            "sample": "%d procs x %d bins E-step (%.2f s, %.3g bins/s), M-step %.3f s on 1 core; extrapolated to %d bins"
-                      % (cores, sample_bins, t_sample, bins_per_s, t_m, total_bins),
-            "estep_bins_per_s": bins_per_s, "mstep_s": t_m, "s_per_iter": t_iter}
+class CpuArm:
+    """E-step of the reference (hmm_forward/backward/lk/expect, khmm.c:145-324, through its own objects) on sample
+    contigs: `cores` processes at once, each on its own sample (the contigs of a genome are independent, em.c:36-55)."""
+
+    def __init__(self, cores, sample_bins):
+        import multiprocessing as mp
+        self.cores, self.sample_bins = cores, sample_bins
+        self.pool = mp.get_context("spawn").Pool(cores)
+        self.pool.map(_cpu_estep_worker, [(1, 2000)] * cores)          # start the workers, load the library
+        self.round = 0
+
+    def step(self):
+        """one timed all-core sample E-step; returns (wall seconds, bins/s over all cores)"""
+        self.round += 1
+        t0 = time.perf_counter()
+        per = self.pool.map(_cpu_estep_worker, [(1000 + self.round * 64 + i, self.sample_bins) for i in range(self.cores)])
+        wall = time.perf_counter() - t0
+        return wall, self.cores * self.sample_bins / max(per)
+
+    def one_core(self):
+        """the same E-step on ONE core (the reference is single-threaded: BASELINE.md section 3's headline figure)"""
+        t = _cpu_estep_worker((999, self.sample_bins))
+        return self.sample_bins / t
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
-def reference_mstep_seconds(chk, kind, seq):
-    """time of one M-step of the reference binary: (psmc -N2) - (psmc -N1) - E-step share, on a small input"""
+def _ref_binary_runs(chk, seq, n_list, pattern=PATTERN, extra=()):
+    """wall seconds of `oracle/_ref/psmc -N n` on seq for every n of n_list (unmodified binary, one core)"""
     from psmc_b200 import psmcfa
     import tempfile
-    if kind != "reference" or not os.path.exists(chk.psmc_bin):
-        return 0.12  # SURVEY.md section 6 probe (0.10-0.15 s); only used when oracle/_ref/psmc is absent
+    out = {}
     with tempfile.TemporaryDirectory() as td:
         fn = os.path.join(td, "s.psmcfa")
         psmcfa.write_psmcfa(fn, [seq])
-        def run(nit):
+        for n in n_list:
             t0 = time.perf_counter()
-            subprocess.run([chk.psmc_bin, "-N%d" % nit, "-t%g" % MAX_T, "-r%g" % TR_RATIO, "-p", PATTERN, "-o", os.path.join(td, "o.psmc"), fn],
-                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            return time.perf_counter() - t0
-        t1 = run(1); t3 = run(3)
-        per_iter = (t3 - t1) / 2.0
-        # E-step share of that small input, measured through the harness on the same sequence
-        from psmc_b200 import host, synth
-        n, nf, _ = host.parse_pattern(PATTERN)
-        hm = host.model_from_params(PATTERN, np.concatenate([[TRUE_THETA, TRUE_RHO, MAX_T], np.ones(nf)]))
-        t0 = time.perf_counter()
-        chk.estep(hm["model"].dense(), hm["e"], hm["a0"], [seq])
-        t_e = time.perf_counter() - t0
-        return max(per_iter - t_e, 0.02)
+            subprocess.run([chk.psmc_bin, "-N%d" % n, "-t%g" % MAX_T, "-r%g" % TR_RATIO, "-p", pattern] + list(extra) +
+                           ["-o", os.path.join(td, "o.psmc"), fn], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out[n] = time.perf_counter() - t0
+    return out
+
+
+def reference_mstep_seconds(chk, kind):
+    """one M-step of the reference (Hooke-Jeeves on the dense O(N^2) objective, em.c:15-25,65; independent of the input
+    length): per-iteration time of the unmodified binary on a small input minus the E-step share of that input"""
+    from psmc_b200 import synth
+    if kind != "reference" or not os.path.exists(chk.psmc_bin):
+        return 0.12  # SURVEY.md section 6 probe (0.10-0.15 s); only used when oracle/_ref/psmc is absent
+    m = _true_model(chk)
+    seq = synth.simulate(m["a0"], m["a"], m["e"], 20000, np.random.default_rng(5))
+    t = _ref_binary_runs(chk, seq, (1, 3))
+    per_iter = (t[3] - t[1]) / 2.0
+    flat = chk.update_hmm(PATTERN, np.concatenate([[TRUE_THETA, TRUE_RHO, MAX_T], np.ones(chk.pattern(PATTERN)[1])]))
+    t0 = time.perf_counter()
+    chk.estep(flat["a"], flat["e"], flat["a0"], [seq])
+    return max(per_iter - (time.perf_counter() - t0), 0.02)
+
+
+def measured_c2(chk, kind, bins=500000, k=2):
+    """MEASURED, not extrapolated: (T(-N k) - T(-N 0)) / k of the unmodified binary on the configs[1] contig"""
+    from psmc_b200 import synth
+    if kind != "reference" or not os.path.exists(chk.psmc_bin):
+        return None
+    m = _true_model(chk)
+    seq = synth.simulate(m["a0"], m["a"], m["e"], bins, np.random.default_rng(SEED))
+    t = _ref_binary_runs(chk, seq, (0, k))
+    return {"bins": bins, "iterations": k, "s_per_iter": (t[k] - t[0]) / k, "wall_s": {"N0": t[0], "N%d" % k: t[k]}, "cores": 1}
+
+
+def cpu_baseline(total_bins, cores, sample_bins=100000, with_c2=True, arm=None):
+    """the reported CPU baseline of the own arm (rank 0, N = 1): one all-core sample E-step, the 1-core figure, the
+    reference M-step, and the measured configs[1] iteration of the unmodified binary"""
+    chk, kind = _checker()
+    own = arm is None
+    arm = arm or CpuArm(cores, sample_bins)
+    wall, bps = arm.step()
+    bps1 = arm.one_core()
+    if own:
+        arm.close()
+    t_m = reference_mstep_seconds(chk, kind)
+    t_iter = total_bins / bps + t_m
+    t_iter1 = total_bins / bps1 + t_m
+    out = {"value": 1.0 / t_iter, "unit": "EM iters/s", "cores": cores, "kind": kind,
+           "sample": "%d procs x %d bins E-step (%.2f s, %.3g bins/s), M-step %.3f s on 1 core; extrapolated linearly in bins to %d bins"
+                     % (cores, sample_bins, wall, bps, t_m, total_bins),
+           "estep_bins_per_s": bps, "mstep_s": t_m, "s_per_iter": t_iter,
+           "one_core": {"value": 1.0 / t_iter1, "unit": "EM iters/s", "estep_bins_per_s": bps1, "s_per_iter": t_iter1,
+                        "what": "the reference is single-threaded: this is what one `psmc` process does (BASELINE.md section 3)"}}
+    if with_c2:
+        c2 = measured_c2(chk, kind)
+        if c2:
+            c2["extrapolated_s_per_iter"] = c2["bins"] / bps1 + t_m      # what the 1-core sample predicts for the same contig
+            c2["measured_over_extrapolated"] = c2["s_per_iter"] / c2["extrapolated_s_per_iter"]
+            out["measured_configs1"] = c2
+    return out
+
+
+def bootstrap_cpu_baseline(cb, bins, replicates, iters):
+    """README:57-62 recipe: R independent single-thread `psmc -b` runs over the split file, `xargs -P cores` of them at
+    a time.  Derived from the measured 1-core E-step rate and M-step time (a replicate has as many bins as the genome)."""
+    per_rep = iters * (bins / cb["one_core"]["estep_bins_per_s"] + cb["mstep_s"])
+    return {"one_core_s": replicates * per_rep, "all_cores_s": replicates * per_rep / max(1, min(cb["cores"], replicates)), "cores": cb["cores"],
+            "kind": cb["kind"], "what": "derived: %d replicates x %d iterations x (bins / 1-core E-step rate + M-step); all cores = xargs -P %d" % (replicates, iters, cb["cores"])}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,22 +269,44 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total_bins = int(sum(__import__("psmc_b200.synth", fromlist=["x"]).HUMAN_AUTOSOME_BINS) * args.scale)
+    from psmc_b200 import synth
+    total_bins = int(sum(synth.HUMAN_AUTOSOME_BINS) * args.scale)
     cores = min(os.cpu_count() or 1, 64)
-    vals = []
+    chk, kind = _checker()
     t_all = time.perf_counter()
+    arm = CpuArm(cores, args.cpu_sample_bins)
+    t_m = reference_mstep_seconds(chk, kind)
+    walls, rates = [], []
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(total_bins, cores, sample_bins=args.cpu_sample_bins)
+        wall, bps = arm.step()                      # one step = one all-core sample E-step (+ the M-step time measured above)
         if i >= args.warmup:
-            vals.append(cb)
-        if time.perf_counter() - t_all > 240:
+            walls.append(wall); rates.append(bps)
+        if time.perf_counter() - t_all > 150:
             break
-    best = max(vals, key=lambda c: c["value"]) if vals else cb
-    v = statistics.mean(c["value"] for c in vals) if vals else cb["value"]
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "EM iters/s", "n_gpus": args.gpus, "steps": len(vals) or 1,
-           "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    bps1 = arm.one_core()
+    arm.close()
+    if not rates:
+        rates, walls = [bps], [wall]
+    bps = statistics.mean(rates)
+    t_iter = total_bins / bps + t_m
+    v = 1.0 / t_iter
+    cb = {"value": v, "unit": "EM iters/s", "cores": cores, "kind": kind,
+          "sample": "%d steps; each: %d procs x %d bins E-step of the reference (mean %.2f s, %.3g bins/s over all cores); M-step %.3f s (binary, 1 core); "
+                    "value = 1 / (bins / rate + M-step) for the %d-bin workload" % (len(rates), cores, args.cpu_sample_bins, statistics.mean(walls), bps, t_m, total_bins),
+          "estep_bins_per_s": bps, "mstep_s": t_m, "s_per_iter": t_iter,
+          "one_core": {"value": 1.0 / (total_bins / bps1 + t_m), "unit": "EM iters/s", "estep_bins_per_s": bps1, "s_per_iter": total_bins / bps1 + t_m}}
+    c2 = measured_c2(chk, kind) if not args.no_extras else None
+    if c2:
+        c2["extrapolated_s_per_iter"] = c2["bins"] / bps1 + t_m
+        c2["measured_over_extrapolated"] = c2["s_per_iter"] / c2["extrapolated_s_per_iter"]
+        cb["measured_configs1"] = c2
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "EM iters/s", "n_gpus": args.gpus, "steps": len(rates),
+           "warmup": args.warmup, "ms_per_step": statistics.mean(walls) * 1e3,
+           "ms_per_step_what": "wall time of one TIMED step = the bounded sample E-step on all cores; the whole-workload iteration it implies is extrapolated_ms_per_iteration",
+           "extrapolated_ms_per_iteration": t_iter * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(total_bins, args),
-           "cpu_baseline": dict(best, value=v),
+           "cpu_baseline": cb,
+           "bootstrap": bootstrap_cpu_baseline(cb, total_bins, args.boot_replicates, args.boot_iters),
            "e2e": {"value": v, "unit": "EM iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -226,7 +316,7 @@ def workload_config(total_bins, args):
                         "one step = E-step over all contigs + host M-step" % (total_bins, PATTERN, MAX_T, TR_RATIO),
             "bins": total_bins, "states": 64, "scale": args.scale,
             "l2": "inputs larger than L2 (forward spill %.1f GB per step)" % (total_bins * 520 / 1e9),
-            "parallelism": "contigs sharded over %d GPU(s), LPT; NCCL all-reduce of 449 doubles per step" % args.gpus}
+            "parallelism": "contigs sharded over %d GPU(s), LPT; NCCL all-reduce of 449 doubles per step, M-step on rank 0, NCCL broadcast of the parameters" % args.gpus}
 
 
 def run_own(args):
@@ -270,6 +360,7 @@ def run_own(args):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
     stats_t = torch.as_tensor(_Dev(lib.psmc_b200_device_stats(ctx), slen), device="cuda:%d" % local)
 
+    par_t = torch.zeros(em.n_params, dtype=torch.float64, device="cuda:%d" % local)
     kern_ms = []   # per step: library's CUDA-event times of its kernels [K1..K5, total]
     launches = [0]
 
@@ -287,7 +378,17 @@ def run_own(args):
         ci = CInfo()
         lib.psmc_b200_get_info(ctx, ctypes.byref(ci))
         kern_ms.append(list(ci.ms)[:8]); launches[0] += ci.launches
-        em.mstep()                                          # replicated on every rank on identical inputs
+        if world == 1:
+            em.mstep()
+        else:
+            # the M-step runs on rank 0 only (with its helper threads); the other ranks receive the parameters: 8 replicated
+            # searches on one host fought for its cores (round 1: 4.6 ms per M-step at 8 ranks against 3.2 ms alone)
+            if rank == 0:
+                em.mstep()
+                par_t.copy_(torch.from_numpy(em.state()["params"]))
+            dist.broadcast(par_t, 0)
+            if rank != 0:
+                em.set_params(par_t.cpu().numpy())
 
     def barrier():
         if world > 1:
@@ -333,6 +434,7 @@ def run_own(args):
     else:
         obs_bytes_total = obs_bytes
 
+    out, cb = None, None
     if rank == 0:
         peak, peak_src = measured_peaks()
         km = np.array(k_resident)                           # steps x 6
@@ -355,7 +457,7 @@ def run_own(args):
                 per_kernel[nm]["alg_GBps"] = kb[nm] * my_bins / (mean_ms[i] * 1e-3) / 1e9
         achieved = alg_bytes_per_bin * my_bins / (estep_ms * 1e-3) / 1e9
         cores = min(os.cpu_count() or 1, 64)
-        cb = cpu_baseline(total_bins, cores, sample_bins=args.cpu_sample_bins) if (world == 1 and not args.no_cpu) else None
+        cb = cpu_baseline(total_bins, cores, sample_bins=args.cpu_sample_bins, with_c2=not args.no_extras) if (world == 1 and not args.no_cpu) else None
         value = args.steps / dt
         out = {"metric": METRIC, "value": value, "unit": "EM iters/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -377,10 +479,122 @@ def run_own(args):
                "final": {"lk": st["lk"], "theta": float(st["params"][0]), "rho": float(st["params"][1])}}
         if cb:
             out["cpu_baseline"] = cb
-        print(json.dumps(out), flush=True)
     em.close()
+    del stats_t
+    torch.cuda.empty_cache()
+    # ---- secondary metrics through the drop-in binary (one process drives all N GPUs; the other ranks stay idle on the CPU)
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    if rank == 0:
+        if not args.no_extras:
+            fa = write_genome_file(seqs)
+            try:
+                out["bootstrap"] = run_bootstrap(args, fa, total_bins, world, cb)
+            except Exception as e:      # the headline line must survive a failing extra
+                out["bootstrap"] = {"error": str(e)[:300]}
+            try:
+                out["decode"] = run_decode(args, fa, total_bins, world)
+            except Exception as e:
+                out["decode"] = {"error": str(e)[:300]}
+        print(json.dumps(out), flush=True)
+        if store is not None:
+            store.set("bench_extras_done", "1")
+    elif store is not None:
+        store.wait(["bench_extras_done"])     # blocks on the CPU: no NCCL kernel spins on this rank's GPU meanwhile
     if world > 1:
         dist.destroy_process_group()
+
+
+GENOME_FA = "/tmp/psmc_b200_bench_genome.psmcfa"
+
+
+def write_genome_file(seqs):
+    from psmc_b200 import psmcfa
+    psmcfa.write_psmcfa(GENOME_FA, seqs)
+    return GENOME_FA
+
+
+def psmc_bin():
+    from psmc_b200 import host
+    return host.PSMC_BIN
+
+
+def run_bootstrap(args, fa, total_bins, n_gpus, cb=None):
+    """BASELINE metric, second half: wall time of 100 bootstrap replicates (x 25 EM iterations) of the split genome
+    (configs[3]; README:49-62 = splitfa + 100 x `psmc -b`), here ONE process: `psmc --split --replicates R --gpus N`
+    (host/bootstrap.c: segments resident once per GPU, replicates batched through psmc_b200_set_batch, no collective)."""
+    R, iters = args.boot_replicates, args.boot_iters
+    base = [psmc_bin(), "-t%g" % MAX_T, "-r%g" % TR_RATIO, "-p", PATTERN, "--split=500000", "--seed", "1", "--gpus", str(n_gpus), "--verbose"]
+    # warm-up: a short run of the same binary (device initialisation, page-in of the input file)
+    subprocess.run(base + ["-N2", "--replicates", str(2 * n_gpus), "-o", "/tmp/psmc_b200_boot_warm.psmc", fa], capture_output=True, text=True)
+    t0 = time.perf_counter()
+    r = subprocess.run(base + ["-N%d" % iters, "--replicates", str(R), "-o", "/tmp/psmc_b200_boot.psmc", fa], capture_output=True, text=True)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("psmc --replicates failed: " + r.stderr[-300:])
+    tail = [l for l in r.stderr.splitlines() if "bootstrap:" in l]
+    em_s = float(tail[-1].split(":")[-1].split()[0]) if tail else None
+    done = sum(1 for l in open("/tmp/psmc_b200_boot.psmc") if l.startswith("RD\t%d" % iters))
+    out = {"metric": "%d-bootstrap wall-time" % R, "value": wall, "unit": "s", "higher_is_better": False, "n_gpus": n_gpus,
+           "replicates": R, "em_iterations": iters, "replicates_completed": done, "em_phase_s": em_s,
+           "replicate_iterations_per_s": R * iters / em_s if em_s else None,
+           "what": "wall clock of the whole process: reading the .psmcfa text, splitfa rule, upload, %d x %d EM iterations, output; em_phase_s excludes reading" % (R, iters),
+           "detail": tail[-1].strip() if tail else None}
+    if cb:
+        out["cpu_baseline"] = bootstrap_cpu_baseline(cb, total_bins, R, iters)
+    return out
+
+
+def run_decode(args, fa, total_bins, n_gpus):
+    """configs[4]: posterior decoding (-d, aux.c:150-182) of the whole genome with fixed parameters (-N0 -i)"""
+    par = "/tmp/psmc_b200_bench_params.txt"
+    from psmc_b200 import host, synth
+    n, nf, _ = host.parse_pattern(PATTERN)
+    lam = synth.bottleneck_lambdas(nf)
+    with open(par, "w") as fp:      # the layout psmc -i reads (aux.c:84-113): the PA line without its tag
+        fp.write("%s %.9f %.9f %.9f %s\n" % (PATTERN, TRUE_THETA, TRUE_RHO, MAX_T, " ".join("%.9f" % x for x in lam)))
+    res = {}
+    for mode, flag in (("DC", "-d"),):
+        cmd = [psmc_bin(), "-N0", "-i", par, flag, "-p", PATTERN, "--gpus", str(n_gpus), "--verbose", "-o", "/tmp/psmc_b200_decode.psmc", fa]
+        subprocess.run(cmd, capture_output=True, text=True)        # warm-up
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError("psmc -d failed: " + r.stderr[-300:])
+        tl = [l for l in r.stderr.splitlines() if "decode:" in l]
+        gpu_s = float(tl[-1].split("decode:")[-1].split()[0]) if tl else None
+        res[mode] = {"wall_s": wall, "decode_phase_s": gpu_s, "bins_per_s": total_bins / gpu_s if gpu_s else None,
+                     "segments": sum(1 for l in open("/tmp/psmc_b200_decode.psmc") if l.startswith("DC")), "detail": tl[-1].strip() if tl else None}
+    return {"metric": "decode throughput (-d) on 3Gbp psmcfa, 64 states", "value": res["DC"]["bins_per_s"], "unit": "bins/s", "higher_is_better": True,
+            "n_gpus": n_gpus, "bins": total_bins, "modes": res,
+            "reference": "oracle/_ref/psmc -N0 -d: 3.65 s per 500 k bins on one core (BASELINE.md section 2) = 1.4e5 bins/s"}
+
+
+def run_workload_only(args):
+    """--workload bootstrap | decode: the secondary metric alone, as its own JSON line (rank 0 of a torchrun launch drives all GPUs)"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from psmc_b200 import synth
+    seqs = make_genome(args.scale)
+    total_bins = sum(len(s) for s in seqs)
+    fa = write_genome_file(seqs)
+    cores = min(os.cpu_count() or 1, 64)
+    if args.workload == "bootstrap":
+        cb = cpu_baseline(total_bins, cores, sample_bins=args.cpu_sample_bins, with_c2=False) if not args.no_cpu else None
+        o = run_bootstrap(args, fa, total_bins, args.gpus, cb)
+        o.update({"steps": 1, "warmup": 1, "ms_per_step": o["value"] * 1e3, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": "configs[3]: %d bootstrap replicates x %d EM iterations of the 22-contig synthetic genome (%d bins) split at 500 000 bins, "
+                                         "pattern %s (64 states); one step = the whole job" % (args.boot_replicates, args.boot_iters, total_bins, PATTERN),
+                             "parallelism": "replicates dealt to %d GPU(s) in batches, no collective" % args.gpus}})
+    else:
+        o = run_decode(args, fa, total_bins, args.gpus)
+        o.update({"steps": 1, "warmup": 1, "ms_per_step": o["modes"]["DC"]["wall_s"] * 1e3, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": "configs[4]: psmc -N0 -i -d on the 22-contig synthetic genome (%d bins), pattern %s (64 states); one step = the whole job" % (total_bins, PATTERN)}})
+    print(json.dumps(o), flush=True)
 
 
 def main():
@@ -389,13 +603,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="em", choices=["em", "bootstrap", "decode"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale every contig length (1.0 = the 28.8 M-bin workload)")
     ap.add_argument("--chunk", type=int, default=0, help="bins per chunk (0 = auto)")
     ap.add_argument("--cpu-sample-bins", type=int, default=100000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary metrics (bootstrap wall time, decode throughput)")
+    ap.add_argument("--boot-replicates", type=int, default=100)
+    ap.add_argument("--boot-iters", type=int, default=25)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "em":
+        run_workload_only(args)
     else:
         run_own(args)
 

@@ -113,6 +113,14 @@ void psmch_py_em_destroy(void *h)
 int psmch_py_em_iterate(void *h) { return psmch_em_iterate(&((session_t*)h)->em, 0); }
 int psmch_py_em_estep(void *h) { return psmch_em_estep(&((session_t*)h)->em); }
 int psmch_py_em_mstep(void *h) { return psmch_em_mstep(&((session_t*)h)->em, 0); }
+/* install parameters found elsewhere (multi-process drivers: the M-step runs on one rank, the others receive its result) */
+int psmch_py_em_set_params(void *h, const double *params)
+{
+	session_t *s = (session_t*)h;
+	memcpy(s->em.model.params, params, sizeof(double) * s->em.sp.n_params);
+	psmch_model_update(&s->em.sp, s->em.model.params, &s->em.model);
+	return 0;
+}
 int psmch_py_em_set_raw(void *h, const double *raw, long long n_seqs_total) { return psmch_em_set_raw(&((session_t*)h)->em, raw, n_seqs_total); }
 void *psmch_py_em_ctx(void *h, int g) { session_t *s = (session_t*)h; return (g >= 0 && g < s->em.n_gpus) ? s->em.ctx[g] : 0; }
 int psmch_py_em_launch(void *h)

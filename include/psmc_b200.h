@@ -83,6 +83,8 @@ typedef struct {
 	/* repair rounds the next E-step will enqueue (adapts to how deep the repairs cascade), and how many E-steps were
 	 * redone on the fast path with more rounds after a failed certificate (before any exact fallback) */
 	int32_t repair_rounds, warm_redos;
+	/* last psmc_b200_decode_run: device ms of its E-step, of the decode kernel + run compaction, and wall ms of the call */
+	float decode_ms[3];
 } psmc_b200_info;
 
 int  psmc_b200_version(void);
@@ -172,6 +174,27 @@ int  psmc_b200_unpack_stats(int32_t n_states, const double *raw, int64_t n_seqs_
  *   post[L*N] (optional), p_recomb[L] (optional, 0 at the last bin), s_out[L] (optional; hmm_data_t::s, aux.c:159-164). */
 int  psmc_b200_decode(psmc_b200_ctx *ctx, const psmc_b200_model *model, int32_t seq_id,
                       int32_t *best_k, double *best_p, double *post, double *p_recomb, double *s_out);
+
+/* Decoding of EVERY sequence of the context in one go, on the fast path (what `psmc -d` / `-D` need at genome scale;
+ * replaces aux.c:157-200 for all sequences).  decode_run = one complete E-step on the model (exact forward spill,
+ * certified boundary directions) + one decode kernel over all chunks; results stay on the device until fetched:
+ *   PSMC_B200_DEC_RUNS  runs of the posterior-argmax state with their maximum posterior -- the DC lines of aux.c:165-182 --
+ *                       compacted on the device, so only the runs cross PCIe (~13 bytes per run instead of 12 per bin);
+ *                       get_runs returns them for all sequences in (sequence, position) order: seq_id indexes the records
+ *                       as given to create, start is the 0-based first bin, state = argmax_k f*b*s (first maximum wins),
+ *                       max_p = the largest posterior of that state inside the run.  Call with cap = 0 to get *n_runs only.
+ *   PSMC_B200_DEC_BINS  per bin: argmax state (uint8) and its posterior (float)            -> get_bins(best_k, best_p)
+ *   PSMC_B200_DEC_POST  per bin: the full posterior row (float, hmm_post_state khmm.c:286-293) and the recombination
+ *                       probability (double, aux.c:188-193; 0 at the last bin)             -> get_bins(post, p_recomb)
+ * Outputs are reduced precision by design (uint8 / float): they feed %.3lf / %.4f text.  psmc_b200_decode above keeps the
+ * double-precision, one-sequence interface.  Not available in batch mode. */
+#define PSMC_B200_DEC_RUNS 1u
+#define PSMC_B200_DEC_BINS 2u
+#define PSMC_B200_DEC_POST 4u
+int  psmc_b200_decode_run(psmc_b200_ctx *ctx, const psmc_b200_model *model, uint32_t what);
+int  psmc_b200_decode_get_runs(psmc_b200_ctx *ctx, int64_t cap, int32_t *seq_id, int32_t *start, int32_t *len, uint8_t *state,
+                               double *max_p, int64_t *n_runs);
+int  psmc_b200_decode_get_bins(psmc_b200_ctx *ctx, int32_t seq_id, uint8_t *best_k, float *best_p, float *post, double *p_recomb);
 
 /* Fast-path control: warm_len = bins of warm-up overlap per chunk (0 = always use the exact transfer-matrix
  * path; < 0 = keep), eps = certificate tolerance in Hilbert's projective metric (<= 0 = keep; default 1e-12).

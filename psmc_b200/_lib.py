@@ -38,7 +38,7 @@ class CInfo(C.Structure):
                 ("failed_fwd", C.c_int32), ("repaired_fwd", C.c_int32), ("failed_bwd", C.c_int32), ("repaired_bwd", C.c_int32),
                 ("active_bins", C.c_int64), ("n_seqs_effective", C.c_int64),
                 ("n_models", C.c_int32), ("n_chunks_bwd", C.c_int32), ("chunk_len_bwd", C.c_int32),
-                ("repair_rounds", C.c_int32), ("warm_redos", C.c_int32)]
+                ("repair_rounds", C.c_int32), ("warm_redos", C.c_int32), ("decode_ms", C.c_float * 3)]
 
 
 # every symbol include/psmc_b200.h declares: name -> (restype, argtypes)
@@ -69,6 +69,9 @@ SYMBOLS = {
     "psmc_b200_estep_fetch_raw": (C.c_int, [C.c_void_p, _dp]),
     "psmc_b200_unpack_stats": (C.c_int, [C.c_int32, _dp, C.c_int64, C.POINTER(CStats)]),
     "psmc_b200_decode": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.c_int32, _ip, _dp, _dp, _dp, _dp]),
+    "psmc_b200_decode_run": (C.c_int, [C.c_void_p, C.POINTER(CModel), C.c_uint32]),
+    "psmc_b200_decode_get_runs": (C.c_int, [C.c_void_p, C.c_int64, _ip, _ip, _ip, C.POINTER(C.c_uint8), _dp, C.POINTER(C.c_int64)]),
+    "psmc_b200_decode_get_bins": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_float), _dp]),
     "psmc_b200_set_warm": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "psmc_b200_set_dense": (C.c_int, [C.c_void_p, C.c_int32]),
     "psmc_b200_dense_counts": (C.c_int, [C.c_void_p, _dp]),

@@ -48,9 +48,13 @@
 #include <stdarg.h>
 #include <math.h>
 #include <limits.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <vector>
 #include <algorithm>
 #include <thread>
+#include <chrono>
 
 #include "psmc_b200.h"
 
@@ -163,6 +167,19 @@ struct psmc_b200_ctx {
 	int32_t *d_bestk = nullptr;
 	double *d_bestp = nullptr, *d_post = nullptr, *d_prec = nullptr;
 	int64_t dec_cap = 0, dec_post_cap = 0;
+	// whole-context decoding on the fast path (psmc_b200_decode_run): per-bin outputs and run lists, indexed by forward-spill row
+	uint8_t *d2_bestk = nullptr, *d2_run_state = nullptr, *d2_o_state = nullptr;
+	float *d2_bestp = nullptr, *d2_post = nullptr;
+	double *d2_prec = nullptr, *d2_run_maxp = nullptr, *d2_o_maxp = nullptr;
+	int32_t *d2_run_start = nullptr, *d2_run_count = nullptr, *d2_o_seq = nullptr, *d2_o_start = nullptr;
+	int64_t *d2_off = nullptr;
+	int64_t d2_rows = 0, d2_rows_post = 0, d2_rows_runs = 0, d2_cap_o = 0;
+	int d2_cap_chunks = 0;
+	uint32_t dec_what = 0;       // what the last psmc_b200_decode_run produced
+	float dec_ms[3] = {};        // E-step, decode kernel (+ run compaction), whole call (wall)
+	std::vector<int32_t> r_seq, r_start, r_len; // merged runs of the last decode_run, in (sequence, position) order
+	std::vector<uint8_t> r_state;
+	std::vector<double> r_maxp;
 	// pinned host staging
 	double *h_model = nullptr, *h_stats = nullptr;
 	uint32_t *h_obs = nullptr; // packed observations (pinned), words_obs 32-bit words
@@ -256,6 +273,9 @@ static void free_ctx(psmc_b200_ctx *c)
 	cudaFree(c->d_stats);
 	cudaFree(c->d_ghat); cudaFree(c->d_cpart); cudaFree(c->d_cdense);
 	cudaFree(c->d_bestk); cudaFree(c->d_bestp); cudaFree(c->d_post); cudaFree(c->d_prec);
+	cudaFree(c->d2_bestk); cudaFree(c->d2_run_state); cudaFree(c->d2_o_state); cudaFree(c->d2_bestp); cudaFree(c->d2_post);
+	cudaFree(c->d2_prec); cudaFree(c->d2_run_maxp); cudaFree(c->d2_o_maxp); cudaFree(c->d2_run_start); cudaFree(c->d2_run_count);
+	cudaFree(c->d2_o_seq); cudaFree(c->d2_o_start); cudaFree(c->d2_off);
 	if (c->h_model) cudaFreeHost(c->h_model);
 	if (c->h_stats) cudaFreeHost(c->h_stats);
 	if (c->h_obs) cudaFreeHost(c->h_obs);
@@ -320,7 +340,19 @@ static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 	for (int i = 0; i < c->n_seqs; ++i)
 		for (int64_t u = 0; u < c->L[i]; u += step)
 			jobs.push_back({sp[i], u, std::min<int64_t>(u + step, c->L[i]), c->h_obs + c->seq_ow0[i]});
-	unsigned nt = std::min<unsigned>(16, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+	// threads: the cores this process may use (affinity mask), shared with the other local ranks of a multi-process job
+	unsigned cores = std::max<unsigned>(1, std::thread::hardware_concurrency());
+#if !defined(PSMC_SIMT_EMU) && defined(__linux__)
+	{
+		cpu_set_t set;
+		if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = std::min<unsigned>(cores, (unsigned)CPU_COUNT(&set));
+	}
+#endif
+	{
+		const char *lws = getenv("LOCAL_WORLD_SIZE");
+		if (lws && atoi(lws) > 1) cores = std::max<unsigned>(1, cores / (unsigned)atoi(lws));
+	}
+	unsigned nt = std::min<unsigned>(16, cores);
 	if (jobs.size() < 4) nt = 1;
 	if (nt == 1) {
 		for (auto &j : jobs) pack_range(j.s, j.u0, j.u1, j.dst);
@@ -1394,6 +1426,153 @@ extern "C" int psmc_b200_decode(psmc_b200_ctx *c, const psmc_b200_model *model, 
 	return 0;
 }
 
+// ---- decoding of every sequence of the context on the fast path ------------------------------------------------------
+template <int NP>
+static void launch_decode2(psmc_b200_ctx *c, const Chunk *chunks, int n, const double *bdir, uint32_t what)
+{
+	constexpr int G = (NP == 32) ? 8 : 16, SPL = NP / G;
+	const bool bins = (what & (PSMC_B200_DEC_BINS | PSMC_B200_DEC_POST)) != 0, post = (what & PSMC_B200_DEC_POST) != 0, runs = (what & PSMC_B200_DEC_RUNS) != 0;
+	LAUNCH((k_decode2<SPL, G>), blocks_for(n, G), 128, c->stream, chunks, 0, n, c->d_obs, c->d_model, bdir, c->d_fhat, c->d_sc, c->N, (int64_t)0,
+	       bins ? c->d2_bestk : nullptr, bins ? c->d2_bestp : nullptr, post ? c->d2_post : nullptr, post ? c->d2_prec : nullptr,
+	       runs ? c->d2_run_start : nullptr, runs ? c->d2_run_state : nullptr, runs ? c->d2_run_maxp : nullptr, runs ? c->d2_run_count : nullptr);
+}
+
+extern "C" int psmc_b200_decode_run(psmc_b200_ctx *c, const psmc_b200_model *model, uint32_t what)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (c->batch) return set_err(PSMC_B200_EINVAL, "decode needs single-model mode (psmc_b200_set_multiplicity leaves batch mode)");
+	if (!(what & (PSMC_B200_DEC_RUNS | PSMC_B200_DEC_BINS | PSMC_B200_DEC_POST))) return set_err(PSMC_B200_EINVAL, "nothing asked for");
+	const auto t_wall = std::chrono::steady_clock::now();
+	// 1. a complete E-step on this model: exact forward spill + certified boundary directions (counts are a by-product)
+	int rc = launch_models(c, 1, model);
+	if (rc) return rc;
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	rc = sync_and_certify(c);
+	if (rc) return rc;
+	collect_times(c, true);
+	c->launched = false;
+	c->dec_ms[0] = c->ms[5];
+	c->dec_what = 0;
+	c->r_seq.clear(); c->r_start.clear(); c->r_len.clear(); c->r_state.clear(); c->r_maxp.clear();
+	// which plan holds the certified directions: the fast path's backward plan (bwarm), else the boundary chains of the main plan (bend)
+	const Chunk *chunks = c->mode_warm ? c->d_chunks_b : c->d_chunks;
+	const int n = c->mode_warm ? c->n_chunks_b : c->n_chunks;
+	const double *bdir = c->mode_warm ? c->d_bwarm : c->d_bend;
+	const int64_t rows = std::max<int64_t>(c->cap_bins, 1);
+#define DALLOC(ptr, type, count)                                                                                      \
+	do {                                                                                                              \
+		cudaFree(ptr); ptr = nullptr;                                                                                 \
+		CUDA_TRY(cudaMalloc((void **)&(ptr), sizeof(type) * (size_t)(count)), PSMC_B200_ECUDA);                       \
+	} while (0)
+	if ((what & (PSMC_B200_DEC_BINS | PSMC_B200_DEC_POST)) && c->d2_rows < rows) {
+		DALLOC(c->d2_bestk, uint8_t, rows); DALLOC(c->d2_bestp, float, rows);
+		c->d2_rows = rows;
+	}
+	if ((what & PSMC_B200_DEC_POST) && c->d2_rows_post < rows) {
+		DALLOC(c->d2_post, float, (size_t)rows * c->N); DALLOC(c->d2_prec, double, rows);
+		c->d2_rows_post = rows;
+	}
+	if ((what & PSMC_B200_DEC_RUNS) && c->d2_rows_runs < rows) {
+		DALLOC(c->d2_run_start, int32_t, rows); DALLOC(c->d2_run_state, uint8_t, rows); DALLOC(c->d2_run_maxp, double, rows);
+		c->d2_rows_runs = rows;
+	}
+	const int nmax = std::max(std::max(c->n_chunks, c->n_chunks_b), 1);
+	if ((what & PSMC_B200_DEC_RUNS) && c->d2_cap_chunks < nmax) {
+		DALLOC(c->d2_run_count, int32_t, nmax); DALLOC(c->d2_off, int64_t, nmax);
+		c->d2_cap_chunks = nmax;
+	}
+	cudaEventRecord(c->ev[0], c->stream);
+	if (n > 0) {
+		switch (c->NP) {
+		case 32: launch_decode2<32>(c, chunks, n, bdir, what); break;
+		case 64: launch_decode2<64>(c, chunks, n, bdir, what); break;
+		default: launch_decode2<128>(c, chunks, n, bdir, what); break;
+		}
+	}
+	CUDA_TRY(cudaGetLastError(), PSMC_B200_ECUDA);
+	if ((what & PSMC_B200_DEC_RUNS) && n > 0) {
+		// 2. compact the runs: per-chunk counts -> offsets (host: a few thousand numbers) -> dense list -> host, merged across chunk boundaries
+		std::vector<int32_t> cnt((size_t)n);
+		std::vector<int64_t> off((size_t)n);
+		CUDA_TRY(cudaMemcpyAsync(cnt.data(), c->d2_run_count, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+		int64_t tot = 0;
+		for (int i = 0; i < n; ++i) { off[i] = tot; tot += cnt[i]; }
+		if (c->d2_cap_o < tot) {
+			DALLOC(c->d2_o_seq, int32_t, tot); DALLOC(c->d2_o_start, int32_t, tot); DALLOC(c->d2_o_state, uint8_t, tot); DALLOC(c->d2_o_maxp, double, tot);
+			c->d2_cap_o = tot;
+		}
+		CUDA_TRY(cudaMemcpyAsync(c->d2_off, off.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+		LAUNCH((k_runs_gather), std::min(n, 8 * c->sm_count), 128, c->stream, chunks, n, (int64_t)0, c->d2_run_count, c->d2_off, c->d2_run_start, c->d2_run_state,
+		       c->d2_run_maxp, c->d2_o_seq, c->d2_o_start, c->d2_o_state, c->d2_o_maxp);
+		std::vector<int32_t> q((size_t)tot), st((size_t)tot);
+		std::vector<uint8_t> ks((size_t)tot);
+		std::vector<double> mp((size_t)tot);
+		CUDA_TRY(cudaMemcpyAsync(q.data(), c->d2_o_seq, sizeof(int32_t) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMemcpyAsync(st.data(), c->d2_o_start, sizeof(int32_t) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMemcpyAsync(ks.data(), c->d2_o_state, sizeof(uint8_t) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+		CUDA_TRY(cudaMemcpyAsync(mp.data(), c->d2_o_maxp, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+		cudaEventRecord(c->ev[1], c->stream);
+		CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+		std::vector<int32_t> given_of((size_t)std::max(c->n_seqs, 1), -1);
+		for (int i = 0; i < c->n_seqs_given; ++i)
+			if (c->kept_of[i] >= 0) given_of[c->kept_of[i]] = i;
+		for (int64_t i = 0; i < tot; ++i) { // a run that continues across a chunk boundary was emitted in two pieces
+			if (!c->r_seq.empty() && c->r_seq.back() == given_of[q[i]] && c->r_state.back() == ks[i]) {
+				if (mp[i] > c->r_maxp.back()) c->r_maxp.back() = mp[i];
+				continue;
+			}
+			c->r_seq.push_back(given_of[q[i]]); c->r_start.push_back(st[i]); c->r_state.push_back(ks[i]); c->r_maxp.push_back(mp[i]);
+		}
+		c->r_len.resize(c->r_seq.size());
+		for (size_t i = 0; i < c->r_seq.size(); ++i) {
+			const bool more = i + 1 < c->r_seq.size() && c->r_seq[i + 1] == c->r_seq[i];
+			c->r_len[i] = (more ? c->r_start[i + 1] : c->L[c->kept_of[c->r_seq[i]]]) - c->r_start[i];
+		}
+	} else {
+		cudaEventRecord(c->ev[1], c->stream);
+		CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	}
+#undef DALLOC
+	cudaEventElapsedTime(&c->dec_ms[1], c->ev[0], c->ev[1]);
+	c->dec_ms[2] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_wall).count();
+	c->dec_what = what;
+	return 0;
+}
+
+extern "C" int psmc_b200_decode_get_runs(psmc_b200_ctx *c, int64_t cap, int32_t *seq_id, int32_t *start, int32_t *len, uint8_t *state,
+                                         double *max_p, int64_t *n_runs)
+{
+	if (!c || !n_runs) return set_err(PSMC_B200_EINVAL, "NULL argument");
+	if (!(c->dec_what & PSMC_B200_DEC_RUNS)) return set_err(PSMC_B200_EINVAL, "no runs: call psmc_b200_decode_run(ctx, model, PSMC_B200_DEC_RUNS) first");
+	const int64_t n = (int64_t)c->r_seq.size();
+	*n_runs = n;
+	if (cap < n) return cap == 0 ? 0 : set_err(PSMC_B200_EINVAL, "capacity %lld < %lld runs", (long long)cap, (long long)n);
+	if (n > 0 && (!seq_id || !start || !len || !state || !max_p)) return set_err(PSMC_B200_EINVAL, "NULL output arrays");
+	for (int64_t i = 0; i < n; ++i) { seq_id[i] = c->r_seq[i]; start[i] = c->r_start[i]; len[i] = c->r_len[i]; state[i] = c->r_state[i]; max_p[i] = c->r_maxp[i]; }
+	return 0;
+}
+
+extern "C" int psmc_b200_decode_get_bins(psmc_b200_ctx *c, int32_t seq_id, uint8_t *best_k, float *best_p, float *post, double *p_recomb)
+{
+	if (!c) return set_err(PSMC_B200_EINVAL, "ctx is NULL");
+	if (seq_id < 0 || seq_id >= c->n_seqs_given) return set_err(PSMC_B200_EINVAL, "seq_id out of range");
+	if (c->kept_of[seq_id] < 0) return set_err(PSMC_B200_EINVAL, "record %d is empty: nothing to decode", seq_id);
+	const bool want_post = post || p_recomb;
+	if (!(c->dec_what & (PSMC_B200_DEC_BINS | PSMC_B200_DEC_POST)) || (want_post && !(c->dec_what & PSMC_B200_DEC_POST)))
+		return set_err(PSMC_B200_EINVAL, "not computed: call psmc_b200_decode_run with PSMC_B200_DEC_BINS / PSMC_B200_DEC_POST first");
+	const int k = c->kept_of[seq_id];
+	if (c->mult[k] <= 0) return set_err(PSMC_B200_EINVAL, "sequence %d has multiplicity 0 (psmc_b200_set_multiplicity)", seq_id);
+	const size_t r0 = (size_t)c->seq_gb0[k], Ls = (size_t)c->L[k];
+	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
+	if (best_k) CUDA_TRY(cudaMemcpyAsync(best_k, c->d2_bestk + r0, Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	if (best_p) CUDA_TRY(cudaMemcpyAsync(best_p, c->d2_bestp + r0, sizeof(float) * Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	if (post) CUDA_TRY(cudaMemcpyAsync(post, c->d2_post + r0 * c->N, sizeof(float) * Ls * c->N, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	if (p_recomb) CUDA_TRY(cudaMemcpyAsync(p_recomb, c->d2_prec + r0, sizeof(double) * Ls, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
+	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	return 0;
+}
+
 // ---- dense transition counts (option) ----
 extern "C" int psmc_b200_set_dense(psmc_b200_ctx *c, int32_t on)
 {
@@ -1497,6 +1676,7 @@ extern "C" int psmc_b200_get_info(const psmc_b200_ctx *c, psmc_b200_info *info)
 	info->n_seqs_effective = c->n_seq_eff;
 	info->n_models = c->n_rep;
 	info->repair_rounds = c->rounds_cur;
+	for (int i = 0; i < 3; ++i) info->decode_ms[i] = c->dec_ms[i];
 	info->warm_redos = c->warm_redos;
 	info->n_chunks_bwd = c->n_chunks_b;
 	info->chunk_len_bwd = c->chunk_len_b;

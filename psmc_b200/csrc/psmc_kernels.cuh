@@ -1790,6 +1790,244 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ part,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6b: decoding on the generation-2 lane groups, for EVERY chunk of the plan at once (aux.c:150-201, khmm.c:264-293).
+// Runs after a complete, certified E-step on the same model: fhat / sc hold the exact forward pass and bdir[c] the exact
+// direction of b at the last bin of chunk c (the fast path's certified bwarm, or the boundary chain's bend), so every
+// chunk decodes independently.  Per transition u-1 -> u the posterior of bin u-1 is f_{u-1} (A diag(e_u) b_u) -- the same
+// quantity the counting kernel accumulates (khmm.c:317) -- so a step is one DualScan plus an argmax over the group.
+// Outputs, all optional: per bin the posterior-argmax state (uint8) and its posterior (float), the full posterior row
+// (float) and the recombination probability (double, aux.c:188-193); and, written by the group's first lane, the RUNS of
+// the argmax state with their maximum posterior (what `psmc -d` prints, aux.c:165-182): run j of chunk c goes to entry
+// gb0 + j of the run arrays (at most one run per bin), in the order the kernel meets them, i.e. right to left.
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G>
+struct DecodeRun {
+	static constexpr int NP = SPL * G, PF = 4;
+	const Chunk &ch;
+	const LaneModel<SPL> &M;
+	const bool valid;
+	const int gl, s0, ulast, N;
+	const uint32_t *__restrict__ obs;
+	const double *__restrict__ frow, *__restrict__ srow; // row of bin ulast
+	uint8_t *__restrict__ best_k;
+	float *__restrict__ best_p, *__restrict__ post;
+	double *__restrict__ p_recomb;
+	int32_t *__restrict__ run_start;
+	uint8_t *__restrict__ run_state;
+	double *__restrict__ run_maxp;
+	const int64_t obase; // output entry of bin u: gb0 - out_base + (u - u0)
+	DualScan<G> ds;
+	double nf[PF][SPL], ns[PF];
+	uint32_t word, wprev;
+	int xu, cur_state, n_runs, ulo;
+	double cur_max;
+
+	__device__ __forceinline__ DecodeRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_, int N_, const uint32_t *__restrict__ obs_,
+	                                     const double *__restrict__ fhat, const double *__restrict__ sc, int64_t out_base, uint8_t *bk, float *bp, float *po,
+	                                     double *pr, int32_t *rs, uint8_t *rk, double *rm)
+	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), ulast(ch_.u0 + ch_.len - 1), N(N_), obs(obs_),
+	      frow(fhat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL), srow(sc + ch_.gb0 + (ch_.len - 1)), best_k(bk), best_p(bp), post(po),
+	      p_recomb(pr), run_start(rs), run_state(rk), run_maxp(rm), obase(ch_.gb0 - out_base - ch_.u0)
+	{
+	}
+
+	// posterior row of bin v is in gam (this lane's states); act: the bin belongs to this group's chunk
+	__device__ __forceinline__ void emit(int v, const double (&gam)[SPL], bool act)
+	{
+		double bv = -1.0;
+		int ba = 0x7fffffff;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i)
+			if (s0 + i < N && gam[i] > bv) { // first maximum wins (khmm.c:270-275)
+				bv = gam[i];
+				ba = s0 + i;
+			}
+#pragma unroll
+		for (int d = G >> 1; d > 0; d >>= 1) {
+			const double ov = __shfl_xor_sync(FULLMASK, bv, d, G);
+			const int oa = __shfl_xor_sync(FULLMASK, ba, d, G);
+			if (ov > bv || (ov == bv && oa < ba)) {
+				bv = ov;
+				ba = oa;
+			}
+		}
+		if (!act) return;
+		const int64_t o = obase + v;
+		if (post) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i)
+				if (s0 + i < N) post[(size_t)o * N + s0 + i] = (float)gam[i];
+		}
+		if (gl == 0) {
+			if (best_k) {
+				best_k[o] = (uint8_t)ba;
+				best_p[o] = (float)bv;
+			}
+			if (run_start) {
+				if (v == ulast) {
+					cur_state = ba;
+					cur_max = bv;
+				} else if (ba != cur_state) { // the run that started at bin v + 1 is complete
+					const int64_t e = obase + ch.u0 + n_runs; // = gb0 - out_base + n_runs
+					run_start[e] = v + 1;
+					run_state[e] = (uint8_t)cur_state;
+					run_maxp[e] = cur_max;
+					++n_runs;
+					cur_state = ba;
+					cur_max = bv;
+				} else if (bv > cur_max) {
+					cur_max = bv;
+				}
+			}
+		}
+	}
+
+	template <int J>
+	__device__ __forceinline__ void step(int t, double (&b)[SPL])
+	{
+		const int u = ulast - t;            // transition u-1 -> u: yields the posterior of bin u-1
+		const bool act = valid && u > ch.u0; // (bin u-1 belongs to this chunk)
+		const bool actp = valid && u > ulo;  // recombination probability of bin u-1: also across the boundary to the left neighbour
+		double fm[SPL];
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) fm[i] = nf[J][i];
+		const double sm = ns[J];
+		if (valid && u - 1 - PF >= ulo) { // (no other rows of the left neighbour are needed)
+			const size_t back = (size_t)(t + 1 + PF);
+			load_vec<SPL>(frow - back * NP, nf[J]);
+			ns[J] = __ldg(srow - back);
+		}
+		const int v = u - 1;
+		int xm = 2;
+		if (act) {
+			if (t > 0 && (v & 15) == 15) {
+				word = wprev;
+				wprev = __ldg(obs + ch.ow0 + max((v >> 4) - 1, 0));
+			}
+			xm = (word >> ((v & 15) * 2)) & 3;
+		}
+		double g[SPL], Pg[SPL], Sg[SPL], gam[SPL], c0, c1;
+		emis_coef(xu, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
+		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);
+		const double inv = fast_rcp(act ? sm : 1.0);
+		double tr = 0.0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i])); // = b_{u-1} s_{u-1} (khmm.c:230-234)
+			gam[i] = fm[i] * bb;                                                   // posterior of bin u-1
+			tr = fma(fm[i] * M.D[i], g[i], tr);                                    // no-recombination mass (aux.c:188-191)
+			if (act) b[i] = bb * inv;
+		}
+		if (p_recomb) {
+			tr = gsum<G>(tr);
+			if (actp && gl == 0) p_recomb[obase + v] = 1.0 - tr;
+		}
+		emit(v, gam, act);
+		if (act) xu = xm;
+	}
+
+	__device__ __forceinline__ void run(double (&b)[SPL])
+	{
+		// lowest bin whose row is read: the chunk's first bin, or (recombination probability asked, not the first chunk of
+		// its sequence) the left neighbour's last bin
+		ulo = (p_recomb && !(ch.flags & CH_FIRST)) ? ch.u0 - 1 : ch.u0;
+#pragma unroll
+		for (int j = 0; j < PF; ++j) {
+			if (valid && ulast - 1 - j >= ulo) {
+				load_vec<SPL>(frow - (size_t)(1 + j) * NP, nf[j]);
+				ns[j] = __ldg(srow - (1 + j));
+			} else {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) nf[j][i] = 0.0;
+				ns[j] = 1.0;
+			}
+		}
+		ds.init(gl);
+		n_runs = 0;
+		cur_state = 0;
+		cur_max = 0.0;
+		xu = (__ldg(obs + ch.ow0 + (ulast >> 4)) >> ((ulast & 15) * 2)) & 3;
+		const int v0 = max(ulast - 1, 0);
+		word = __ldg(obs + ch.ow0 + (v0 >> 4));
+		wprev = __ldg(obs + ch.ow0 + max((v0 >> 4) - 1, 0));
+		{ // the chunk's last bin: posterior = f b s (khmm.c:274); nothing follows it inside this chunk
+			double fu[SPL], gam[SPL];
+			load_vec<SPL>(frow, fu);
+			const double su = __ldg(srow);
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) gam[i] = fu[i] * b[i] * su;
+			if (p_recomb && valid && gl == 0 && (ch.flags & CH_LAST)) p_recomb[obase + ulast] = 0.0; // aux.c:194
+			emit(ulast, gam, valid);
+		}
+		const int trips = (warp_trips(valid ? ulast - ulo : 0) + PF - 1) / PF * PF;
+		for (int t = 0; t < trips; t += PF) {
+			step<0>(t, b);
+			step<1>(t + 1, b);
+			step<2>(t + 2, b);
+			step<3>(t + 3, b);
+		}
+		if (valid && gl == 0 && run_start) { // the run that reaches the chunk's first bin
+			const int64_t e = obase + ch.u0 + n_runs;
+			run_start[e] = ch.u0;
+			run_state[e] = (uint8_t)cur_state;
+			run_maxp[e] = cur_max;
+			++n_runs;
+		}
+	}
+};
+
+template <int SPL, int G>
+__global__ void __launch_bounds__(128) k_decode2(const Chunk *__restrict__ chunks, int c_first, int n_chunks, const uint32_t *__restrict__ obs,
+                                                 const double *__restrict__ model, const double *__restrict__ bdir,
+                                                 const double *__restrict__ fhat, const double *__restrict__ sc, int N, int64_t out_base,
+                                                 uint8_t *__restrict__ best_k, float *__restrict__ best_p, float *__restrict__ post,
+                                                 double *__restrict__ p_recomb, int32_t *__restrict__ run_start, uint8_t *__restrict__ run_state,
+                                                 double *__restrict__ run_maxp, int32_t *__restrict__ run_count)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = c_first + id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
+	double beta[SPL], b[SPL];
+	load_vec<SPL>(bdir + (size_t)c * NP + s0, beta);
+	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc); // b of the chunk's last bin in the reference's scaling
+	if (ch.flags & CH_LAST) { // khmm.c:226: b_L[k] = 1/s_L
+		const double v = 1.0 / __ldg(sc + ch.gb0 + (ch.len - 1));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = v;
+	}
+	DecodeRun<SPL, G> r(ch, id.valid, M, gl, N, obs, fhat, sc, out_base, best_k, best_p, post, p_recomb, run_start, run_state, run_maxp);
+	r.run(b);
+	if (id.valid && gl == 0 && run_count) run_count[c] = r.n_runs;
+}
+
+// dense list of runs: chunk c's runs (stored right to left at gb0 - out_base + j) go, left to right, to off[c] ...
+__global__ void __launch_bounds__(128) k_runs_gather(const Chunk *__restrict__ chunks, int n_chunks, int64_t out_base, const int32_t *__restrict__ run_count,
+                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ run_start,
+                                                     const uint8_t *__restrict__ run_state, const double *__restrict__ run_maxp,
+                                                     int32_t *__restrict__ o_seq, int32_t *__restrict__ o_start, uint8_t *__restrict__ o_state,
+                                                     double *__restrict__ o_maxp)
+{
+	for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+		const Chunk ch = chunks[c];
+		const int n = run_count[c];
+		const int64_t src = ch.gb0 - out_base, dst = off[c];
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+			const int64_t e = src + (n - 1 - j);
+			o_seq[dst + j] = ch.seq;
+			o_start[dst + j] = run_start[e];
+			o_state[dst + j] = run_state[e];
+			o_maxp[dst + j] = run_maxp[e];
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: decode backward.  One warp per chunk of ONE sequence: posterior argmax / max, optional full
 // posterior and recombination probability (aux.c:167-200, khmm.c:264-293).
 // ------------------------------------------------------------------------------------------------

@@ -158,6 +158,41 @@ class EStep:
                                                   _d(s) if want_s else None))
         return dict(best_k=bk, best_p=bp, post=post, p_recomb=pr, s=s)
 
+    DEC_RUNS, DEC_BINS, DEC_POST = 1, 2, 4
+
+    def decode_all(self, model, runs=True, bins=False, post=False):
+        """whole-context decoding on the fast path (psmc_b200_decode_run); returns dict(runs=..., seqs=[per-record dicts])"""
+        what = (self.DEC_RUNS if runs else 0) | (self.DEC_BINS if bins else 0) | (self.DEC_POST if post else 0)
+        m = model.c_struct()
+        check(self.lib, self.lib.psmc_b200_decode_run(self.h, C.byref(m), what))
+        out = {}
+        if runs:
+            n = C.c_int64()
+            check(self.lib, self.lib.psmc_b200_decode_get_runs(self.h, 0, None, None, None, None, None, C.byref(n)))
+            k = max(int(n.value), 1)
+            sq = np.zeros(k, dtype=np.int32); st = np.zeros(k, dtype=np.int32); ln = np.zeros(k, dtype=np.int32)
+            ks = np.zeros(k, dtype=np.uint8); mp = np.zeros(k)
+            ip = C.POINTER(C.c_int32)
+            check(self.lib, self.lib.psmc_b200_decode_get_runs(self.h, k, sq.ctypes.data_as(ip), st.ctypes.data_as(ip), ln.ctypes.data_as(ip),
+                                                               ks.ctypes.data_as(C.POINTER(C.c_uint8)), _d(mp), C.byref(n)))
+            k = int(n.value)
+            out["runs"] = dict(seq=sq[:k], start=st[:k], len=ln[:k], state=ks[:k], max_p=mp[:k])
+        if bins or post:
+            out["seqs"] = []
+            for i, L in enumerate(self.L):
+                if L == 0:
+                    out["seqs"].append(None)
+                    continue
+                bk = np.zeros(L, dtype=np.uint8); bp = np.zeros(L, dtype=np.float32)
+                po = np.zeros((L, self.N), dtype=np.float32) if post else None
+                pr = np.zeros(L) if post else None
+                check(self.lib, self.lib.psmc_b200_decode_get_bins(self.h, i, bk.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                                   bp.ctypes.data_as(C.POINTER(C.c_float)),
+                                                                   po.ctypes.data_as(C.POINTER(C.c_float)) if post else None,
+                                                                   _d(pr) if post else None))
+                out["seqs"].append(dict(best_k=bk, best_p=bp, post=po, p_recomb=pr))
+        return out
+
     def set_multiplicity(self, mult=None):
         """bootstrap replicate = multiplicity of every resident record (aux.c:8-47); None restores 1 everywhere"""
         if mult is None:

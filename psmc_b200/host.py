@@ -188,6 +188,13 @@ class EMSession:
         raw = np.ascontiguousarray(raw, dtype=np.float64)
         self._chk(self.L.psmch_py_em_set_raw(self.h, _d(raw), n_seqs_total))
 
+    def set_params(self, params):
+        """install parameters (the result of an M-step that ran on another rank); the model is recomputed from them"""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        assert p.shape == (self.n_params,)
+        self.L.psmch_py_em_set_params.argtypes = [C.c_void_p, _dp]
+        self._chk(self.L.psmch_py_em_set_params(self.h, _d(p)))
+
     def state(self):
         sc = np.zeros(10)
         self.L.psmch_py_em_scalars(self.h, _d(sc))

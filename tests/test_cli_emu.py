@@ -77,3 +77,29 @@ def test_emulated_batched_replicates_equal_one_at_a_time(emu_env, tmp_path):
     assert sum(1 for l in bat if l.startswith("RD")) == 12
     assert bat == one
     assert two == one
+
+
+def test_emulated_cli_decode_modes_match_reference(emu_env, tmp_path):
+    """-d (runs compacted on the device), -D (float rows, hand-rolled %.4f on a thread pool) and -s against the
+    reference's own output for the same fixed parameters"""
+    import gzip
+    import numpy as np
+    fa, par = os.path.join(G, "c1.psmcfa.gz"), os.path.join(G, "c1_params.txt")
+    got = run(["-N0", "-i", par, "-d", "--chunk", "700", fa], emu_env, str(tmp_path / "d.psmc"))
+    want = parse(os.path.join(G, "c1_decode.psmc"))
+    assert [l for l in got if l.startswith("TC")] == [l for l in want if l.startswith("TC")]
+    dc_g = [l for l in got if l.startswith("DC")]; dc_w = [l for l in want if l.startswith("DC")]
+    same = sum(a == b for a, b in zip(dc_g, dc_w))
+    assert len(dc_g) == len(dc_w) and same >= 0.995 * len(dc_w), (len(dc_g), len(dc_w), same)
+    assert [l for l in got if l[:2] not in ("TC", "DC")] == [l for l in want if l[:2] not in ("TC", "DC")]
+    got = run(["-N0", "-i", par, "-D", "--chunk", "700", fa], emu_env, str(tmp_path / "D.psmc"))
+    want = gzip.open(os.path.join(G, "c1_fulldecode.psmc.gz"), "rt").read().splitlines()
+    df_g = [l for l in got if l.startswith("DF")]; df_w = [l for l in want if l.startswith("DF")]
+    assert len(df_g) == len(df_w) == 10000
+    A = np.array([[float(x) for x in l.split("\t")[1:]] for l in df_g])
+    B = np.array([[float(x) for x in l.split("\t")[1:]] for l in df_w])
+    assert np.array_equal(A[:, 0], B[:, 0])
+    assert np.max(np.abs(A[:, 1] - B[:, 1])) <= 2e-6           # recombination probability, %lf
+    assert np.max(np.abs(A[:, 2:] - B[:, 2:])) <= 1.0001e-4    # posteriors, %.4f
+    assert np.mean(A[:, 2:] == B[:, 2:]) > 0.999               # (float rows: the last printed digit may differ at a rounding boundary)
+    assert all(len(l.split("\t")[2]) >= 8 for l in df_g[:50])  # %lf keeps six decimals

@@ -264,3 +264,96 @@ def test_benchmark_regime_matches_unmodified_reference(ref, L, seed):
             assert info["fallbacks"] == 0
             assert info["warm_len"] > 0 and info["n_chunks"] > 900      # the default plan: one resident wave, fast path
             assert info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
+
+
+def test_decode_counts_records_as_given(oracle):
+    """seq_id of psmc_b200_decode indexes the records as given to create: an empty record in front must not shift it"""
+    from psmc_b200 import EStep, Psmc200Error
+    N = 23
+    m = make_model(oracle, N, seed=23)
+    a, b = _seqs(m, [3000, 4111], seed=24)
+    with EStep([np.zeros(0, dtype=np.int8), a, b], N, chunk_len=500) as es:
+        mod = _model(m)
+        with pytest.raises(Psmc200Error):
+            es.decode(mod, 0)
+        for i, s in ((1, a), (2, b)):
+            got = es.decode(mod, i, full=False)
+            want = oracle.decode(m["a"], m["e"], m["a0"], s, full=False)
+            assert len(got["best_p"]) == len(s) and np.max(np.abs(got["best_p"] - want["best_p"])) < 1e-11
+
+
+def _runs_of(best_k, best_p):
+    out, start = [], 0
+    for u in range(1, len(best_k) + 1):
+        if u == len(best_k) or best_k[u] != best_k[start]:
+            out.append((start, u - start, int(best_k[start]), float(best_p[start:u].max())))
+            start = u
+    return out
+
+
+@pytest.mark.parametrize("N,chunk_len,warm", [(23, 1000, 0), (64, 997, 3000), (64, 0, -1), (100, 640, 2000)])
+def test_decode_all_runs_bins_and_posteriors(oracle, N, chunk_len, warm):
+    """whole-context decoding on the fast path (psmc_b200_decode_run): runs compacted on the device (-d), uint8 / float
+    per-bin outputs and float posterior rows (-D), against the oracle's double-precision decode"""
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=121)
+    a, b, c3 = _seqs(m, [60000, 1, 7333], seed=122)
+    seqs = [a, np.zeros(0, dtype=np.int8), b, c3]
+    with EStep(seqs, N, chunk_len=chunk_len) as es:
+        if warm >= 0:
+            es.set_warm(warm)
+        got = es.decode_all(_model(m), runs=True, bins=True, post=True)
+        info = es.info()
+    assert info["fallbacks"] == 0
+    runs = got["runs"]
+    for i, s in enumerate(seqs):
+        if len(s) == 0:
+            assert got["seqs"][i] is None and not (runs["seq"] == i).any()
+            continue
+        want = oracle.decode(m["a"], m["e"], m["a0"], s, full=True)
+        g = got["seqs"][i]
+        assert np.max(np.abs(g["post"] - want["post"])) < 2e-7
+        assert np.max(np.abs(g["p_recomb"] - want["p_recomb"])) < 1e-10
+        assert np.max(np.abs(g["best_p"] - want["best_p"])) < 2e-7
+        diff = g["best_k"] != want["best_k"]
+        if diff.any():
+            srt = np.sort(want["post"][diff], axis=1)
+            assert np.all(srt[:, -1] - srt[:, -2] < 1e-10)
+        sel = runs["seq"] == i
+        mine = list(zip(runs["start"][sel], runs["len"][sel], runs["state"][sel], runs["max_p"][sel]))
+        ref_runs = _runs_of(g["best_k"], want["best_p"] if not diff.any() else g["best_p"].astype(np.float64))
+        assert [(x[0], x[1], x[2]) for x in mine] == [(x[0], x[1], x[2]) for x in ref_runs]
+        assert max(abs(x[3] - y[3]) for x, y in zip(mine, ref_runs)) < (1e-10 if not diff.any() else 2e-7)
+
+
+@pytest.mark.parametrize("chunk_len", [1500, 0])
+def test_batch_of_models_matches_oracle_and_single_runs(oracle, chunk_len):
+    """psmc_b200_set_batch: several models, each over its own multiset of the resident records, in one launch sequence"""
+    from psmc_b200 import EStep
+    N = 64
+    ms = [make_model(oracle, N, seed=81 + r) for r in range(4)]
+    seqs = _seqs(ms[0], [30000, 14000, 1, 22000, 9000], seed=82)
+    rng = np.random.default_rng(5)
+    mults = rng.integers(0, 3, size=(4, 5)).astype(np.int32)
+    mults[:, 0] = [1, 0, 2, 1]
+    with EStep(seqs, N, chunk_len=chunk_len) as es:
+        es.set_warm(3000)
+        es.set_batch(mults)
+        got = es.run_batch([_model(m) for m in ms])
+        got2 = es.run_batch([_model(m) for m in ms])
+        assert es.info()["fallbacks"] == 0 and es.info()["n_models"] == 4
+        alone = []
+        for r in range(4):
+            es.set_multiplicity(mults[r])
+            alone.append(es.run(_model(ms[r])))
+    for r in range(4):
+        expanded = [s for s, k in zip(seqs, mults[r]) for _ in range(k)]
+        want = oracle_stats(oracle, ms[r], expanded)
+        compare_stats(got[r], want, TOL, N)
+        compare_stats(got2[r], want, TOL, N)
+        if chunk_len > 0:
+            assert got[r]["LL"] == alone[r]["LL"]
+            for k in ("E", "RL", "CL", "RU", "CU", "AD"):
+                assert np.array_equal(got[r][k], alone[r][k]), k
+        else:
+            compare_stats(got[r], alone[r], 1e-11, N)

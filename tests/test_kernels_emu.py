@@ -290,3 +290,50 @@ def test_emulated_deep_repair_cascade_stays_on_the_fast_path(oracle, emu_plain):
     assert rounds[-1][2] == 0, rounds             # never the exact fallback
     assert rounds[-1][1] == 1, rounds             # one retry on the fast path (first E-step), none afterwards
     assert rounds[-1][0] > 3, rounds              # the cascade was deeper than the default three rounds: adapted
+
+
+def _runs_of(best_k, best_p):
+    """reference semantics of the DC lines (aux.c:165-182): runs of the argmax state with their maximum posterior"""
+    out = []
+    start = 0
+    for u in range(1, len(best_k) + 1):
+        if u == len(best_k) or best_k[u] != best_k[start]:
+            out.append((start, u - start, int(best_k[start]), float(best_p[start:u].max())))
+            start = u
+    return out
+
+
+@pytest.mark.parametrize("N,chunk_len,warm", [(23, 100, 0), (64, 97, 250), (64, 1 << 20, 250), (100, 64, 150)])
+def test_emulated_decode_all_runs_bins_and_posteriors(oracle, emu_plain, N, chunk_len, warm):
+    """whole-context decoding on the generation-2 kernels and the fast path: runs compacted on the device (-d), per-bin
+    uint8 / float outputs and full posterior rows (-D), against the oracle's double-precision decode"""
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=121)
+    a, b, c3 = _seqs(m, [900, 1, 333], seed=122)
+    seqs = [a, np.zeros(0, dtype=np.int8), b, c3]
+    with EStep(seqs, N, chunk_len=chunk_len) as es:
+        es.set_warm(warm)
+        got = es.decode_all(_model(m), runs=True, bins=True, post=True)
+        info = es.info()
+    assert info["fallbacks"] == 0
+    runs = got["runs"]
+    for i, s in enumerate(seqs):
+        if len(s) == 0:
+            assert got["seqs"][i] is None and not (runs["seq"] == i).any()
+            continue
+        want = oracle.decode(m["a"], m["e"], m["a0"], s, full=True)
+        g = got["seqs"][i]
+        assert np.max(np.abs(g["post"] - want["post"])) < 2e-7                     # float rows
+        assert np.max(np.abs(g["p_recomb"] - want["p_recomb"])) < 1e-10
+        assert np.max(np.abs(g["best_p"] - want["best_p"])) < 2e-7
+        diff = g["best_k"] != want["best_k"]
+        if diff.any():                                                             # argmax may differ only at ties
+            srt = np.sort(want["post"][diff], axis=1)
+            assert np.all(srt[:, -1] - srt[:, -2] < 1e-10)
+        sel = runs["seq"] == i
+        mine = list(zip(runs["start"][sel], runs["len"][sel], runs["state"][sel], runs["max_p"][sel]))
+        ref_runs = _runs_of(g["best_k"], want["best_p"] if not diff.any() else g["best_p"].astype(np.float64))
+        assert [(x[0], x[1], x[2]) for x in mine] == [(x[0], x[1], x[2]) for x in ref_runs]
+        tol = 1e-10 if not diff.any() else 2e-7
+        assert max(abs(x[3] - y[3]) for x, y in zip(mine, ref_runs)) < tol
+        assert sum(x[1] for x in mine) == len(s)
