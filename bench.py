@@ -425,7 +425,10 @@ def run_own(args):
     lib.psmc_b200_get_info(ctx, ctypes.byref(ci))
     inf = {"n_chunks": ci.n_chunks, "chunk_len": ci.chunk_len, "warm_len": ci.warm_len, "fallbacks": ci.fallbacks,
            "repaired_fwd": ci.repaired_fwd, "repaired_bwd": ci.repaired_bwd, "failed_fwd": ci.failed_fwd, "failed_bwd": ci.failed_bwd,
-           "fwd_mismatch": ci.fwd_mismatch, "bwd_mismatch": ci.bwd_mismatch}
+           "fwd_mismatch": ci.fwd_mismatch, "bwd_mismatch": ci.bwd_mismatch,
+           "planned": ci.planned, "probe_plans": ci.probe_plans, "avg_overlap_fwd": ci.avg_overlap_fwd, "avg_overlap_bwd": ci.avg_overlap_bwd,
+           "slow_fwd": ci.slow_fwd, "slow_bwd": ci.slow_bwd, "repair_rounds": ci.repair_rounds, "warm_redos": ci.warm_redos,
+           "n_chunks_bwd": ci.n_chunks_bwd, "chunk_len_bwd": ci.chunk_len_bwd}
     obs_bytes = ci.bytes_obs
     if world > 1:
         t = torch.tensor([float(obs_bytes)], dtype=torch.float64, device="cuda")

@@ -85,6 +85,12 @@ typedef struct {
 	int32_t repair_rounds, warm_redos;
 	/* last psmc_b200_decode_run: device ms of its E-step, of the decode kernel + run compaction, and wall ms of the call */
 	float decode_ms[3];
+	/* planned overlaps (mixing probe): 1 when the current chunk plans come from a probe (chunk_len is then the mean
+	 * chunk length), how many plans were built from probes, the mean overlap per boundary in bins (the fixed overlap when
+	 * not planned), and the boundaries the probe declared out of reach of any overlap (repaired with operators) */
+	int32_t planned, probe_plans;
+	float avg_overlap_fwd, avg_overlap_bwd;
+	int32_t slow_fwd, slow_bwd;
 } psmc_b200_info;
 
 int  psmc_b200_version(void);

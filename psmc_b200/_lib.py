@@ -38,7 +38,9 @@ class CInfo(C.Structure):
                 ("failed_fwd", C.c_int32), ("repaired_fwd", C.c_int32), ("failed_bwd", C.c_int32), ("repaired_bwd", C.c_int32),
                 ("active_bins", C.c_int64), ("n_seqs_effective", C.c_int64),
                 ("n_models", C.c_int32), ("n_chunks_bwd", C.c_int32), ("chunk_len_bwd", C.c_int32),
-                ("repair_rounds", C.c_int32), ("warm_redos", C.c_int32), ("decode_ms", C.c_float * 3)]
+                ("repair_rounds", C.c_int32), ("warm_redos", C.c_int32), ("decode_ms", C.c_float * 3),
+                ("planned", C.c_int32), ("probe_plans", C.c_int32), ("avg_overlap_fwd", C.c_float), ("avg_overlap_bwd", C.c_float),
+                ("slow_fwd", C.c_int32), ("slow_bwd", C.c_int32)]
 
 
 # every symbol include/psmc_b200.h declares: name -> (restype, argtypes)

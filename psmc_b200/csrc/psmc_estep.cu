@@ -203,6 +203,27 @@ struct psmc_b200_ctx {
 	// Batch mode (psmc_b200_set_batch): n_rep models side by side in ONE launch sequence -- bootstrap replicates, each a
 	// multiset of the resident records under its own model.  A "virtual sequence" is a (model, record) pair; the chunk
 	// plans cover the virtual sequences, chunks carry their model index, k_reduce sums per model.
+	// Mixing probe and planned overlaps (k_probe; DESIGN.md "Planned overlaps"): every now and then an E-step also measures
+	// the local contraction rate of the chain; the chunk plans are then rebuilt with, per boundary, the overlap it needs
+	// (plus a margin), chunk lengths balanced so that overlap + length is the same for every chunk, and the boundaries no
+	// admissible overlap reaches known in advance (their operators are "predicted" from the first E-step of a plan on).
+	bool probe_on = true;        // PSMC_B200_PROBE=0: fixed overlaps, uniform chunks (the round-1 plans)
+	int estep_no = 0;            // E-steps launched on the current sequences
+	bool probe_now = false;      // the E-step in flight also runs k_probe
+	bool plan_dirty = false;     // a probe result is waiting: re-plan before the next E-step
+	bool have_probe = false, planned = false;
+	float *d_probeK = nullptr, *h_probeK = nullptr;
+	int64_t cap_probeK = 0, n_probeK = 0;
+	std::vector<std::vector<double>> probe_cum; // per kept sequence: cum[j] = log contraction accumulated over the bins < 64 j (non-increasing)
+	double probe_th = 35.0;      // e-folds an overlap must cover: ln(1 / 1e-12) = 27.6 + margin (start distance, probe accuracy); swept on B200
+	int probe_hmax = 0, probe_hslow = 0, probe_lead = 0, probe_plans = 0; // 0 = derived from the fixed overlap: 5/3, 1/6 and 1/12 of it (20480 / 2048 / 1024 bins)
+	int hmax() const { return probe_hmax > 0 ? probe_hmax : warm_len + 2 * warm_len / 3; }
+	int hslow() const { return probe_hslow > 0 ? probe_hslow : std::max(64, warm_len / 6); }
+	int lead() const { return probe_lead > 0 ? probe_lead : std::max(32, warm_len / 12); }
+	int32_t *d_warm_f = nullptr, *d_warm_b = nullptr; // per chunk: overlap in front of (forward plan) / behind (backward plan) it
+	double avg_warm_f = 0.0, avg_warm_b = 0.0;
+	int slow_f = 0, slow_b = 0;
+	uint64_t obs_hash = 0;
 	int n_rep = 1;
 	bool batch = false;
 	std::vector<int32_t> bmult;          // batch mode: n_rep x n_seqs multiplicities (kept-record index)
@@ -255,7 +276,8 @@ static void free_plan(psmc_b200_ctx *c)
 	              (void **)&c->d_chunk_sub0, (void **)&c->d_Tsub, (void **)&c->d_Texsub, (void **)&c->d_vsub, (void **)&c->d_bsub,
 	              (void **)&c->d_llsub, (void **)&c->d_partsub, (void **)&c->d_cw, (void **)&c->d_cw_b,
 	              (void **)&c->d_pred[0], (void **)&c->d_pred[1], (void **)&c->d_pred_b[0], (void **)&c->d_pred_b[1],
-	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b, (void **)&c->d_seq_c0, (void **)&c->d_seq_nc, (void **)&c->d_rep_c0, (void **)&c->d_rep_c0_b};
+	              (void **)&c->d_Tsub_b, (void **)&c->d_Texsub_b, (void **)&c->d_seq_c0, (void **)&c->d_seq_nc, (void **)&c->d_rep_c0, (void **)&c->d_rep_c0_b,
+	              (void **)&c->d_warm_f, (void **)&c->d_warm_b};
 	for (auto q : p) { cudaFree(*q); *q = nullptr; }
 	c->bytes_total -= c->bytes_plan;
 	c->bytes_plan = 0;
@@ -267,7 +289,8 @@ static void free_ctx(psmc_b200_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	free_plan(c);
-	cudaFree(c->d_obs);
+	cudaFree(c->d_obs); cudaFree(c->d_probeK);
+	if (c->h_probeK) cudaFreeHost(c->h_probeK);
 	cudaFree(c->d_model); cudaFree(c->d_fhat); cudaFree(c->d_sc); cudaFree(c->d_cert);
 	if (c->h_cert) cudaFreeHost(c->h_cert);
 	cudaFree(c->d_stats);
@@ -324,6 +347,21 @@ static void pack_range(const signed char *s, int64_t u0, int64_t u1, uint32_t *d
 		dst[w] = v;
 	}
 }
+static uint64_t hash_obs(const psmc_b200_ctx *c)
+{
+	uint64_t h = 1469598103934665603ull; // word-wise multiply-xor over the packed tracks (~1 ms for a 3 Gbp genome)
+	const uint64_t *p = (const uint64_t *)c->h_obs;
+	const int64_t n = c->words_obs / 2;
+	uint64_t a = h, b = h ^ 0x9e3779b97f4a7c15ull, d = h + 7, e = h + 13;
+	int64_t i = 0;
+	for (; i + 4 <= n; i += 4) {
+		a = (a ^ p[i]) * 1099511628211ull; b = (b ^ p[i + 1]) * 1099511628211ull;
+		d = (d ^ p[i + 2]) * 1099511628211ull; e = (e ^ p[i + 3]) * 1099511628211ull;
+	}
+	for (; i < n; ++i) a = (a ^ p[i]) * 1099511628211ull;
+	return a ^ (b * 3) ^ (d * 5) ^ (e * 7);
+}
+
 static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 {
 	// only the alignment padding behind every sequence needs the 'missing' fill; the rest is overwritten below
@@ -370,6 +408,88 @@ static void pack_all(psmc_b200_ctx *c, const signed char *const *sp)
 // the forward spill (indexed by bin) and everything else that does not depend on the plan stay where they are.
 struct VSeq { int32_t seq, rep, mult; int64_t gb0; };
 
+// ---- planned overlaps: what the mixing probe says about a boundary ------------------------------------------------
+// cum[j] = log contraction accumulated over the bins < 64 j of one sequence (cum[0] = 0, non-increasing).
+static inline double probe_at(const std::vector<double> &cum, int64_t u) // accumulated over the bins < u (linear inside a cell)
+{
+	const int64_t j = u >> 6, nj = (int64_t)cum.size() - 1;
+	if (j >= nj) return cum[nj];
+	return cum[j] + (cum[j + 1] - cum[j]) * (double)(u & 63) / 64.0;
+}
+// bins of overlap a forward boundary in front of bin p needs: the shortest window [p - H, p) over which th e-folds are
+// lost (p itself if the whole prefix does not lose that much: the warm-up then starts at the sequence start, exactly)
+static int need_fwd(const std::vector<double> &cum, int64_t p, double th)
+{
+	const double target = probe_at(cum, p) + th;
+	if (cum[0] < target) return (int)p;
+	int64_t lo = 0, hi = p >> 6; // largest j <= p/64 with cum[j] >= target
+	while (lo < hi) {
+		const int64_t mid = (lo + hi + 1) >> 1;
+		if (cum[mid] >= target) lo = mid; else hi = mid - 1;
+	}
+	return (int)(p - (lo << 6));
+}
+// bins of overlap a backward boundary behind bin q needs: the shortest window (q, q + H] over which th e-folds are lost
+static int need_bwd(const std::vector<double> &cum, int64_t q, int64_t L, double th)
+{
+	const double target = probe_at(cum, q + 1) - th;
+	const int64_t nj = (int64_t)cum.size() - 1;
+	if (cum[nj] > target) return (int)(L - 1 - q);
+	int64_t lo = (q + 1 + 63) >> 6, hi = nj; // smallest j >= (q+1)/64 with cum[j] <= target
+	if (lo > hi) return (int)(L - 1 - q);
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (cum[mid] <= target) hi = mid; else lo = mid + 1;
+	}
+	return (int)std::min<int64_t>(L - 1 - q, (lo << 6) - (q + 1));
+}
+struct Piece { int32_t u0, len, warm, slow; };
+// one sequence cut into chunks with overlap + length == T (as far as a minimum length and the ends allow); dir 0: the
+// overlap of a chunk lies in front of it (forward plan), dir 1: behind it (backward plan).  Returns the number of chunks.
+static int cut_sequence(const std::vector<double> &cum, int L, int T, int dir, double th, int hmax, int hslow, std::vector<Piece> *out, double sw = 2.0)
+{
+	// sw: a stored bin costs the forward kernel about twice a warm-up bin (normalisation, stores), so the budget of a chunk is
+	// overlap + sw * length = T
+	const int MINLEN = 512;
+	int n = 0;
+	if (dir == 0) {
+		int pos = 0;
+		while (pos < L) {
+			int H = 0, slow = 0;
+			if (pos > 0) {
+				const int need = need_fwd(cum, pos, th);
+				if (need > hmax) { H = std::min(pos, hslow); slow = 1; }
+				else H = std::min(pos, need + 128);
+			}
+			int len = std::max(MINLEN, (int)((T - H) / sw));
+			if (slow) { // this chunk will be recomputed through transfer operators (64 columns): end it where the slow tract ends
+				for (int p = pos + MINLEN; p < pos + len && p < L; p += 256)
+					if (need_fwd(cum, p, th) <= hmax) { len = p - pos; break; }
+			}
+			if (L - pos < len + len / 2) len = L - pos;
+			if (out) out->push_back({pos, len, H, slow});
+			pos += len;
+			++n;
+		}
+	} else {
+		// backward plan: the counting kernel only walks the chunk itself (the overlap is the side stream's warm-up kernel), so
+		// its chunks stay equally long (T = chunk length here); only the overlap behind every chunk follows the probe
+		const int nc = (L + T - 1) / T;
+		for (int k = 0; k < nc; ++k) {
+			const int64_t a = (int64_t)L * k / nc, b = (int64_t)L * (k + 1) / nc;
+			int H = 0, slow = 0;
+			if (b < L) {
+				const int need = need_bwd(cum, b - 1, L, th);
+				if (need > hmax) { H = std::min((int)(L - b), hslow); slow = 1; }
+				else H = std::min((int)(L - b), need + 128);
+			}
+			if (out) out->push_back({(int32_t)a, (int32_t)(b - a), H, slow});
+			++n;
+		}
+	}
+	return n;
+}
+
 static int replan(psmc_b200_ctx *c)
 {
 	const int NP = c->NP;
@@ -411,13 +531,54 @@ static int replan(psmc_b200_ctx *c)
 	c->chunk_len_b = chunk_len_b;
 	std::vector<int32_t> k1;
 	std::vector<double> cw, cw_b;
+	// planned overlaps: one target T = overlap + length per plan, the smallest that fits the plan into one resident wave
+	const bool planned = c->have_probe && c->probe_on && !c->batch && c->chunk_len_req <= 0 && c->warm_len > 0 && (int)c->probe_cum.size() == c->n_seqs;
+	int T_plan[2] = {0, 0}, hmax_plan[2] = {0, 0};
+	if (planned) {
+		// forward plan: the kernel runs overlap + length steps per chunk (a stored step costing two warm-up steps) and lasts as
+		// long as its most expensive chunk, so no overlap may exceed T - 2 * 512 (boundaries that need more are "slow": short overlap, operators); T never drops below the fixed overlap's
+		// reach (small shards: more slow boundaries would cost more than shorter chunks save).  backward plan: T is the chunk
+		// length; its overlaps run in the side stream's warm-up kernel, which should not outlast the forward kernel.
+		for (int dir = 0; dir < 2; ++dir) {
+			const int target = std::max(1, c->sm_count * (dir == 0 ? c->slots_fwd : c->slots_bwd));
+			auto cap = [&](int T) { return dir == 0 ? std::min(c->hmax(), T - 1024) : std::min(c->hmax(), std::max(hmax_plan[0], c->warm_len)); };
+			auto count = [&](int T) {
+				int64_t n = 0;
+				for (int v = 0; v < c->n_vseq; ++v)
+					if (vs[v].mult > 0) n += cut_sequence(c->probe_cum[vs[v].seq], c->L[vs[v].seq], T, dir, c->probe_th, cap(T), c->hslow(), nullptr);
+				return n;
+			};
+			int lo = dir == 0 ? c->warm_len + 1024 : 512, hi = 1 << 25;
+			while (lo < hi) { // count is non-increasing in T
+				const int mid = lo + (hi - lo) / 2;
+				if (count(mid) <= target) hi = mid; else lo = mid + 1;
+			}
+			T_plan[dir] = lo;
+			hmax_plan[dir] = cap(lo);
+		}
+	}
+	std::vector<int32_t> warm_f, warm_b, slow_f, slow_b;
 	auto build_plan = [&](int clen, bool is_main, std::vector<Chunk> &chunks, std::vector<Chunk> &subs,
-	                      std::vector<int32_t> &sub_parent, std::vector<int32_t> &chunk_sub0, std::vector<double> &w, std::vector<int32_t> &rep_c0) {
+	                      std::vector<int32_t> &sub_parent, std::vector<int32_t> &chunk_sub0, std::vector<double> &w, std::vector<int32_t> &rep_c0,
+	                      std::vector<int32_t> &warm_of, std::vector<int32_t> &slow_of) {
 		rep_c0.assign((size_t)c->n_rep + 1, 0);
 		int next_rep = 0;
+		std::vector<Piece> pieces;
 		for (int v = 0; v < c->n_vseq; ++v) {
 			const int i = vs[v].seq, Li = c->L[i];
-			const int nc = vs[v].mult > 0 ? (Li + clen - 1) / clen : 0;
+			pieces.clear();
+			if (vs[v].mult > 0) {
+				if (planned) {
+					cut_sequence(c->probe_cum[i], Li, T_plan[is_main ? 0 : 1], is_main ? 0 : 1, c->probe_th, hmax_plan[is_main ? 0 : 1], c->hslow(), &pieces);
+				} else {
+					const int nc0 = (Li + clen - 1) / clen;
+					for (int k = 0; k < nc0; ++k) {
+						const int64_t a = (int64_t)Li * k / nc0, b = (int64_t)Li * (k + 1) / nc0;
+						pieces.push_back({(int32_t)a, (int32_t)(b - a), is_main ? c->warm_len : c->warm_len_bwd, 0});
+					}
+				}
+			}
+			const int nc = (int)pieces.size();
 			const int64_t gb = vs[v].gb0;
 			while (next_rep <= vs[v].rep) rep_c0[next_rep++] = (int32_t)chunks.size();
 			if (is_main) {
@@ -427,18 +588,19 @@ static int replan(psmc_b200_ctx *c)
 			}
 			for (int k = 0; k < nc; ++k) {
 				Chunk ch;
-				const int64_t a = (int64_t)Li * k / nc, b = (int64_t)Li * (k + 1) / nc;
 				ch.seq = v;
 				ch.flags = (k == 0 ? CH_FIRST : 0) | (k == nc - 1 ? CH_LAST : 0);
-				ch.u0 = (int)a;
-				ch.len = (int)(b - a);
-				ch.gb0 = gb + a;
+				ch.u0 = pieces[k].u0;
+				ch.len = pieces[k].len;
+				ch.gb0 = gb + pieces[k].u0;
 				ch.ow0 = c->seq_ow0[i];
 				ch.Lseq = Li;
 				ch.rep = vs[v].rep;
 				if (is_main && nc > 1) k1.push_back((int)chunks.size());
 				chunks.push_back(ch);
 				w.push_back((double)vs[v].mult);
+				warm_of.push_back(pieces[k].warm);
+				slow_of.push_back(pieces[k].slow);
 			}
 		}
 		while (next_rep <= c->n_rep) rep_c0[next_rep++] = (int32_t)chunks.size();
@@ -464,8 +626,20 @@ static int replan(psmc_b200_ctx *c)
 	std::vector<Chunk> subs, chunks_b, subs_b;
 	std::vector<int32_t> sub_parent, chunk_sub0, sub_parent_b, chunk_sub0_b;
 	c->chunks.clear();
-	build_plan(chunk_len, true, c->chunks, subs, sub_parent, chunk_sub0, cw, c->rep_c0);
-	build_plan(chunk_len_b, false, chunks_b, subs_b, sub_parent_b, chunk_sub0_b, cw_b, c->rep_c0_b);
+	build_plan(chunk_len, true, c->chunks, subs, sub_parent, chunk_sub0, cw, c->rep_c0, warm_f, slow_f);
+	build_plan(chunk_len_b, false, chunks_b, subs_b, sub_parent_b, chunk_sub0_b, cw_b, c->rep_c0_b, warm_b, slow_b);
+	c->planned = planned;
+	if (planned) { // (what the info block reports for a planned context: the typical chunk, the mean overlaps)
+		int64_t sl = 0, sw = 0, sl_b = 0, sw_b = 0;
+		c->slow_f = c->slow_b = 0;
+		for (size_t i = 0; i < c->chunks.size(); ++i) { sl += c->chunks[i].len; sw += warm_f[i]; c->slow_f += slow_f[i]; }
+		for (size_t i = 0; i < chunks_b.size(); ++i) { sl_b += chunks_b[i].len; sw_b += warm_b[i]; c->slow_b += slow_b[i]; }
+		c->chunk_len = c->chunks.empty() ? 0 : (int)(sl / (int64_t)c->chunks.size());
+		c->chunk_len_b = chunks_b.empty() ? 0 : (int)(sl_b / (int64_t)chunks_b.size());
+		c->avg_warm_f = c->chunks.empty() ? 0.0 : (double)sw / (double)c->chunks.size();
+		c->avg_warm_b = chunks_b.empty() ? 0.0 : (double)sw_b / (double)chunks_b.size();
+		++c->probe_plans;
+	}
 	c->n_chunks = (int)c->chunks.size();
 	c->n_sub = (int)subs.size();
 	c->n_chunks_b = (int)chunks_b.size();
@@ -551,6 +725,8 @@ static int replan(psmc_b200_ctx *c)
 		alloc((void **)&c->d_seq_nc, sizeof(int32_t) * (size_t)cv);
 		alloc((void **)&c->d_rep_c0, sizeof(int32_t) * (size_t)(cr + 1));
 		alloc((void **)&c->d_rep_c0_b, sizeof(int32_t) * (size_t)(cr + 1));
+		alloc((void **)&c->d_warm_f, sizeof(int32_t) * (size_t)cc);
+		alloc((void **)&c->d_warm_b, sizeof(int32_t) * (size_t)cb);
 		c->bytes_total += c->bytes_plan;
 		if (!ok) { free_plan(c); return PSMC_B200_ECUDA; }
 		c->cap_chunks = cc; c->cap_chunks_b = cb; c->cap_sub = cs; c->cap_sub_b = csb; c->cap_k1 = ck; c->cap_vseq = cv; c->cap_rep = cr;
@@ -566,12 +742,17 @@ static int replan(psmc_b200_ctx *c)
 	UP(c->d_chunks_b, chunks_b); UP(c->d_sub_b, subs_b); UP(c->d_sub_parent_b, sub_parent_b); UP(c->d_chunk_sub0_b, chunk_sub0_b);
 	UP(c->d_k1, k1); UP(c->d_cw, cw); UP(c->d_cw_b, cw_b);
 	UP(c->d_seq_c0, c->seq_c0); UP(c->d_seq_nc, c->seq_nc); UP(c->d_rep_c0, c->rep_c0); UP(c->d_rep_c0_b, c->rep_c0_b);
+	UP(c->d_warm_f, warm_f); UP(c->d_warm_b, warm_b);
 #undef UP
 	CUDA_TRY(cudaMemsetAsync(c->d_flag_b, 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaMemsetAsync(c->d_flag, 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), st), PSMC_B200_ECUDA);
-	for (int q = 0; q < 2; ++q) { // no prediction for a new plan
+	for (int q = 0; q < 2; ++q) { // no prediction for a new plan ...
 		CUDA_TRY(cudaMemsetAsync(c->d_pred[q], 0, sizeof(int32_t) * (size_t)(c->n_chunks + 2), st), PSMC_B200_ECUDA);
 		CUDA_TRY(cudaMemsetAsync(c->d_pred_b[q], 0, sizeof(int32_t) * (size_t)(c->n_chunks_b + 2), st), PSMC_B200_ECUDA);
+	}
+	if (planned) { // ... except the boundaries the probe already knows no overlap reaches: their operators are computed ahead of time
+		if (!slow_f.empty()) CUDA_TRY(cudaMemcpyAsync(c->d_pred[c->pred_cur] + 1, slow_f.data(), sizeof(int32_t) * slow_f.size(), cudaMemcpyHostToDevice, st), PSMC_B200_ECUDA);
+		if (!slow_b.empty()) CUDA_TRY(cudaMemcpyAsync(c->d_pred_b[c->pred_cur] + 1, slow_b.data(), sizeof(int32_t) * slow_b.size(), cudaMemcpyHostToDevice, st), PSMC_B200_ECUDA);
 	}
 	CUDA_TRY(cudaMemsetAsync(c->d_vstart, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaMemsetAsync(c->d_bend, 0, sizeof(double) * (size_t)std::max(c->n_chunks, 1) * NP, st), PSMC_B200_ECUDA);
@@ -641,6 +822,12 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	{
 		const char *env = getenv("PSMC_B200_GEN");
 		if (env && atoi(env) == 1) c->gen = 1;
+		env = getenv("PSMC_B200_PROBE");
+		if (env) c->probe_on = atoi(env) != 0;
+		env = getenv("PSMC_B200_PROBE_TH");
+		if (env && atof(env) > 0) c->probe_th = atof(env);
+		env = getenv("PSMC_B200_PROBE_HMAX");
+		if (env && atoi(env) > 0) c->probe_hmax = atoi(env);
 		env = getenv("PSMC_B200_G2_FWD");
 		if (env && atoi(env) == 16) c->g2_fwd = 16;
 		env = getenv("PSMC_B200_G2_BWW");
@@ -739,6 +926,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	CTRY(cudaMallocHost((void **)&c->h_cert, sizeof(unsigned long long) * 16));
 	CTRY(cudaMallocHost((void **)&c->h_obs, (size_t)c->bytes_obs));
 	pack_all(c, sp.data());
+	c->obs_hash = hash_obs(c);
 	CTRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream));
 	CTRY(cudaStreamSynchronize(c->stream));
 #undef CTRY
@@ -839,6 +1027,14 @@ extern "C" int psmc_b200_upload(psmc_b200_ctx *c, int32_t n_seqs, const int32_t 
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
 	pack_all(c, sp.data());
 	CUDA_TRY(cudaMemcpyAsync(c->d_obs, c->h_obs, (size_t)c->bytes_obs, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
+	{ // the mixing probe describes the OBSERVATIONS: it survives a re-upload of the same data, not new data
+		const uint64_t h = hash_obs(c);
+		if (h != c->obs_hash) {
+			c->obs_hash = h;
+			c->estep_no = 0;
+			if (c->have_probe) { c->have_probe = false; c->plan_dirty = c->planned; }
+		}
+	}
 	c->fwd_valid = false; // (have_prev stays: stale vectors are still legal warm starts, the certificate decides)
 	return 0;
 }
@@ -901,7 +1097,7 @@ template <int NP>
 static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
-#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm)
+#define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, (c->planned && warm > 0 && !use_prev) ? c->d_warm_f : nullptr)
 	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWD(16, 2);
 	else if (c->gen == 2) FWD(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8, 1);
@@ -941,7 +1137,7 @@ static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const dou
 template <int NP>
 static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int use_prev)
 {
-#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr)
+#define BWW(G_, V_) LAUNCH((k_backward_warm<NP / G_, G_, V_>), blocks_for(c->n_chunks_b, G_), 128, st, c->d_chunks_b, c->n_chunks_b, c->d_obs, c->d_model, warm, c->d_bwarm, use_prev ? c->d_bsave[c->bsave_cur] : nullptr, (c->planned && !use_prev) ? c->d_warm_b : nullptr)
 	if (c->gen == 2 && (c->g2_bww == 16 || NP > 64)) BWW(16, 2);
 	else if (c->gen == 2) BWW(8, 2);
 	else if (c->g_bww == 8 && NP / 8 <= 8) BWW(8, 1);
@@ -1105,7 +1301,13 @@ static int launch_warm(psmc_b200_ctx *c)
 	LAUNCH((k_certify<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 0, c->d_cert);
 	LAUNCH((k_certify<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->d_fhat, c->d_fwarm, c->d_bwarm, c->d_bexact, c->cert_eps, 1, c->d_cert);
 	cudaEventRecord(c->ev[5], st);
-	c->launches = 6 + 10 * rounds + (c->predict ? 2 : 0);
+	if (c->probe_now && c->d_probeK) { // mixing probe next to the (now exact) forward pass; the result is read in sync_and_certify
+		constexpr int GP = (NP > 64) ? 16 : 8;
+		cudaMemsetAsync(c->d_probeK, 0, sizeof(float) * (size_t)c->n_probeK, st);
+		LAUNCH((k_probe<NP / GP, GP>), blocks_for(c->n_chunks, GP), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_fhat, c->d_probeK, c->N, c->lead());
+		cudaMemcpyAsync(c->h_probeK, c->d_probeK, sizeof(float) * (size_t)c->n_probeK, cudaMemcpyDeviceToHost, st);
+	}
+	c->launches = 6 + 10 * rounds + (c->predict ? 2 : 0) + ((c->probe_now && c->d_probeK) ? 1 : 0);
 	c->pred_cur ^= 1;
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_err(PSMC_B200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -1114,6 +1316,41 @@ static int launch_warm(psmc_b200_ctx *c)
 	c->certified = false;
 	c->have_prev = true;
 	return 0;
+}
+
+// the probe's pieces (k_probe) -> per sequence, the log contraction accumulated along a 64-bin grid
+static void parse_probe(psmc_b200_ctx *c)
+{
+	c->probe_cum.assign((size_t)c->n_seqs, std::vector<double>());
+	for (int i = 0; i < c->n_seqs; ++i) c->probe_cum[i].assign((size_t)((c->L[i] + 63) / 64) + 1, 0.0);
+	const float *K = c->h_probeK;
+	for (int ci = 0; ci < c->n_chunks; ++ci) {
+		const Chunk &ch = c->chunks[ci];
+		std::vector<double> &cell = c->probe_cum[ch.seq]; // (single mode: the virtual sequence index is the kept-record index)
+		int64_t k = (ch.gb0 >> 6) + ci;
+		int u = ch.u0;
+		const int uend = ch.u0 + ch.len;
+		while (u < uend) { // piece [u, ue]: up to the next global row with (row & 63) == 63, or the chunk's last bin
+			const int64_t row = ch.gb0 + (u - ch.u0);
+			const int ue = (int)std::min<int64_t>(uend - 1, u + (63 - (row & 63)));
+			double v = (k < c->n_probeK) ? (double)K[k] : 0.0;
+			if (!(v <= 0.0) || !std::isfinite(v)) v = 0.0;
+			const double per_bin = v / (double)(ue - u + 1);
+			for (int x = u; x <= ue;) { // spread over the sequence's own 64-bin cells
+				const int xe = std::min(ue, x | 63);
+				cell[(size_t)(x >> 6) + 1] += per_bin * (double)(xe - x + 1);
+				x = xe + 1;
+			}
+			u = ue + 1;
+			++k;
+		}
+	}
+	for (int i = 0; i < c->n_seqs; ++i) { // cells -> prefix sums: cum[j] = accumulated over the bins < 64 j
+		std::vector<double> &cum = c->probe_cum[i];
+		for (size_t j = 1; j < cum.size(); ++j) cum[j] += cum[j - 1];
+	}
+	c->have_probe = true;
+	c->plan_dirty = true;
 }
 
 static int launch_dispatch(psmc_b200_ctx *c, bool with_counts)
@@ -1146,6 +1383,26 @@ static int launch_models(psmc_b200_ctx *c, int n_rep, const psmc_b200_model *mod
 	}
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA); // pinned staging buffer is reused
+	if (c->plan_dirty && !c->batch) { // a mixing probe came back with the previous E-step: new plans with the overlaps it asks for
+		c->plan_dirty = false;
+		int rc = replan(c);
+		if (rc) return rc;
+	}
+	// probe on the E-steps 0, 1, 2, 4, 8, ... of a context (the model moves fast early in EM, slowly later)
+	c->probe_now = c->probe_on && !c->batch && !c->dense && c->warm_len > 0 && c->n_k1 > 0 && c->chunk_len_req <= 0 && (c->estep_no & (c->estep_no - 1)) == 0;
+	if (c->probe_now) {
+		const int64_t need = (c->cap_bins >> 6) + c->n_chunks + 2;
+		if (need > c->cap_probeK) {
+			cudaFree(c->d_probeK);
+			if (c->h_probeK) cudaFreeHost(c->h_probeK);
+			c->d_probeK = c->h_probeK = nullptr;
+			c->cap_probeK = 0;
+			if (cudaMalloc((void **)&c->d_probeK, sizeof(float) * (size_t)need) == cudaSuccess && cudaMallocHost((void **)&c->h_probeK, sizeof(float) * (size_t)need) == cudaSuccess) c->cap_probeK = need;
+			else { cudaGetLastError(); c->probe_now = false; }
+		}
+		c->n_probeK = need;
+	}
+	++c->estep_no;
 	for (int r = 0; r < n_rep; ++r) stage_model(c, models + r, r);
 	CUDA_TRY(cudaMemcpyAsync(c->d_model, c->h_model, sizeof(double) * M_COUNT * c->NP * (size_t)n_rep, cudaMemcpyHostToDevice, c->stream), PSMC_B200_ECUDA);
 	int rc = launch_dispatch(c, true);
@@ -1196,6 +1453,8 @@ static int sync_and_certify(psmc_b200_ctx *c)
 	const bool need = c->mode_warm && !c->certified;
 	if (need) CUDA_TRY(cudaMemcpyAsync(c->h_cert, c->d_cert, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA);
+	if (need && c->probe_now && c->h_probeK) parse_probe(c);
+	c->probe_now = false;
 	if (need) {
 		c->certified = true;
 		long long bf = (long long)c->h_cert[1], bb = (long long)c->h_cert[2];
@@ -1676,6 +1935,12 @@ extern "C" int psmc_b200_get_info(const psmc_b200_ctx *c, psmc_b200_info *info)
 	info->n_seqs_effective = c->n_seq_eff;
 	info->n_models = c->n_rep;
 	info->repair_rounds = c->rounds_cur;
+	info->planned = c->planned ? 1 : 0;
+	info->probe_plans = c->probe_plans;
+	info->avg_overlap_fwd = (float)(c->planned ? c->avg_warm_f : (double)c->warm_len);
+	info->avg_overlap_bwd = (float)(c->planned ? c->avg_warm_b : (double)c->warm_len_bwd);
+	info->slow_fwd = c->planned ? c->slow_f : 0;
+	info->slow_bwd = c->planned ? c->slow_b : 0;
 	for (int i = 0; i < 3; ++i) info->decode_ms[i] = c->dec_ms[i];
 	info->warm_redos = c->warm_redos;
 	info->n_chunks_bwd = c->n_chunks_b;

@@ -1016,7 +1016,8 @@ template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunks, int n_chunks,
                                                  const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                  const double *__restrict__ vstart, int warm, int use_prev, double *__restrict__ fhat,
-                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm)
+                                                 double *__restrict__ sc, double *__restrict__ llpart, double *__restrict__ fwarm,
+                                                 const int32_t *__restrict__ warm_of)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
@@ -1028,7 +1029,7 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	double f[SPL];
 	int ubeg = ch.u0;
 	if ((ch.flags & CH_FIRST) || warm > 0) {
-		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - warm);
+		if (!(ch.flags & CH_FIRST)) ubeg = max(0, ch.u0 - (warm_of ? warm_of[c] : warm)); // (warm_of: this boundary's own overlap, from the mixing probe)
 		if (use_prev && ubeg > 0) {
 			// warm start: the vector the PREVIOUS E-step stored for bin ubeg-1 (the parameters moved only a little since;
 			// any positive vector is a legal start -- the certificate decides -- so a stale or concurrently rewritten row is harmless)
@@ -1046,6 +1047,112 @@ __global__ void __launch_bounds__(128) k_forward(const Chunk *__restrict__ chunk
 	if constexpr (VER == 2) ll = forward_chunk2<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	else ll = forward_chunk<SPL, G>(ch, id.valid, ubeg, M, f, gl, obs, fhat, sc, fwarm + (size_t)c * NP);
 	if (gl == 0 && id.valid) llpart[c] = ll;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mixing probe.  How many bins of overlap a boundary needs is a property of the data in front of it: the chain forgets
+// its start at the local rate of its second Lyapunov exponent, ~1/120 per bin on average but 50x slower inside long
+// low-TMRCA tracts.  The probe measures that rate everywhere, once in a while: next to the exact forward pass (already in
+// fhat) every chunk runs a second, slightly perturbed chain h through the same bins and records, per piece of <= 64 bins,
+// the logarithm of the factor by which the projective (Hilbert) distance between h and the exact vector shrank.  The
+// host sums the pieces along every sequence; the overlap a boundary at bin p needs is then the shortest window in front
+// of p over which the sum reaches log(eps) minus a safety margin (psmc_estep.cu, plan_from_probe) -- typically 3-5 k bins
+// instead of the 12 k a fixed overlap must allow for, and known in advance for the boundaries no overlap can reach.
+// Pieces end at the global rows r with (r & 63) == 63 and at the chunk's last row; piece k of chunk c goes to
+// K[(gb0 >> 6) + c + k] (disjoint ranges for different chunks: no atomics, deterministic).  The perturbed chain starts
+// `lead` bins in front of the chunk so that it has turned into the slowest-decaying direction when measuring starts.
+// ------------------------------------------------------------------------------------------------
+template <int SPL, int G>
+__global__ void __launch_bounds__(128) k_probe(const Chunk *__restrict__ chunks, int n_chunks, const uint32_t *__restrict__ obs,
+                                               const double *__restrict__ model, const double *__restrict__ fhat, float *__restrict__ K,
+                                               int N, int lead)
+{
+	constexpr int NP = SPL * G;
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
+	const int uend = ch.u0 + ch.len, ub = max(0, ch.u0 - lead);
+	const double kappa = 1e-3;
+	double h[SPL], pat[SPL];
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) pat[i] = 1.0 - 2.0 * (double)(s0 + i) / (double)(NP - 1); // a smooth relative perturbation across the states
+	if (ub == 0) {
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) h[i] = MODEL_OF(model, ch, NP)[M_A0 * NP + s0 + i];
+	} else {
+		load_vec<SPL>(fhat + ((size_t)ch.gb0 - (size_t)(ch.u0 - ub) - 1) * NP + s0, h);
+	}
+#pragma unroll
+	for (int i = 0; i < SPL; ++i) h[i] *= fma(kappa, pat[i], 1.0);
+	DualScan<G> ds;
+	ds.init(gl);
+	const int trips = warp_trips(id.valid ? uend - ub : 0);
+	const int64_t kbase = (ch.gb0 >> 6) + c;
+	double d_prev = -1.0; // distance at the previous knot (< 0: not measured yet)
+	int k = 0;
+	uint32_t word = 0;
+	for (int t = 0; t < trips; ++t) {
+		const int u = ub + t;
+		const bool act = id.valid && u < uend;
+		const int uo = act ? u : uend - 1;
+		if (t == 0 || (uo & 15) == 0) word = __ldg(obs + ch.ow0 + (uo >> 4));
+		const int x = (word >> ((uo & 15) * 2)) & 3;
+		double out[SPL], c0, c1;
+		semisep2<SPL, G>(h, M.W, M.Z, M.U, M.V, M.D, ds, out);
+		emis_coef(x, c0, c1);
+		if (act) {
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) h[i] = ((u == 0) ? h[i] : out[i]) * fma(c1, M.e0[i], c0); // first bin of a sequence: no transition
+		}
+		// knots: the bin in front of the chunk (reference distance), every 64th global row, the chunk's last row
+		const int64_t row = ch.gb0 + (u - ch.u0);
+		const bool knot = act && (u == ch.u0 - 1 || (row & 63) == 63 || u == uend - 1); // (in front of the chunk: renormalisation only)
+		if (__any_sync(FULLMASK, knot)) {
+			double f[SPL], mx = 0.0, mn = 1e300, tot = 0.0;
+			if (knot) load_vec<SPL>(fhat + (size_t)row * NP + s0, f);
+			else {
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) f[i] = 1.0;
+			}
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				tot += h[i];
+				if (s0 + i < N && f[i] > 0.0 && h[i] > 0.0) {
+					const double r = h[i] / f[i];
+					mx = fmax(mx, r);
+					mn = fmin(mn, r);
+				}
+			}
+#pragma unroll
+			for (int d = G >> 1; d > 0; d >>= 1) {
+				mx = fmax(mx, __shfl_xor_sync(FULLMASK, mx, d, G));
+				mn = fmin(mn, __shfl_xor_sync(FULLMASK, mn, d, G));
+			}
+			tot = gsum<G>(tot);
+			if (knot) {
+				double dist = (mn < 1e300 && mn > 0.0) ? mx / mn - 1.0 : 1.0;
+				if (!(dist > 1e-15)) dist = 1e-15;
+				if (u >= ch.u0) {
+					// (a chunk that starts its sequence, or has no lead, measures its first piece from the perturbation it was given)
+					const double ref = d_prev > 0.0 ? d_prev : 2.0 * kappa;
+					K[kbase + k] = (float)fmin(log(dist / ref), 0.0);
+					++k;
+				}
+				d_prev = dist;
+				// keep the perturbation small but far from the rounding floor: rescale the relative deviation to kappa
+				const double sc_ = (dist < 1e-6) ? kappa / dist : 1.0, inv = 1.0 / tot;
+#pragma unroll
+				for (int i = 0; i < SPL; ++i) {
+					if (s0 + i < N && f[i] > 0.0 && h[i] > 0.0 && sc_ != 1.0) h[i] = f[i] * fma(h[i] / (f[i] * mn) - 1.0, sc_, 1.0);
+					else h[i] *= inv; // (sum-normalised: the chain is carried unnormalised between knots)
+				}
+				if (sc_ != 1.0) d_prev = kappa; // (the relative deviations now span [0, dist * sc_])
+			}
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1423,7 +1530,8 @@ __device__ __forceinline__ void publish_direction(const double (&b)[SPL], double
 template <int SPL, int G, int VER>
 __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__ chunks, int n_chunks,
                                                        const uint32_t *__restrict__ obs, const double *__restrict__ model,
-                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev)
+                                                       int warm, double *__restrict__ bwarm, const double *__restrict__ bsave_prev,
+                                                       const int32_t *__restrict__ warm_of)
 {
 	constexpr int NP = SPL * G;
 	const GroupId<G> id(n_chunks);
@@ -1437,6 +1545,7 @@ __global__ void __launch_bounds__(128) k_backward_warm(const Chunk *__restrict__
 	double beta[SPL];
 #pragma unroll
 	for (int i = 0; i < SPL; ++i) beta[i] = 1.0;
+	if (warm_of) warm = warm_of[c]; // this boundary's own overlap (mixing probe)
 	int z0 = is_last ? ulast : min(ch.Lseq - 1, ulast + warm);
 	if (bsave_prev && !is_last) {
 		// warm start: the direction the right neighbour saved during the PREVIOUS E-step at the bin

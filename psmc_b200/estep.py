@@ -241,6 +241,7 @@ class EStep:
     def info(self):
         inf = CInfo()
         check(self.lib, self.lib.psmc_b200_get_info(self.h, C.byref(inf)))
-        d = {f: getattr(inf, f) for f, _ in CInfo._fields_ if f != "ms"}
+        d = {f: getattr(inf, f) for f, _ in CInfo._fields_ if f not in ("ms", "decode_ms")}
         d["ms"] = list(inf.ms)
+        d["decode_ms"] = list(inf.decode_ms)
         return d

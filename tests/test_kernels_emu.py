@@ -337,3 +337,32 @@ def test_emulated_decode_all_runs_bins_and_posteriors(oracle, emu_plain, N, chun
         tol = 1e-10 if not diff.any() else 2e-7
         assert max(abs(x[3] - y[3]) for x, y in zip(mine, ref_runs)) < tol
         assert sum(x[1] for x in mine) == len(s)
+
+
+def test_emulated_mixing_probe_plans_the_overlaps(oracle, emu_plain, monkeypatch):
+    """automatic chunk plan: E-step 0 runs with the fixed overlap and measures the local mixing rate (k_probe); from E-step 1
+    on every boundary gets the overlap the probe asks for, chunk lengths are balanced, slow tracts are known in advance.
+    Results stay exact (certificate) whatever the probe says."""
+    from psmc_b200 import EStep
+    monkeypatch.setenv("PSMC_EMU_SMS", "3")
+    N = 64
+    m = make_model(oracle, N, seed=141)
+    seqs = _seqs(m, [26000, 9000, 300], seed=142)
+    seqs[0][8000:14000] = 0              # a long homozygous tract: no admissible overlap gets through it
+    want = oracle_stats(oracle, m, seqs)
+    m2 = make_model(oracle, N, seed=143)
+    want2 = oracle_stats(oracle, m2, seqs)
+    with EStep(seqs, N) as es:
+        es.set_warm(1500)
+        infos = []
+        for it in range(4):
+            mm, ww = (m, want) if it != 2 else (m2, want2)     # the model moves between E-steps, the plan is one E-step old
+            got = es.run(_model(mm))
+            infos.append(es.info())
+            compare_stats(got, ww, TOL, N)
+    assert infos[0]["planned"] == 0 and infos[1]["planned"] == 1
+    assert infos[1]["avg_overlap_fwd"] < 1500 and infos[1]["avg_overlap_bwd"] < 2000
+    assert all(i["fallbacks"] == 0 for i in infos)
+    assert infos[1]["slow_fwd"] > 0 and infos[1]["slow_bwd"] > 0      # the tract
+    print([(i["planned"], i["n_chunks"], i["chunk_len"], round(i["avg_overlap_fwd"]), round(i["avg_overlap_bwd"]), i["slow_fwd"], i["slow_bwd"],
+            i["failed_fwd"], i["failed_bwd"], i["repair_rounds"]) for i in infos])
