@@ -69,8 +69,18 @@
 		auto kfn_ = PSMC_UNPAREN kern;                                \
 		kfn_<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);          \
 	} while (0)
+#define LAUNCH_SMEM(kern, grid, block, smem, stream, ...)              \
+	do {                                                              \
+		auto kfn_ = PSMC_UNPAREN kern;                                \
+		kfn_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
+	} while (0)
 #define PIN_REG(x) asm volatile("" : "+d"(x))
 #else
+#define LAUNCH_SMEM(kern, grid, block, smem, stream, ...)             \
+	do {                                                              \
+		auto kfn_ = PSMC_UNPAREN kern;                                \
+		simt_emu::launch((grid), (block), [&]() { kfn_(__VA_ARGS__); }, (smem)); \
+	} while (0)
 #define LAUNCH(kern, grid, block, stream, ...)                        \
 	do {                                                              \
 		auto kfn_ = PSMC_UNPAREN kern;                                \
@@ -159,6 +169,7 @@ struct psmc_b200_ctx {
 	bool dense_valid = false;   // ghat holds the rows of the last E-step
 	double *d_ghat = nullptr, *d_cpart = nullptr, *d_cdense = nullptr;
 	int cap_cpart = 0;
+	bool staged_bwd = true;     // backward pass reads the forward spill through bulk-asynchronous copies into shared memory (PSMC_B200_TMA=0: register prefetch ring)
 	int gen = 2;                // kernel generation (PSMC_B200_GEN=1: the Kogge-Stone kernels)
 	int g_fwd = 16, g_bwd = 32; // lanes per chunk in the forward / backward kernels (PSMC_B200_G_FWD / PSMC_B200_G_BWD: 8, 16 or 32)
 	long long rep_fwd_fail = 0, rep_fwd_chunks = 0, rep_bwd_fail = 0, rep_bwd_chunks = 0; // of the last run
@@ -655,8 +666,13 @@ static int replan(psmc_b200_ctx *c)
 		c->bytes_forward = 0; c->cap_bins = 0;
 		// (batch mode: 1/8 head room, so that the next batch of the same size -- whose draws differ -- reuses the allocation)
 		const size_t need = (size_t)std::max<int64_t>(c->batch ? rows + rows / 8 : rows, 1);
-		cudaError_t e1 = cudaMalloc((void **)&c->d_fhat, need * NP * sizeof(double));
-		cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void **)&c->d_sc, need * sizeof(double)) : e1;
+		// (+8 rows: the backward pass stages tiles of 8 rows aligned in the row index, the last one may reach past the spill)
+		cudaError_t e1 = cudaMalloc((void **)&c->d_fhat, (need + 8) * NP * sizeof(double));
+		cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void **)&c->d_sc, (need + 8) * sizeof(double)) : e1;
+		if (e2 == cudaSuccess) { // (the padding rows are read, never used: give them defined contents)
+			cudaMemsetAsync(c->d_fhat + need * NP, 0, 8 * NP * sizeof(double), c->stream);
+			cudaMemsetAsync(c->d_sc + need, 0, 8 * sizeof(double), c->stream);
+		}
 		cudaError_t e3 = (e2 == cudaSuccess && c->dense) ? cudaMalloc((void **)&c->d_ghat, need * NP * sizeof(double)) : e2;
 		if (e3 != cudaSuccess) {
 			cudaFree(c->d_fhat); cudaFree(c->d_sc); c->d_fhat = nullptr; c->d_sc = nullptr;
@@ -822,6 +838,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	{
 		const char *env = getenv("PSMC_B200_GEN");
 		if (env && atoi(env) == 1) c->gen = 1;
+		env = getenv("PSMC_B200_TMA");
+		if (env) c->staged_bwd = atoi(env) != 0;
 		env = getenv("PSMC_B200_PROBE");
 		if (env) c->probe_on = atoi(env) != 0;
 		env = getenv("PSMC_B200_PROBE_TH");
@@ -1124,6 +1142,13 @@ static void run_backward(psmc_b200_ctx *c, const Chunk *chunks, int n, const dou
 #define BWD(G_, V_) LAUNCH((k_backward<NP / G_, G_, V_>), blocks_for(n, G_), 128, st, chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc, c->d_part, c->d_bexact, bsave_next, c->warm_hot, (c->dense && V_ == 2) ? c->d_ghat : nullptr)
 	// (forcing 4 resident blocks per SM with __launch_bounds__(128, 4) was measured: the spills cost more than the occupancy gives)
 	if constexpr (Gen2<NP>::BWD_OK) {
+		if (c->gen == 2 && c->staged_bwd) {
+			constexpr int GB = Gen2<NP>::G_BWD;
+			typedef BackwardStaged<NP / GB, GB> BS;
+			LAUNCH_SMEM((k_backward_staged<NP / GB, GB>), blocks_for(n, GB), 128, BS::SMEM_BYTES, st, chunks, n, c->d_obs, c->d_model, bdir, publish, c->d_fhat, c->d_sc,
+			            c->d_part, c->d_bexact, bsave_next, c->warm_hot, c->dense ? c->d_ghat : nullptr, c->d_cert + 15);
+			return;
+		}
 		if (c->gen == 2) {
 			BWD(Gen2<NP>::G_BWD, 2);
 			return;
@@ -1175,7 +1200,14 @@ static void chunk_slots(const psmc_b200_ctx *c, int *slots_fwd, int *slots_bwd)
 	else OCC(k_forward, 32, 1, bf);
 	bool done = false;
 	if constexpr (Gen2<NP>::BWD_OK) {
-		if (c->gen == 2) { gb = Gen2<NP>::G_BWD; OCC(k_backward, Gen2<NP>::G_BWD, 2, bb); done = true; }
+		if (c->gen == 2 && c->staged_bwd) {
+			constexpr int GB = Gen2<NP>::G_BWD;
+			typedef BackwardStaged<NP / GB, GB> BS;
+			gb = GB;
+			cudaFuncSetAttribute(k_backward_staged<NP / GB, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS::SMEM_BYTES);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bb, k_backward_staged<NP / GB, GB>, 128, BS::SMEM_BYTES);
+			done = true;
+		} else if (c->gen == 2) { gb = Gen2<NP>::G_BWD; OCC(k_backward, Gen2<NP>::G_BWD, 2, bb); done = true; }
 	}
 	if (done) {}
 	else if (c->g_bwd == 8 && NP / 8 <= 4) { gb = 8; OCC(k_backward, 8, 1, bb); }
@@ -1462,6 +1494,7 @@ static int sync_and_certify(psmc_b200_ctx *c)
 		memcpy(&c->mis_b, &bb, sizeof(double));
 		c->rep_fwd_fail = (long long)c->h_cert[4]; c->rep_fwd_chunks = (long long)c->h_cert[5];
 		c->rep_bwd_fail = (long long)c->h_cert[6]; c->rep_bwd_chunks = (long long)c->h_cert[7];
+		if (c->h_cert[15] > 0) return set_err(PSMC_B200_ECUDA, "internal: a staged tile of the forward spill never arrived (%llu waits timed out)", (unsigned long long)c->h_cert[15]);
 		const bool cert_failed = c->h_cert[0] > 0;
 		if (!c->rounds_fixed) { // the next E-step enqueues two rounds more than the deepest round that still saw a failure
 			const int deepest = (int)std::max(c->h_cert[8], c->h_cert[9]);

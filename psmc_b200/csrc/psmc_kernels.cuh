@@ -1483,6 +1483,229 @@ struct BackwardRun {
 	}
 };
 
+// ------------------------------------------------------------------------------------------------
+// Bulk-asynchronous staging of the forward spill for the backward pass (TMA unit, 1-D bulk copies + mbarrier).
+// The register prefetch ring of BackwardRun costs 40 registers and its loads share the warp's six scoreboards with the
+// packed-observation loads: ncu shows ~9 % of the backward kernel's cycles in long-scoreboard stalls at the consumers
+// (profiles/r02_*).  Here every chunk (lane group) owns a ring of STAGES tiles in shared memory; a tile is ROWS
+// consecutive rows of fhat (ROWS x 512 B at 64 states) plus their scale factors, aligned to a multiple of ROWS in the
+// global row index so that both bulk copies are 16-byte aligned and all groups of all warps cross tile boundaries in
+// the same step.  The group's first lane issues cp.async.bulk (global -> shared, completion on the tile's mbarrier) two
+// tiles ahead; the sixteen lanes wait on the mbarrier's phase parity and read their states with 128-bit LDS.  No
+// scoreboard is involved, the loads are in flight 16+ bins ahead, and the ring lives in shared memory, not registers.
+// ------------------------------------------------------------------------------------------------
+#ifndef PSMC_SIMT_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+	             "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+#define PSMC_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#else
+// host emulation of the same protocol (tests/emu): a barrier is {pending bytes, arrivals left, completed phases}
+struct EmuBar { int32_t tx; int16_t arrivals, phases; };
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { EmuBar *b = (EmuBar *)bar; b->tx = 0; b->arrivals = (int16_t)count; b->phases = 0; }
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void emu_bar_check(EmuBar *b, int count) { if (b->arrivals <= 0 && b->tx == 0) { b->arrivals = (int16_t)count; ++b->phases; } }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { EmuBar *b = (EmuBar *)bar; b->tx += (int32_t)bytes; --b->arrivals; }
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	EmuBar *b = (EmuBar *)bar;
+	memcpy(dst, src, bytes);
+	b->tx -= (int32_t)bytes;
+	emu_bar_check(b, 1);
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+	EmuBar *b = (EmuBar *)bar;
+	if (((uint32_t)b->phases & 1u) != parity) return true;
+	simt_emu::yield(); // let the producer lane run
+	return false;
+}
+#define PSMC_DYN_SMEM(name) unsigned char *name = simt_emu::dyn_smem()
+#endif
+// bounded wait: a protocol error must not hang the GPU (the flag makes the E-step fail loudly on the host)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned long long *err_flag)
+{
+	for (int i = 0; i < (1 << 22); ++i)
+		if (mbar_try_wait(bar, parity)) return;
+	if (err_flag) atomicAdd(err_flag, 1ull);
+}
+
+template <int SPL, int G>
+struct BackwardStaged {
+	static constexpr int NP = SPL * G, ROWS = 8, STAGES = 3;
+	static constexpr int TILE_BYTES = ROWS * NP * 8 + ROWS * 8;      // rows, then their scale factors
+	static constexpr int GROUP_BYTES = STAGES * TILE_BYTES;
+	static constexpr int GROUPS_PER_BLOCK = 128 / G;
+	static constexpr int SMEM_BYTES = GROUPS_PER_BLOCK * GROUP_BYTES + GROUPS_PER_BLOCK * STAGES * 8;
+	const Chunk &ch;
+	const LaneModel<SPL> &M;
+	const bool valid;
+	const int gl, s0, ulast;
+	const uint32_t *__restrict__ obs;
+	const double *__restrict__ fhat, *__restrict__ sc;
+	double *__restrict__ bsave_c;
+	const int usave;
+	double *__restrict__ grow; // dense-count option (row of bin ulast), or nullptr
+	unsigned char *tiles;      // this group's ring
+	uint64_t *bars;            // this group's STAGES barriers
+	unsigned long long *err_flag;
+	DualScan<G> ds;
+	double aE0[SPL], aE1[SPL], aRL[SPL], aCL[SPL], aRU[SPL], aCU[SPL], aAD[SPL];
+	uint32_t word, wprev;
+	int xu;
+	int64_t rtop; // global row of the f row used by step 0 of the aligned walk (rtop % ROWS == ROWS - 1)
+	int64_t rlo;  // lowest global row this chunk reads
+
+	__device__ __forceinline__ BackwardStaged(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_, const uint32_t *__restrict__ obs_,
+	                                          const double *__restrict__ fhat_, const double *__restrict__ sc_, double *__restrict__ bsave_c_, int usave_,
+	                                          double *__restrict__ ghat, unsigned char *smem, int group_in_block, unsigned long long *err)
+	    : ch(ch_), M(M_), valid(valid_), gl(gl_), s0(gl_ * SPL), ulast(ch_.u0 + ch_.len - 1), obs(obs_), fhat(fhat_), sc(sc_), bsave_c(bsave_c_),
+	      usave(usave_), grow(ghat ? ghat + ((size_t)ch_.gb0 + (ch_.len - 1)) * NP + gl_ * SPL : nullptr),
+	      tiles(smem + (size_t)group_in_block * GROUP_BYTES), bars((uint64_t *)(smem + (size_t)GROUPS_PER_BLOCK * GROUP_BYTES) + group_in_block * STAGES),
+	      err_flag(err)
+	{
+	}
+
+	__device__ __forceinline__ void issue(int64_t tile, int stage) // called by the group's first lane
+	{
+		unsigned char *dst = tiles + (size_t)stage * TILE_BYTES;
+		mbar_expect_tx(&bars[stage], (uint32_t)TILE_BYTES);
+		bulk_load(dst, fhat + (size_t)tile * ROWS * NP, (uint32_t)(ROWS * NP * 8), &bars[stage]);
+		bulk_load(dst + ROWS * NP * 8, sc + (size_t)tile * ROWS, (uint32_t)(ROWS * 8), &bars[stage]);
+	}
+
+	// one transition; fm / sm = the f row of bin u-1 and its scale factor (from the staged tile)
+	__device__ __forceinline__ void step(int u, int t_of_chunk, double (&b)[SPL], const double (&fm)[SPL], double sm)
+	{
+		const bool act = valid && u >= ch.u0 && u <= ulast;
+		const bool trans = act && u > 0; // no transition into the first bin of a sequence
+		if (act && u == usave && bsave_c) store_vec<SPL>(bsave_c + s0, b);
+		const int v = u - 1;
+		int xm = 2;
+		if (trans) {
+			if (u != ulast && (v & 15) == 15) {
+				word = wprev;
+				wprev = __ldg(obs + ch.ow0 + max((v >> 4) - 1, 0));
+			}
+			xm = (word >> ((v & 15) * 2)) & 3;
+		}
+		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
+		emis_coef(xu, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
+		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);
+		prefsuf2<SPL, G>(fm, M.W, M.U, ds, Pf, Sf);
+		if (trans) {
+			if (grow) store_vec<SPL>(grow - (size_t)t_of_chunk * NP, g);
+			const double inv = fast_rcp(sm);
+			const double w0 = (xm == 0) ? 1.0 : 0.0, w1 = (xm == 1) ? 1.0 : 0.0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				aRL[i] = fma(fm[i], Pg[i], aRL[i]);
+				aRU[i] = fma(fm[i], Sg[i], aRU[i]);
+				aAD[i] = fma(fm[i], g[i], aAD[i]);
+				aCL[i] = fma(g[i], Sf[i], aCL[i]);
+				aCU[i] = fma(g[i], Pf[i], aCU[i]);
+				const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i])); // = b_{u-1} s_{u-1} (khmm.c:230-234)
+				const double gam = fm[i] * bb;                                         // posterior of bin u-1 (khmm.c:317)
+				aE0[i] = fma(gam, w0, aE0[i]);
+				aE1[i] = fma(gam, w1, aE1[i]);
+				b[i] = bb * inv;
+			}
+			xu = xm;
+		}
+	}
+
+	__device__ __forceinline__ void run(double (&b)[SPL], double *__restrict__ part_c)
+	{
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) aE0[i] = aE1[i] = aRL[i] = aCL[i] = aRU[i] = aCU[i] = aAD[i] = 0.0;
+		ds.init(gl);
+		xu = (__ldg(obs + ch.ow0 + (ulast >> 4)) >> ((ulast & 15) * 2)) & 3;
+		const int v0 = max(ulast - 1, 0);
+		word = __ldg(obs + ch.ow0 + (v0 >> 4));
+		wprev = __ldg(obs + ch.ow0 + max((v0 >> 4) - 1, 0));
+		// aligned walk over f rows: step t uses global row rtop - t (the row of bin u - 1, u = that row's bin + 1)
+		const int64_t r_first = ch.gb0 + (ch.len - 1) - 1;               // f row of the chunk's first step (bin ulast)
+		rtop = r_first >= 0 ? (r_first | (ROWS - 1)) : (ROWS - 1);
+		rlo = ch.gb0 - (ch.u0 > 0 ? 1 : 0);                               // the left neighbour's last row is needed by bin u0
+		if (rlo < 0) rlo = 0;
+		const int my_tiles = (valid && r_first >= rlo) ? (int)(rtop / ROWS - rlo / ROWS + 1) : 0;
+		const int n_tiles = warp_trips(my_tiles);
+		const int64_t tile_top = rtop / ROWS;
+		if (gl == 0) {
+#pragma unroll
+			for (int k = 0; k < STAGES; ++k)
+				if (k < my_tiles) issue(tile_top - k, k);
+		}
+		__syncwarp();
+		for (int k = 0; k < n_tiles; ++k) {
+			const int stage = k % STAGES;
+			const uint32_t parity = (uint32_t)((k / STAGES) & 1);
+			if (k < my_tiles) mbar_wait(&bars[stage], parity, err_flag);
+			const double *rows = (const double *)(tiles + (size_t)stage * TILE_BYTES);
+			const double *scs = rows + ROWS * NP;
+#pragma unroll
+			for (int i = 0; i < ROWS; ++i) {
+				const int64_t row = rtop - ((int64_t)k * ROWS + i);   // f row of this step
+				const int u = (int)(row - ch.gb0) + ch.u0 + 1;        // the bin whose b is current
+				double fm[SPL];
+				const double *rp = rows + (size_t)(ROWS - 1 - i) * NP + s0;
+				if (k < my_tiles) {
+#pragma unroll
+					for (int q = 0; q < SPL; q += 2) {
+						const double2 t2 = *reinterpret_cast<const double2 *>(rp + q);
+						fm[q] = t2.x; fm[q + 1] = t2.y;
+					}
+				} else {
+#pragma unroll
+					for (int q = 0; q < SPL; ++q) fm[q] = 0.0;
+				}
+				const double sm = (k < my_tiles) ? scs[ROWS - 1 - i] : 1.0;
+				step(u, ulast - u, b, fm, sm);
+			}
+			__syncwarp(); // every lane of the group has consumed this stage: its first lane may refill it
+			if (gl == 0 && k + STAGES < my_tiles) issue(tile_top - (k + STAGES), stage);
+		}
+		if (valid) {
+			double *po = part_c + s0;
+#pragma unroll
+			for (int i = 0; i < SPL; ++i) {
+				po[S_E0 * NP + i] = aE0[i];
+				po[S_E1 * NP + i] = aE1[i];
+				po[S_RL * NP + i] = aRL[i] * M.U[i];
+				po[S_CL * NP + i] = aCL[i] * M.V[i];
+				po[S_RU * NP + i] = aRU[i] * M.W[i];
+				po[S_CU * NP + i] = aCU[i] * M.Z[i];
+				po[S_AD * NP + i] = aAD[i] * M.D[i];
+			}
+		}
+	}
+};
+
 template <int SPL, int G>
 __device__ __forceinline__ void backward_chunk2(const Chunk &ch, bool valid, const LaneModel<SPL> &M, double (&b)[SPL], int gl,
                                                 const uint32_t *__restrict__ obs, const double *__restrict__ fhat,
@@ -1682,6 +1905,47 @@ __global__ void __launch_bounds__(128) k_backward(const Chunk *__restrict__ chun
 		backward_chunk<SPL, G>(ch, id.valid, M, b, gl, obs, fhat, sc, part + (size_t)c * S_COUNT * NP,
 		                       bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave);
 	// b now belongs to the last bin of chunk c-1: publish its direction for the certificate
+	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && publish && !(ch.flags & CH_FIRST));
+}
+
+// K4 with the forward spill staged through shared memory by bulk-asynchronous copies (BackwardStaged); same contract as
+// k_backward<SPL, G, 2>.  Dynamic shared memory: BackwardStaged<SPL, G>::SMEM_BYTES.
+template <int SPL, int G>
+__global__ void __launch_bounds__(128) k_backward_staged(const Chunk *__restrict__ chunks, int n_chunks, const uint32_t *__restrict__ obs,
+                                                         const double *__restrict__ model, const double *__restrict__ bdir, int publish,
+                                                         const double *__restrict__ fhat, const double *__restrict__ sc, double *__restrict__ part,
+                                                         double *__restrict__ bexact, double *__restrict__ bsave_next, int warm_next,
+                                                         double *__restrict__ ghat, unsigned long long *__restrict__ err_flag)
+{
+	typedef BackwardStaged<SPL, G> BS;
+	constexpr int NP = SPL * G;
+	PSMC_DYN_SMEM(smem);
+	{ // one barrier per (group, stage), armed by the group's first lane
+		uint64_t *bars = (uint64_t *)(smem + (size_t)BS::GROUPS_PER_BLOCK * BS::GROUP_BYTES);
+		if (threadIdx.x < BS::GROUPS_PER_BLOCK * BS::STAGES) mbar_init(&bars[threadIdx.x], 1);
+		mbar_fence_init();
+		__syncthreads();
+	}
+	const GroupId<G> id(n_chunks);
+	if (!__any_sync(FULLMASK, id.valid)) return;
+	const int c = id.c, gl = id.gl, s0 = gl * SPL;
+	const Chunk ch = chunks[c];
+	LaneModel<SPL> M;
+	M.load(MODEL_OF(model, ch, NP), s0, NP);
+	const int ulast = ch.u0 + ch.len - 1;
+	const bool is_last = (ch.flags & CH_LAST) != 0;
+	double beta[SPL], b[SPL];
+	load_vec<SPL>(bdir + (size_t)c * NP + s0, beta);
+	scale_boundary<SPL, G>(ch, beta, b, gl, fhat, sc);
+	if (is_last) { // khmm.c:226: b_L[k] = 1/s_L
+		const double v = 1.0 / __ldg(sc + ch.gb0 + (ch.len - 1));
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) b[i] = v;
+	}
+	const int usave = (ch.flags & CH_FIRST) ? -1 : min(ch.u0 - 1 + warm_next, ulast);
+	BS r(ch, id.valid, M, gl, obs, fhat, sc, bsave_next ? bsave_next + (size_t)(c > 0 ? c - 1 : 0) * NP : nullptr, usave, ghat, smem,
+	     (int)(threadIdx.x / G), err_flag);
+	r.run(b, part + (size_t)c * S_COUNT * NP);
 	publish_direction<SPL, G>(b, bexact + (size_t)(c > 0 ? c - 1 : 0) * NP, gl, id.valid && publish && !(ch.flags & CH_FIRST));
 }
 

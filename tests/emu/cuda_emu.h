@@ -108,6 +108,8 @@ struct Fiber {
 	const std::function<void()> *entry = nullptr;
 };
 inline thread_local Fiber *cur = nullptr;
+inline thread_local unsigned char *dyn_smem_ptr = nullptr; // dynamic shared memory of the block this host thread is running
+inline unsigned char *dyn_smem() { return dyn_smem_ptr; }
 inline thread_local void *sched_sp = nullptr;
 inline thread_local uint64_t progress = 0;
 
@@ -174,7 +176,7 @@ inline double rcp_seed(double s)
 }
 
 template <class F>
-inline void launch(dim3 grid, dim3 block, F body);
+inline void launch(dim3 grid, dim3 block, F body, size_t smem_bytes = 0);
 
 } // namespace simt_emu
 
@@ -269,7 +271,7 @@ inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v)
 
 namespace simt_emu {
 template <class F>
-inline void launch(dim3 grid, dim3 block, F body)
+inline void launch(dim3 grid, dim3 block, F body, size_t smem_bytes)
 {
 	std::lock_guard<std::mutex> lk(launch_mutex());
 	const int nthreads = (int)(block.x * block.y * block.z);
@@ -284,6 +286,8 @@ inline void launch(dim3 grid, dim3 block, F body)
 		std::unique_ptr<char[]> stacks(new char[(size_t)nthreads * STACK + 64]); // untouched pages cost nothing
 		Block blk;
 		blk.warps = std::vector<Warp>(nwarps);
+		std::unique_ptr<unsigned char[]> dsm(new unsigned char[smem_bytes + 256]);
+		dyn_smem_ptr = (unsigned char *)(((uintptr_t)dsm.get() + 127) & ~(uintptr_t)127);
 		for (;;) {
 			const long b = next.fetch_add(1);
 			if (b >= nblocks) break;
@@ -432,6 +436,9 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent
 	*ms = 0.f;
 	return cudaSuccess;
 }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class K>
+static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class K>
 static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t)
 {

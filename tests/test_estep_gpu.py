@@ -253,16 +253,20 @@ def test_benchmark_regime_matches_unmodified_reference(ref, L, seed):
     m0 = ref.update_hmm("4+25*2+4+6", np.concatenate([[th, th / 5.0, 15.0], np.ones(28)]))
     m1 = make_model(ref, N, seed=7, theta=0.05)
     with EStep([seq], N) as es:
-        for it, m in enumerate((m0, m1)):
+        for it, m in enumerate((m0, m1, m1)):
             got = es.run(_model(m))
             info = es.info()
             want = _ref_stats(ref, m, [seq])
             errs = compare_stats(got, want, TOL, N)
-            print("L=%d E-step %d: chunks %d x %d, failed fwd/bwd %d/%d, fallbacks %d, worst rel err %s"
-                  % (L, it, info["n_chunks"], info["chunk_len"], info["failed_fwd"], info["failed_bwd"], info["fallbacks"],
-                     {k: "%.1e" % v for k, v in errs.items()}))
+            print("L=%d E-step %d: chunks %d x %d, planned %d (mean overlaps %.0f / %.0f), failed fwd/bwd %d/%d, fallbacks %d, worst rel err %s"
+                  % (L, it, info["n_chunks"], info["chunk_len"], info["planned"], info["avg_overlap_fwd"], info["avg_overlap_bwd"],
+                     info["failed_fwd"], info["failed_bwd"], info["fallbacks"], {k: "%.1e" % v for k, v in errs.items()}))
             assert info["fallbacks"] == 0
-            assert info["warm_len"] > 0 and info["n_chunks"] > 900      # the default plan: one resident wave, fast path
+            assert info["warm_len"] > 0                                 # the fast path (overlaps + certificate), default settings
+            if it == 0:
+                assert info["planned"] == 0 and info["n_chunks"] > 900  # first E-step: fixed overlaps, one resident wave of chunks
+            else:
+                assert info["planned"] == 1                             # then the overlaps the mixing probe of E-step 0 asked for
             assert info["fwd_mismatch"] < 1e-12 and info["bwd_mismatch"] < 1e-12
 
 
@@ -357,3 +361,22 @@ def test_batch_of_models_matches_oracle_and_single_runs(oracle, chunk_len):
                 assert np.array_equal(got[r][k], alone[r][k]), k
         else:
             compare_stats(got[r], alone[r], 1e-11, N)
+
+
+def test_staged_backward_equals_register_ring(oracle, monkeypatch):
+    """bulk-asynchronous staging of the forward spill (cp.async.bulk + mbarrier, the default) vs the register prefetch ring:
+    the same arithmetic, hence the same bits -- at a size where tiles wrap the ring many times"""
+    from psmc_b200 import EStep
+    N = 64
+    m = make_model(oracle, N, seed=151)
+    seqs = _seqs(m, [1, 2, 7, 8, 9, 70000, 10333, 64], seed=152)
+    res = {}
+    for tma in ("0", "1"):
+        monkeypatch.setenv("PSMC_B200_TMA", tma)
+        with EStep(seqs, N, chunk_len=613) as es:
+            es.set_warm(3000)
+            res[tma] = es.run(_model(m))
+    compare_stats(res["1"], oracle_stats(oracle, m, seqs), TOL, N)
+    assert res["0"]["LL"] == res["1"]["LL"]
+    for k in ("E", "RL", "CL", "RU", "CU", "AD"):
+        assert np.array_equal(res["0"][k], res["1"][k]), k

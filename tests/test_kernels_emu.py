@@ -366,3 +366,24 @@ def test_emulated_mixing_probe_plans_the_overlaps(oracle, emu_plain, monkeypatch
     assert infos[1]["slow_fwd"] > 0 and infos[1]["slow_bwd"] > 0      # the tract
     print([(i["planned"], i["n_chunks"], i["chunk_len"], round(i["avg_overlap_fwd"]), round(i["avg_overlap_bwd"]), i["slow_fwd"], i["slow_bwd"],
             i["failed_fwd"], i["failed_bwd"], i["repair_rounds"]) for i in infos])
+
+
+@pytest.mark.parametrize("N", [23, 64])
+def test_emulated_staged_backward_equals_register_ring(oracle, emu_plain, monkeypatch, N):
+    """the backward pass with the forward spill staged through shared memory (bulk-asynchronous copies + mbarrier, the
+    default) performs the same arithmetic as the register-prefetch variant: same bits, ragged records, dense option included"""
+    from psmc_b200 import EStep
+    m = make_model(oracle, N, seed=151)
+    seqs = _seqs(m, [1, 2, 7, 8, 9, 700, 1033, 64], seed=152)
+    res = {}
+    for tma in ("0", "1"):
+        monkeypatch.setenv("PSMC_B200_TMA", tma)
+        with EStep(seqs, N, chunk_len=61) as es:
+            es.set_warm(150)
+            es.set_dense(True)
+            res[tma] = (es.run(_model(m)), es.dense_counts())
+    compare_stats(res["1"][0], oracle_stats(oracle, m, seqs), TOL, N)
+    assert res["0"][0]["LL"] == res["1"][0]["LL"]
+    for k in ("E", "RL", "CL", "RU", "CU", "AD"):
+        assert np.array_equal(res["0"][0][k], res["1"][0][k]), k
+    assert np.array_equal(res["0"][1], res["1"][1])
