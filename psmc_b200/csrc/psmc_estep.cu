@@ -75,6 +75,8 @@
 		kfn_<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
 	} while (0)
 #define PIN_REG(x) asm volatile("" : "+d"(x))
+#define PIN_PTR(x) asm volatile("" : "+l"(x))
+#define PIN_INT(x) asm volatile("" : "+r"(x))
 #else
 #define LAUNCH_SMEM(kern, grid, block, smem, stream, ...)             \
 	do {                                                              \
@@ -87,6 +89,8 @@
 		simt_emu::launch((grid), (block), [&]() { kfn_(__VA_ARGS__); }); \
 	} while (0)
 #define PIN_REG(x) ((void)(x))
+#define PIN_PTR(x) ((void)(x))
+#define PIN_INT(x) ((void)(x))
 #endif
 #define HMM_TINY_ 1e-25 /* khmm.h:28 */
 

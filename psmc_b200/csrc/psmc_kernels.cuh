@@ -834,6 +834,8 @@ struct ForwardRun {
 	uint32_t wa, wb, wna, wnb; // packed observation words of the current block (word ia and the one after it) / of the next block (ina)
 	int ia, ina;
 	double *prow, *psc; // where the row / scale factor of the bin finished by the next store-phase step go (advance one bin per step)
+	double *pwarm;      // fwarm_c + s0, and "am I the group's first lane": made opaque (PIN_*) before the store loop, otherwise ptxas
+	int lane0;          // re-derives both from SR_TID.X in every iteration (two S2R per bin, 5 % of the kernel's stall samples: ncu r02)
 
 	__device__ __forceinline__ ForwardRun(const Chunk &ch_, bool valid_, const LaneModel<SPL> &M_, int gl_,
 	                                      const uint32_t *__restrict__ obs_, double *__restrict__ fhat_, double *__restrict__ sc_,
@@ -893,9 +895,9 @@ struct ForwardRun {
 				double fn[SPL];
 #pragma unroll
 				for (int i = 0; i < SPL; ++i) fn[i] = g[i] * inv1;
-				store_vec<SPL>(st_f ? prow : fwarm_c + s0, fn);
+				store_vec<SPL>(st_f ? prow : pwarm, fn);
 			}
-			if (st_f && gl == 0) *psc = S1 * inv_prev * rq_cur;
+			if (st_f && lane0) *psc = S1 * inv_prev * rq_cur;
 			prow += NP;
 			psc += 1;
 			if (u == u_first) Sstart = S1;
@@ -971,6 +973,10 @@ struct ForwardRun {
 			const long long row0 = (long long)ch.gb0 + ((long long)ubase + t - 1 - u0);
 			prow = (double *)((char *)fhat + (row0 * NP + s0) * (long long)sizeof(double));
 			psc = (double *)((char *)sc + row0 * (long long)sizeof(double));
+			pwarm = fwarm_c ? fwarm_c + s0 : prow;
+			lane0 = gl == 0 ? 1 : 0;
+			PIN_PTR(pwarm);
+			PIN_INT(lane0);
 		}
 		while (t < trips) { // store phase
 			if (t == tpend) start_due(t, f, inv_before);
