@@ -290,8 +290,10 @@ static void *batch_worker(void *arg)
 		}
 		if (w->o->verbose) {
 			psmc_b200_get_info(ctx, &inf);
-			fprintf(stderr, "[psmc-b200] replicates %d..%d on device %d: %lld bins drawn, plan %.1f ms, chunks %d x %d (backward %d x %d), fallbacks %d, %.1f ms\n",
-			        r0, r0 + b - 1, w->o->devices[w->gpu_slot], (long long)inf.active_bins, t_plan, inf.n_chunks, inf.chunk_len, inf.n_chunks_bwd, inf.chunk_len_bwd, inf.fallbacks, now_ms() - t0);
+			fprintf(stderr, "[psmc-b200] replicates %d..%d on device %d: %lld bins drawn, plan %.1f ms, chunks %d x %d (backward %d x %d), fallbacks %d, %.1f ms; last E-step on the device: %.1f ms "
+			        "(forward %.1f [kernel %.1f], backward %.1f [kernel %.1f]), failed boundaries %d/%d, repair rounds %d\n",
+			        r0, r0 + b - 1, w->o->devices[w->gpu_slot], (long long)inf.active_bins, t_plan, inf.n_chunks, inf.chunk_len, inf.n_chunks_bwd, inf.chunk_len_bwd, inf.fallbacks, now_ms() - t0,
+			        inf.ms[5], inf.ms[2], inf.ms[6], inf.ms[3], inf.ms[7], inf.failed_fwd, inf.failed_bwd, inf.repair_rounds);
 		}
 		for (j = 0; j < b; ++j) { psmch_em_free(&em[j]); fclose(fp[j]); fp[j] = 0; }
 		if (w->rc != 0) break;

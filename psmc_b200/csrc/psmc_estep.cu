@@ -163,7 +163,7 @@ struct psmc_b200_ctx {
 	// run (its left vector changed).  With chunks much shorter than the overlap (small inputs, many GPUs) a slow tract
 	// needs many rounds.  rounds_cur adapts: two more than the deepest round of the last E-step that still saw a failure; if
 	// the certificate fails, the E-step is first redone on the fast path with rounds_max rounds, then with exact operators.
-	int rounds_cur = 3, rounds_max = 48, warm_redos = 0;
+	int rounds_cur = 3, rounds_max = 48, warm_redos = 0; // (rounds_max <= 64: one device counter per round and direction)
 	bool rounds_fixed = false; // PSMC_B200_REPAIR_ROUNDS given
 	bool redoing = false;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
@@ -223,13 +223,16 @@ struct psmc_b200_ctx {
 	// (plus a margin), chunk lengths balanced so that overlap + length is the same for every chunk, and the boundaries no
 	// admissible overlap reaches known in advance (their operators are "predicted" from the first E-step of a plan on).
 	bool probe_on = true;        // PSMC_B200_PROBE=0: fixed overlaps, uniform chunks (the round-1 plans)
+	bool probe_batch = false;    // PSMC_B200_PROBE_BATCH=1: also in batch mode (measured on B200: no gain there -- chunks are ~100 k bins, the
+	                             // overlaps a few percent of the work, and a probe costs a third of a batch E-step)
 	int estep_no = 0;            // E-steps launched on the current sequences
 	bool probe_now = false;      // the E-step in flight also runs k_probe
 	bool plan_dirty = false;     // a probe result is waiting: re-plan before the next E-step
 	bool have_probe = false, planned = false;
 	float *d_probeK = nullptr, *h_probeK = nullptr;
 	int64_t cap_probeK = 0, n_probeK = 0;
-	std::vector<std::vector<double>> probe_cum; // per kept sequence: cum[j] = log contraction accumulated over the bins < 64 j (non-increasing)
+	std::vector<std::vector<double>> probe_cum; // per kept sequence: cum[j] = log contraction accumulated over the bins < 64 j (non-increasing); empty = not probed yet
+	std::vector<int32_t> vseq_seq;              // virtual sequence -> kept sequence (batch mode: a record appears once per model that drew it)
 	double probe_th = 35.0;      // e-folds an overlap must cover: ln(1 / 1e-12) = 27.6 + margin (start distance, probe accuracy); swept on B200
 	int probe_hmax = 0, probe_hslow = 0, probe_lead = 0, probe_plans = 0; // 0 = derived from the fixed overlap: 5/3, 1/6 and 1/12 of it (20480 / 2048 / 1024 bins)
 	int hmax() const { return probe_hmax > 0 ? probe_hmax : warm_len + 2 * warm_len / 3; }
@@ -527,6 +530,8 @@ static int replan(psmc_b200_ctx *c)
 		}
 	c->n_seq_eff = c->rep_seq_eff[0];
 	c->n_vseq = (int)vs.size();
+	c->vseq_seq.resize(vs.size());
+	for (size_t v = 0; v < vs.size(); ++v) c->vseq_seq[v] = vs[v].seq;
 	c->seq_c0.assign((size_t)std::max(c->n_vseq, 1), 0); c->seq_nc.assign((size_t)std::max(c->n_vseq, 1), 0); c->seq_gb0.assign((size_t)std::max(c->n_vseq, 1), 0);
 	// The chunk kernels are latency-bound and every block lives as long as the kernel, so a plan must fit in ONE
 	// resident wave of its kernel (one block too many doubles the kernel time; more chunks only add warm-up work).
@@ -547,7 +552,22 @@ static int replan(psmc_b200_ctx *c)
 	std::vector<int32_t> k1;
 	std::vector<double> cw, cw_b;
 	// planned overlaps: one target T = overlap + length per plan, the smallest that fits the plan into one resident wave
-	const bool planned = c->have_probe && c->probe_on && !c->batch && c->chunk_len_req <= 0 && c->warm_len > 0 && (int)c->probe_cum.size() == c->n_seqs;
+	// (a record the probe has not seen yet -- batch mode: first drawn by this batch -- is cut uniformly with the fixed overlap)
+	const bool planned = c->have_probe && c->probe_on && (!c->batch || c->probe_batch) && c->chunk_len_req <= 0 && c->warm_len > 0 && (int)c->probe_cum.size() == c->n_seqs;
+	auto has_cum = [&](int seq) { return !c->probe_cum[seq].empty(); };
+	auto cut_any = [&](int seq, int T, int dir, int hm, std::vector<Piece> *out) {
+		const int Li = c->L[seq];
+		if (has_cum(seq)) return cut_sequence(c->probe_cum[seq], Li, T, dir, c->probe_th, hm, c->hslow(), out);
+		const int warm = dir == 0 ? c->warm_len : c->warm_len_bwd;
+		const int clen = std::max(512, dir == 0 ? (T - warm) / 2 : T);
+		const int nc0 = (Li + clen - 1) / clen;
+		if (out)
+			for (int k = 0; k < nc0; ++k) {
+				const int64_t a = (int64_t)Li * k / nc0, b = (int64_t)Li * (k + 1) / nc0;
+				out->push_back({(int32_t)a, (int32_t)(b - a), warm, 0});
+			}
+		return nc0;
+	};
 	int T_plan[2] = {0, 0}, hmax_plan[2] = {0, 0};
 	if (planned) {
 		// forward plan: the kernel runs overlap + length steps per chunk (a stored step costing two warm-up steps) and lasts as
@@ -560,7 +580,7 @@ static int replan(psmc_b200_ctx *c)
 			auto count = [&](int T) {
 				int64_t n = 0;
 				for (int v = 0; v < c->n_vseq; ++v)
-					if (vs[v].mult > 0) n += cut_sequence(c->probe_cum[vs[v].seq], c->L[vs[v].seq], T, dir, c->probe_th, cap(T), c->hslow(), nullptr);
+					if (vs[v].mult > 0) n += cut_any(vs[v].seq, T, dir, cap(T), nullptr);
 				return n;
 			};
 			int lo = dir == 0 ? c->warm_len + 1024 : 512, hi = 1 << 25;
@@ -584,7 +604,7 @@ static int replan(psmc_b200_ctx *c)
 			pieces.clear();
 			if (vs[v].mult > 0) {
 				if (planned) {
-					cut_sequence(c->probe_cum[i], Li, T_plan[is_main ? 0 : 1], is_main ? 0 : 1, c->probe_th, hmax_plan[is_main ? 0 : 1], c->hslow(), &pieces);
+					cut_any(i, T_plan[is_main ? 0 : 1], is_main ? 0 : 1, hmax_plan[is_main ? 0 : 1], &pieces);
 				} else {
 					const int nc0 = (Li + clen - 1) / clen;
 					for (int k = 0; k < nc0; ++k) {
@@ -846,6 +866,8 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		if (env) c->staged_bwd = atoi(env) != 0;
 		env = getenv("PSMC_B200_PROBE");
 		if (env) c->probe_on = atoi(env) != 0;
+		env = getenv("PSMC_B200_PROBE_BATCH");
+		if (env) c->probe_batch = atoi(env) != 0;
 		env = getenv("PSMC_B200_PROBE_TH");
 		if (env && atof(env) > 0) c->probe_th = atof(env);
 		env = getenv("PSMC_B200_PROBE_HMAX");
@@ -923,7 +945,7 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 	} while (0)
 	c->bytes_obs = c->words_obs * 4;
 	ALLOC(c->d_obs, c->bytes_obs);
-	ALLOC(c->d_cert, sizeof(unsigned long long) * 16);
+	ALLOC(c->d_cert, sizeof(unsigned long long) * 144); // 16 counters + one "flagged in this round" counter per repair round and direction
 #undef ALLOC
 #define CTRY(call)                                                                                \
 	do {                                                                                          \
@@ -1000,6 +1022,8 @@ extern "C" int psmc_b200_set_batch(psmc_b200_ctx *c, int32_t n_rep, const int32_
 	c->bmult.swap(m);
 	c->batch = true;
 	c->n_rep = n_rep;
+	c->estep_no = 0; // (the probe schedule restarts with every batch; records probed before keep their data)
+	c->plan_dirty = false;
 	rc = replan(c);
 	if (rc) { // (typically: the forward spill of so many models does not fit) -- back to single mode, still usable
 		c->batch = false; c->n_rep = 1; c->bmult.clear();
@@ -1054,7 +1078,7 @@ extern "C" int psmc_b200_upload(psmc_b200_ctx *c, int32_t n_seqs, const int32_t 
 		if (h != c->obs_hash) {
 			c->obs_hash = h;
 			c->estep_no = 0;
-			if (c->have_probe) { c->have_probe = false; c->plan_dirty = c->planned; }
+			if (c->have_probe) { c->have_probe = false; c->probe_cum.clear(); c->plan_dirty = c->planned; }
 		}
 	}
 	c->fwd_valid = false; // (have_prev stays: stale vectors are still legal warm starts, the certificate decides)
@@ -1128,10 +1152,10 @@ static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 #undef FWD
 }
 template <int NP>
-static void run_forward_repair(psmc_b200_ctx *c)
+static void run_forward_repair(psmc_b200_ctx *c, const unsigned long long *rcnt)
 {
 	cudaStream_t st = c->stream;
-#define FWR(G_, V_) LAUNCH((k_forward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub, G_), 128, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4)
+#define FWR(G_, V_) LAUNCH((k_forward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub, G_), 128, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4, rcnt)
 	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWR(16, 2);
 	else if (c->gen == 2) FWR(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWR(8, 1);
@@ -1175,10 +1199,10 @@ static void run_backward_warm(psmc_b200_ctx *c, cudaStream_t st, int warm, int u
 #undef BWW
 }
 template <int NP>
-static void run_backward_repair(psmc_b200_ctx *c)
+static void run_backward_repair(psmc_b200_ctx *c, const unsigned long long *rcnt)
 {
 	cudaStream_t st = c->stream;
-#define BWR(G_, V_) LAUNCH((k_backward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub_b, G_), 128, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4, (c->dense && V_ == 2) ? c->d_ghat : nullptr)
+#define BWR(G_, V_) LAUNCH((k_backward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub_b, G_), 128, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_chunks_b, c->d_obs, c->d_model, c->d_flag_b + 1, c->d_bsub, c->d_fhat, c->d_sc, c->d_partsub, c->d_bwarm, c->d_bexact, c->d_cert + 4, (c->dense && V_ == 2) ? c->d_ghat : nullptr, rcnt)
 	if constexpr (Gen2<NP>::BWD_OK) {
 		if (c->gen == 2) {
 			BWR(Gen2<NP>::G_BWD, 2);
@@ -1232,7 +1256,7 @@ static int launch_core(psmc_b200_ctx *c, bool with_counts)
 	if (c->n_k1 > 0) {
 		constexpr int G1 = (NP > 64) ? 16 : 8, SPL1 = NP / G1, COLS = 128 / G1;
 		dim3 grid((unsigned)c->n_k1, NP / COLS);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), grid, COLS * G1, st, c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr, c->n_k1, nullptr, 0);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), grid, COLS * G1, st, c->d_chunks, c->d_k1, c->d_obs, c->d_model, c->d_T, c->d_Tex, c->N, nullptr, 0, nullptr, c->n_k1, nullptr, 0, nullptr);
 		++c->launches;
 	}
 	cudaEventRecord(c->ev[1], st);
@@ -1270,7 +1294,7 @@ static int launch_warm(psmc_b200_ctx *c)
 {
 	constexpr int NP = 32 * SPL;
 	cudaStream_t st = c->stream;
-	cudaMemsetAsync(c->d_cert, 0, sizeof(unsigned long long) * 16, st);
+	cudaMemsetAsync(c->d_cert, 0, sizeof(unsigned long long) * 144, st);
 	const int rounds = c->rounds_cur;
 	// reach of a cascade front in chunks (see k_mark_fwd): overlap / chunk length, at least one chunk
 	const int spread_f = std::min(16, std::max(1, (c->warm_len + c->chunk_len - 1) / std::max(c->chunk_len, 1)));
@@ -1296,7 +1320,7 @@ static int launch_warm(psmc_b200_ctx *c)
 	const int32_t *pred = c->predict ? c->d_pred[c->pred_cur] + 1 : nullptr, *pred_b = c->predict ? c->d_pred_b[c->pred_cur] + 1 : nullptr;
 	int32_t *pred_next = c->d_pred[c->pred_cur ^ 1] + 1, *pred_next_b = c->d_pred_b[c->pred_cur ^ 1] + 1;
 	auto side_k1f = [&]() {
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, c->stream2, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr, c->n_sub, c->d_chunk_sub0, 0);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, c->stream2, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, pred, 3, nullptr, c->n_sub, c->d_chunk_sub0, 0, nullptr);
 		cudaEventRecord(c->ev_k1f, c->stream2);
 	};
 	auto side_warm = [&]() {
@@ -1308,16 +1332,17 @@ static int launch_warm(psmc_b200_ctx *c)
 	cudaEventRecord(c->ev[6], st); // forward kernel done (the repair rounds follow)
 	if (c->predict) side_k1f();
 	if (c->predict) {
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, c->stream2, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, pred_b, 3, nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1, nullptr);
 		cudaEventRecord(c->ev_k1b, c->stream2);
 		cudaStreamWaitEvent(st, c->ev_k1f, 0);
 	}
 	for (int r = 0; r < rounds; ++r) {
-		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr, c->d_cert + 8, r == 0 ? 0 : spread_f, r);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub, c->d_chunk_sub0, 0);
-		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
-		run_forward_repair<NP>(c);
-		LAUNCH((k_fold), c->n_chunks, 128, st, c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
+		unsigned long long *rc_f = c->d_cert + 16 + r;
+		LAUNCH((k_mark_fwd<SPL>), nblk, wpb * 32, st, c->d_chunks, c->n_chunks, c->N, c->cert_eps, c->d_fhat, c->d_fwarm, c->d_flag + 1, c->d_cert + 4, r == 0 ? pred_next : nullptr, c->d_cert + 8, r == 0 ? 0 : spread_f, r, rc_f);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridT, COLS * G1, st, c->d_sub, c->d_sub_parent, c->d_obs, c->d_model, c->d_Tsub, c->d_Texsub, c->N, c->d_flag + 1, 3, r == 0 ? pred : nullptr, c->n_sub, c->d_chunk_sub0, 0, rc_f);
+		LAUNCH((k_chain_subs<NP>), c->n_chunks, NP, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_flag + 1, 0, c->d_Tsub, c->d_Texsub, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub, rc_f);
+		run_forward_repair<NP>(c, rc_f);
+		LAUNCH((k_fold), c->n_chunks, 128, st, c->d_chunk_sub0, c->d_flag + 1, 0, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part, rc_f);
 	}
 	cudaEventRecord(c->ev[3], st);
 	cudaStreamWaitEvent(st, c->ev_join, 0);
@@ -1326,11 +1351,12 @@ static int launch_warm(psmc_b200_ctx *c)
 	c->bsave_cur ^= 1;
 	if (c->predict) cudaStreamWaitEvent(st, c->ev_k1b, 0);
 	for (int r = 0; r < rounds; ++r) {
-		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr, c->d_cert + 9, r == 0 ? 0 : spread_b, r);
-		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1);
-		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub);
-		run_backward_repair<NP>(c);
-		LAUNCH((k_fold), c->n_chunks_b, 128, st, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part);
+		unsigned long long *rc_b = c->d_cert + 16 + 64 + r;
+		LAUNCH((k_mark_bwd<SPL>), nblk_b, wpb * 32, st, c->d_chunks_b, c->n_chunks_b, c->N, c->cert_eps, c->d_bwarm, c->d_bexact, c->d_flag_b + 1, c->d_cert + 4, r == 0 ? pred_next_b : nullptr, c->d_cert + 9, r == 0 ? 0 : spread_b, r, rc_b);
+		LAUNCH((k_transfer<SPL1, G1, COLS>), gridTb, COLS * G1, st, c->d_sub_b, c->d_sub_parent_b, c->d_obs, c->d_model, c->d_Tsub_b, c->d_Texsub_b, c->N, c->d_flag_b + 1, 3, r == 0 ? pred_b : nullptr, c->n_sub_b, c->d_chunk_sub0_b, 1, rc_b);
+		LAUNCH((k_chain_subs<NP>), c->n_chunks_b, NP, st, c->d_sub_b, c->n_sub_b, c->d_sub_parent_b, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, c->d_Tsub_b, c->d_Texsub_b, c->d_fhat, c->d_bexact, c->d_vsub, c->d_bsub, rc_b);
+		run_backward_repair<NP>(c, rc_b);
+		LAUNCH((k_fold), c->n_chunks_b, 128, st, c->d_chunk_sub0_b, c->d_flag_b + 1, 1, NP, c->d_llsub, c->d_llpart, c->d_partsub, c->d_part, rc_b);
 	}
 	cudaEventRecord(c->ev[4], st);
 	LAUNCH((k_reduce), dim3(1 + S_COUNT * c->N, c->n_rep), 256, st, c->d_part, c->d_llpart, c->d_rep_c0, c->d_rep_c0_b, c->N, NP, c->d_stats, c->weighted ? c->d_cw : nullptr, c->weighted ? c->d_cw_b : nullptr);
@@ -1357,12 +1383,19 @@ static int launch_warm(psmc_b200_ctx *c)
 // the probe's pieces (k_probe) -> per sequence, the log contraction accumulated along a 64-bin grid
 static void parse_probe(psmc_b200_ctx *c)
 {
-	c->probe_cum.assign((size_t)c->n_seqs, std::vector<double>());
-	for (int i = 0; i < c->n_seqs; ++i) c->probe_cum[i].assign((size_t)((c->L[i] + 63) / 64) + 1, 0.0);
+	if ((int)c->probe_cum.size() != c->n_seqs) c->probe_cum.assign((size_t)c->n_seqs, std::vector<double>());
+	std::vector<char> touched((size_t)std::max(c->n_seqs, 1), 0);
 	const float *K = c->h_probeK;
+	int last_v = -1;
 	for (int ci = 0; ci < c->n_chunks; ++ci) {
 		const Chunk &ch = c->chunks[ci];
-		std::vector<double> &cell = c->probe_cum[ch.seq]; // (single mode: the virtual sequence index is the kept-record index)
+		const int seq = c->vseq_seq[ch.seq];
+		std::vector<double> &cell = c->probe_cum[seq];
+		if (ch.seq != last_v) { // a new virtual sequence: its record's cells start from zero (batch mode: the last model that drew a record wins)
+			cell.assign((size_t)((c->L[seq] + 63) / 64) + 1, 0.0);
+			touched[seq] = 1;
+			last_v = ch.seq;
+		}
 		int64_t k = (ch.gb0 >> 6) + ci;
 		int u = ch.u0;
 		const int uend = ch.u0 + ch.len;
@@ -1372,7 +1405,7 @@ static void parse_probe(psmc_b200_ctx *c)
 			double v = (k < c->n_probeK) ? (double)K[k] : 0.0;
 			if (!(v <= 0.0) || !std::isfinite(v)) v = 0.0;
 			const double per_bin = v / (double)(ue - u + 1);
-			for (int x = u; x <= ue;) { // spread over the sequence's own 64-bin cells
+			for (int x = u; x <= ue;) { // spread over the record's own 64-bin cells
 				const int xe = std::min(ue, x | 63);
 				cell[(size_t)(x >> 6) + 1] += per_bin * (double)(xe - x + 1);
 				x = xe + 1;
@@ -1382,6 +1415,7 @@ static void parse_probe(psmc_b200_ctx *c)
 		}
 	}
 	for (int i = 0; i < c->n_seqs; ++i) { // cells -> prefix sums: cum[j] = accumulated over the bins < 64 j
+		if (!touched[i]) continue;
 		std::vector<double> &cum = c->probe_cum[i];
 		for (size_t j = 1; j < cum.size(); ++j) cum[j] += cum[j - 1];
 	}
@@ -1419,13 +1453,21 @@ static int launch_models(psmc_b200_ctx *c, int n_rep, const psmc_b200_model *mod
 	}
 	CUDA_TRY(cudaSetDevice(c->device), PSMC_B200_ECUDA);
 	CUDA_TRY(cudaStreamSynchronize(c->stream), PSMC_B200_ECUDA); // pinned staging buffer is reused
-	if (c->plan_dirty && !c->batch) { // a mixing probe came back with the previous E-step: new plans with the overlaps it asks for
+	if (c->plan_dirty) { // a mixing probe came back with the previous E-step: new plans with the overlaps it asks for
 		c->plan_dirty = false;
 		int rc = replan(c);
 		if (rc) return rc;
 	}
-	// probe on the E-steps 0, 1, 2, 4, 8, ... of a context (the model moves fast early in EM, slowly later)
-	c->probe_now = c->probe_on && !c->batch && !c->dense && c->warm_len > 0 && c->n_k1 > 0 && c->chunk_len_req <= 0 && (c->estep_no & (c->estep_no - 1)) == 0;
+	// probe on the E-steps 0, 2, 8, 32, 128, ... of a context (the model moves fast early in EM, slowly later; a probe costs
+	// about as much as the forward kernel, a stale plan a few more repaired boundaries)
+	bool due = c->estep_no == 0;
+	for (int e = 2; e <= c->estep_no && !due; e *= 4) due = (e == c->estep_no);
+	if (due && c->estep_no == 0 && c->have_probe && (int)c->probe_cum.size() == c->n_seqs) { // (batch mode: records probed by an earlier batch keep their plan data)
+		bool all = true;
+		for (int v = 0; v < c->n_vseq && all; ++v) all = !c->probe_cum[c->vseq_seq[v]].empty();
+		if (all) due = false;
+	}
+	c->probe_now = c->probe_on && (!c->batch || c->probe_batch) && !c->dense && c->warm_len > 0 && c->n_k1 > 0 && c->chunk_len_req <= 0 && due;
 	if (c->probe_now) {
 		const int64_t need = (c->cap_bins >> 6) + c->n_chunks + 2;
 		if (need > c->cap_probeK) {

@@ -393,9 +393,11 @@ __global__ void __launch_bounds__(COLS *G) k_transfer(const Chunk *__restrict__ 
                                                       const uint32_t *__restrict__ obs, const double *__restrict__ model,
                                                       double *__restrict__ T, int32_t *__restrict__ Tex, int N,
                                                       const int32_t *__restrict__ flag, int sel, const int32_t *__restrict__ skip,
-                                                      int n_items, const int32_t *__restrict__ chunk_sub0, int dir)
+                                                      int n_items, const int32_t *__restrict__ chunk_sub0, int dir,
+                                                      const unsigned long long *__restrict__ round_cnt)
 {
 	constexpr int NP = SPL * G;
+	if (round_cnt && *round_cnt == 0) return; // nothing flagged in this repair round
 	// sel 0: chunk list (transfer mode), one block row per listed chunk.  sel 3: repair rounds of the warm-up mode: `chunks`
 	// is the SUB-chunk table; the block rows stride over it and work on the sub-chunks whose parent chunk is flagged (flag has
 	// guard entries at -1 and n) -- a few hundred of ~19 000, so a block row per sub-chunk would spend 0.1 ms per launch on
@@ -579,9 +581,10 @@ __global__ void __launch_bounds__(NP) k_chain_subs(const Chunk *__restrict__ sub
                                                    const int32_t *__restrict__ chunk_sub0, const int32_t *__restrict__ flag, int dir,
                                                    const double *__restrict__ T, const int32_t *__restrict__ Tex,
                                                    const double *__restrict__ fhat, const double *__restrict__ bexact,
-                                                   double *__restrict__ vsub, double *__restrict__ bsub)
+                                                   double *__restrict__ vsub, double *__restrict__ bsub, const unsigned long long *__restrict__ round_cnt)
 {
 	__shared__ double vec[NP];
+	if (*round_cnt == 0) return;
 	__shared__ double red[4];
 	__shared__ int redi[4];
 	const int c = blockIdx.x, i = threadIdx.x;
@@ -612,8 +615,9 @@ __global__ void __launch_bounds__(NP) k_chain_subs(const Chunk *__restrict__ sub
 // (dir 0: log-likelihood partials; dir 1: expected-count partials).  One block per chunk.
 __global__ void __launch_bounds__(128) k_fold(const int32_t *__restrict__ chunk_sub0, const int32_t *__restrict__ flag, int dir, int NP,
                                               const double *__restrict__ llsub, double *__restrict__ llpart,
-                                              const double *__restrict__ partsub, double *__restrict__ part)
+                                              const double *__restrict__ partsub, double *__restrict__ part, const unsigned long long *__restrict__ round_cnt)
 {
+	if (*round_cnt == 0) return;
 	const int c = blockIdx.x;
 	if (!flag[c]) return;
 	const int s0 = chunk_sub0[c], s1 = chunk_sub0[c + 1];
@@ -1127,7 +1131,7 @@ __global__ void __launch_bounds__(128) k_probe(const Chunk *__restrict__ chunks,
 			for (int i = 0; i < SPL; ++i) {
 				tot += h[i];
 				if (s0 + i < N && f[i] > 0.0 && h[i] > 0.0) {
-					const double r = h[i] / f[i];
+					const double r = h[i] * fast_rcp(f[i]);
 					mx = fmax(mx, r);
 					mn = fmin(mn, r);
 				}
@@ -1152,7 +1156,7 @@ __global__ void __launch_bounds__(128) k_probe(const Chunk *__restrict__ chunks,
 				const double sc_ = (dist < 1e-6) ? kappa / dist : 1.0, inv = 1.0 / tot;
 #pragma unroll
 				for (int i = 0; i < SPL; ++i) {
-					if (s0 + i < N && f[i] > 0.0 && h[i] > 0.0 && sc_ != 1.0) h[i] = f[i] * fma(h[i] / (f[i] * mn) - 1.0, sc_, 1.0);
+					if (s0 + i < N && f[i] > 0.0 && h[i] > 0.0 && sc_ != 1.0) h[i] = f[i] * fma(h[i] * fast_rcp(f[i] * mn) - 1.0, sc_, 1.0);
 					else h[i] *= inv; // (sum-normalised: the chain is carried unnormalised between knots)
 				}
 				if (sc_ != 1.0) d_prev = kappa; // (the relative deviations now span [0, dist * sc_])
@@ -1187,8 +1191,10 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ fhat, const double *__restrict__ fwarm,
                                                   int32_t *__restrict__ flag_f, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next, unsigned long long *__restrict__ last_round, int spread, int round)
+                                                  int32_t *__restrict__ pred_next, unsigned long long *__restrict__ last_round, int spread, int round,
+                                                  unsigned long long *__restrict__ round_cnt)
 {
+	// round_cnt: chunks flagged by THIS round -- the other kernels of the round return at once when it stays zero.
 	// spread > 0 (rounds after the first): a boundary that fails NOW fails because the repair of the previous round changed
 	// the vector to its left -- a cascade front.  The chunks behind it would fail one per round; chunk c is therefore also
 	// flagged when one of the `spread` boundaries to its left fails (spread = overlap / chunk length: the front's reach).
@@ -1206,6 +1212,7 @@ __global__ void __launch_bounds__(128) k_mark_fwd(const Chunk *__restrict__ chun
 	}
 	if (gl == 0) {
 		flag_f[c] = fl;
+		if (fl) atomicAdd(round_cnt, 1ull);
 		if (pred_next) pred_next[c] = fl;
 		if (own) atomicAdd(&stat[0], 1ull);
 		if (own) atomicMax(last_round, (unsigned long long)(round + 1)); // the deepest round that still saw a failure: the host sizes the next E-step's rounds by it
@@ -1219,9 +1226,10 @@ __global__ void __launch_bounds__(128) k_forward_repair(const Chunk *__restrict_
                                                         const int32_t *__restrict__ flag_f, const double *__restrict__ vsub,
                                                         double *__restrict__ fhat, double *__restrict__ sc,
                                                         double *__restrict__ llsub, double *__restrict__ fwarm,
-                                                        unsigned long long *__restrict__ stat)
+                                                        unsigned long long *__restrict__ stat, const unsigned long long *__restrict__ round_cnt)
 {
 	constexpr int NP = SPL * G;
+	if (*round_cnt == 0) return;
 	const GroupId<G> id(n_sub);
 	const int s = id.c, gl = id.gl, s0 = gl * SPL;
 	const int pc = parent[s];
@@ -1975,7 +1983,8 @@ template <int SPL>
 __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chunks, int n_chunks, int N, double eps,
                                                   const double *__restrict__ bwarm, const double *__restrict__ bexact,
                                                   int32_t *__restrict__ flag_b, unsigned long long *__restrict__ stat,
-                                                  int32_t *__restrict__ pred_next, unsigned long long *__restrict__ last_round, int spread, int round)
+                                                  int32_t *__restrict__ pred_next, unsigned long long *__restrict__ last_round, int spread, int round,
+                                                  unsigned long long *__restrict__ round_cnt)
 {
 	// (spread: see k_mark_fwd; the backward cascade runs to the left, so chunk c looks at the boundaries to its right)
 	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1991,6 +2000,7 @@ __global__ void __launch_bounds__(128) k_mark_bwd(const Chunk *__restrict__ chun
 	}
 	if (gl == 0) {
 		flag_b[c] = fl;
+		if (fl) atomicAdd(round_cnt, 1ull);
 		if (pred_next) pred_next[c] = fl;
 		if (own) atomicAdd(&stat[2], 1ull);
 		if (own) atomicMax(last_round, (unsigned long long)(round + 1));
@@ -2005,9 +2015,10 @@ __global__ void __launch_bounds__(128) k_backward_repair(const Chunk *__restrict
                                                          const double *__restrict__ fhat, const double *__restrict__ sc,
                                                          double *__restrict__ partsub, double *__restrict__ bwarm,
                                                          double *__restrict__ bexact, unsigned long long *__restrict__ stat,
-                                                         double *__restrict__ ghat)
+                                                         double *__restrict__ ghat, const unsigned long long *__restrict__ round_cnt)
 {
 	constexpr int NP = SPL * G;
+	if (*round_cnt == 0) return;
 	const GroupId<G> id(n_sub);
 	const int s = id.c, gl = id.gl, s0 = gl * SPL;
 	const int pc = parent[s];
