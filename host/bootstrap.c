@@ -346,9 +346,12 @@ int psmch_bootstrap_run(const psmch_opts_t *o, const psmch_seqs_t *sq, int n_rep
 		double e_ms = 0.0, m_ms = 0.0;
 		if (psmch_space_init(&hdr, o->pattern ? o->pattern : "4+5*3+4", 0, o->alpha0) != 0) { free(bw); free(th); free(w); free(buf); free(len); free(ms); return -1; }
 		if (B <= 0) B = auto_batch(o, sq, hdr.n + 1, bslots);
-		per = (n_rep + nw - 1) / nw; /* no point in batches larger than a worker's share */
-		if (B > per) B = per;
+		per = (n_rep + nw - 1) / nw; /* a worker's share: split it into equal batches (13 replicates = 7 + 6, not 11 + 2) */
 		if (B < 1) B = 1;
+		{
+			const int nb = (per + B - 1) / B;
+			B = (per + nb - 1) / nb;
+		}
 		psmch_space_free(&hdr);
 		if (cores < 1) cores = 1;
 		for (i = 0; i < nw; ++i) {
