@@ -1467,7 +1467,7 @@ static int launch_models(psmc_b200_ctx *c, int n_rep, const psmc_b200_model *mod
 		for (int v = 0; v < c->n_vseq && all; ++v) all = !c->probe_cum[c->vseq_seq[v]].empty();
 		if (all) due = false;
 	}
-	c->probe_now = c->probe_on && (!c->batch || c->probe_batch) && !c->dense && c->warm_len > 0 && c->n_k1 > 0 && c->chunk_len_req <= 0 && due;
+	c->probe_now = c->probe_on && (!c->batch || c->probe_batch) && c->warm_len > 0 && c->n_k1 > 0 && c->chunk_len_req <= 0 && due;
 	if (c->probe_now) {
 		const int64_t need = (c->cap_bins >> 6) + c->n_chunks + 2;
 		if (need > c->cap_probeK) {
