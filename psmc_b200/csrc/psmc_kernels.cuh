@@ -1569,7 +1569,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsign
 
 template <int SPL, int G>
 struct BackwardStaged {
-	static constexpr int NP = SPL * G, ROWS = 8, STAGES = 3;
+#ifndef PSMC_BWD_ROWS
+#define PSMC_BWD_ROWS 8   /* rows per tile; the loop body is unrolled ROWS times (measured: 4 rows x 6 stages is 3 % slower although the 8-row body is 41 KB of code) */
+#define PSMC_BWD_STAGES 3 /* tiles in flight per chunk: (STAGES - 1) * ROWS rows of look-ahead */
+#endif
+	static constexpr int NP = SPL * G, ROWS = PSMC_BWD_ROWS, STAGES = PSMC_BWD_STAGES;
 	static constexpr int TILE_BYTES = ROWS * NP * 8 + ROWS * 8;      // rows, then their scale factors
 	static constexpr int GROUP_BYTES = STAGES * TILE_BYTES;
 	static constexpr int GROUPS_PER_BLOCK = 128 / G;

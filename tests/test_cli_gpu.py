@@ -81,6 +81,7 @@ def test_config2_25_iterations_inside_the_reference_spread(tmp_path):
                                                          dev[k] / spread[k] if spread.get(k) else 0.0))
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):
+        open(os.path.join(out_dir, "c2_gpu.psmc"), "w").write("\n".join(got) + "\n")
         json.dump({"after_round": {str(k): v for k, v in rounds.items()}, "all_rounds": dev, "reference_spread": spread},
                   open(os.path.join(out_dir, "c2_deviations.json"), "w"), indent=1)
     assert dev["LK"] <= 1e-7

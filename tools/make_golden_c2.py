@@ -7,7 +7,8 @@
        * the same sources compiled with FMA contraction (gcc -O2 -mfma -ffp-contract=fast) and with -O3,
        * the same records in a different order (changes only hmm_add_expect's summation order, khmm.c:346-359):
          c2 cut into 5 records by the reference's own splitfa, run as is and reversed.
-     Per tag (LK, TR, MT, RS lambda / pi / A columns) the largest relative deviation over all rounds between two such runs.
+     Per tag (LK, TR, MT, RS lambda / pi / A columns) the largest relative deviation over all rounds between two such runs
+     (tests/psmc_text.py:deviations; one unit in the sixth printed decimal is not counted).
      This is the band inside which "matches the reference" is meaningful; tests/test_cli_gpu.py holds the GPU build to it.
 
 Runs the reference ~5 times for 25 iterations on 500 k bins (about 3-4 minutes each, in parallel).  Dev container only
@@ -27,7 +28,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle.pyoracle import Ref  # noqa: E402
 from psmc_b200 import psmcfa, synth  # noqa: E402
-from psmc_text import fields, parse  # noqa: E402
+from psmc_text import deviations, parse  # noqa: E402
 
 G = os.path.join(ROOT, "tests", "golden")
 REF = "/root/reference"
@@ -46,26 +47,6 @@ def build_variant(tmp, name, flags):
 def run(binary, fa, out):
     subprocess.run([binary] + ARGS + ["-o", out, fa], check=True, stderr=subprocess.DEVNULL)
     return parse(out)
-
-
-def deviations(a, b):
-    """largest relative deviation per tag (RS split by column) between two .psmc texts with the same line structure"""
-    worst = {}
-    assert len(a) == len(b)
-    for la, lb in zip(a, b):
-        ta, fa_ = fields(la); tb, fb = fields(lb)
-        assert ta == tb
-        if ta not in ("LK", "TR", "MT", "RS", "QD", "RI"):
-            continue
-        for j, (x, y) in enumerate(zip(fa_, fb)):
-            try:
-                x = float(x); y = float(y)
-            except ValueError:
-                continue
-            key = ta if ta != "RS" else "RS.%s" % ["k", "t_k", "lambda_k", "pi_k", "sum_A_kl", "A_kk"][j]
-            d = abs(x - y) / max(abs(y), 1e-300) if y != 0 else abs(x)
-            worst[key] = max(worst.get(key, 0.0), d)
-    return worst
 
 
 def main():
