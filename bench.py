@@ -472,7 +472,7 @@ def run_own(args):
                "clocks": clocks,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             # dram__bytes_read+write of k_forward + k_backward per bin from the committed ncu --set full capture
-                            # (profiles/r01_gen2_ncu_full.txt: 3.687 GB + 3.759 GB over 7 187 491 bins), scaled to this launch
+                            # (profiles/r02_ncu_full.txt: k_forward 3.680 GB written + k_backward_staged 3.755 GB read over 7 187 491 bins), scaled to this launch
                             "traffic": 1036.0 * my_bins / 1e9, "traffic_unit": "GB per E-step (k_forward + k_backward; ncu, scaled per bin)",
                             "kernel": "whole E-step (all kernels of one iteration on rank 0; dominant: %s)" % names[dom],
                             "algorithmic_bytes_per_bin": alg_bytes_per_bin, "bins_per_launch": my_bins, "peak_source": peak_src,

@@ -66,9 +66,8 @@ def full(rep, out):
             cur["hdr"] = r
         elif cur is not None and r:
             cur["rows"].append(r)
-    seen = set()
     with open(out, "w") as fo:
-        for r in rows[2:]:
+        for ki, r in enumerate(rows[2:]):
             d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
             fo.write("--- %s\n" % d["Kernel Name"][:150])
             for k in WANT:
@@ -77,17 +76,13 @@ def full(rep, out):
             st = {k: v for k, v in d.items() if "smsp__average_warps_issue_stalled" in k and "_per_issue_active" in k and "not_issued" not in k}
             top = sorted(((float(v) if v not in ("", "n/a") else 0.0, k) for k, v in st.items()), reverse=True)[:8]
             fo.write("  top stalls (warps per issue): " + ", ".join("%s %.2f" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v) for v, k in top) + "\n")
-            for b in blocks:
-                if b["name"][:60] != d["Kernel Name"][:60] or b["name"] in seen:
-                    continue
-                seen.add(b["name"])
+            for b in blocks[ki:ki + 1]:   # (the source page lists the kernels in the same order)
                 h = b["hdr"]; ia, isrc, ins, iex = h.index("Address"), h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
                 tot = sum(int(x[ins] or 0) for x in b["rows"]) or 1
                 fo.write("  hottest instructions (stall samples; wait / short_scoreboard / long_scoreboard / math_pipe):\n")
                 for x in sorted(b["rows"], key=lambda x: -int(x[ins] or 0))[:12]:
                     fo.write("    %-58s %5.1f%%  exec %9s  wait %5s short %5s long %5s math %5s\n" % (x[isrc][:58], 100 * int(x[ins]) / tot, x[iex], x[h.index("stall_wait")],
                              x[h.index("stall_short_sb")], x[h.index("stall_long_sb")], x[h.index("stall_math")]))
-                break
 
 
 if __name__ == "__main__":
