@@ -70,7 +70,7 @@ def make_genome(scale=1.0, lengths=None):
     return seqs
 
 
-from psmc_b200.sharding import lpt_shards  # noqa: E402
+from psmc_b200.sharding import broadcast_params, lpt_shards  # noqa: E402
 
 
 class ClockSampler:
@@ -386,7 +386,7 @@ def run_own(args):
             if rank == 0:
                 em.mstep()
                 par_t.copy_(torch.from_numpy(em.state()["params"]))
-            dist.broadcast(par_t, 0)
+            broadcast_params(par_t, 0)
             if rank != 0:
                 em.set_params(par_t.cpu().numpy())
 

@@ -1,6 +1,7 @@
 """Multi-GPU data parallelism of the E-step: whole contigs are the unit, assigned to ranks by
 longest-processing-time-first; the only exchange is one sum all-reduce of the raw statistics vector
-[LL | E0(N) E1(N) | RL CL RU CU AD] (7N+1 doubles) per EM iteration, after which every rank runs the same M-step."""
+[LL | E0(N) E1(N) | RL CL RU CU AD] (7N+1 doubles) per EM iteration, after which rank 0 runs the M-step (it is a serial
+search; replicating it on every rank of one host only makes the ranks fight for cores) and broadcasts the parameters."""
 import numpy as np
 
 
@@ -30,3 +31,10 @@ def all_reduce_raw(raw_tensor, group=None):
     import torch.distributed as dist
     dist.all_reduce(raw_tensor, op=dist.ReduceOp.SUM, group=group)
     return raw_tensor
+
+
+def broadcast_params(params_tensor, src=0, group=None):
+    """parameters found by the M-step on rank `src` -> every rank (NCCL on GPUs, gloo in the CPU tests)"""
+    import torch.distributed as dist
+    dist.broadcast(params_tensor, src, group=group)
+    return params_tensor

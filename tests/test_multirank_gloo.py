@@ -46,8 +46,15 @@ def _worker(rank, world, port, out_dir):
     assert lib.psmc_b200_unpack_stats(m["N"], arr.ctypes.data_as(C.POINTER(C.c_double)), len(seqs), C.byref(buf.c)) == 0
     st = buf.result()
     res = host.mstep(m["pattern"], m["params"], st["E"], marg=st)
+    # the exchange bench.py uses from round 2 on: the M-step's result of rank 0 is broadcast, the other ranks rebuild their
+    # model from it (here: every rank also ran the search, so the broadcast value can be checked against the local one)
+    from psmc_b200.sharding import broadcast_params
+    bp = torch.from_numpy(res["params"].copy() if rank == 0 else np.zeros_like(res["params"]))
+    broadcast_params(bp, 0)
+    mod_b = host.model_from_params(m["pattern"], bp.numpy())["model"]
+    mod_l = host.model_from_params(m["pattern"], res["params"])["model"]
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), LL=st["LL"], E=st["E"], RL=st["RL"], params=res["params"], Q1=res["Q1"],
-             owner=np.array(owner))
+             owner=np.array(owner), bparams=bp.numpy(), same_model=np.array([np.array_equal(mod_b.U, mod_l.U) and np.array_equal(mod_b.D, mod_l.D)]))
     dist.destroy_process_group()
 
 
@@ -61,6 +68,7 @@ def test_two_ranks_equal_one_process(oracle, tmp_path):
     for k in ("LL", "E", "RL", "params", "Q1"):
         assert np.array_equal(r0[k], r1[k]), k                     # all-reduce result and M-step identical on both ranks
     assert set(r0["owner"].tolist()) == {0, 1}
+    assert np.array_equal(r1["bparams"], r0["params"]) and bool(r1["same_model"][0])   # rank 1 received rank 0's parameters
     m = make_model(oracle, 23, seed=9)
     seqs = synth.simulate_genome(m["a0"], m["a"], m["e"], [3000, 800, 2500, 1200, 50], seed=10)
     one = oracle.estep(m["a"], m["e"], m["a0"], seqs)
