@@ -32,6 +32,58 @@ static int n_threads(void)
 	return c < 1 ? 1 : (c > 32 ? 32 : (int)c);
 }
 
+/* ---- one thread per GPU: the contexts decode their sequences concurrently ---- */
+typedef struct {
+	psmc_b200_ctx *ctx;
+	const psmc_b200_model *mv;
+	uint32_t what;
+	int rc;
+	char err[256];
+	int64_t nr;
+	int32_t *rs, *rst, *rl;
+	uint8_t *rk;
+	double *rm;
+	psmc_b200_info inf;
+} gpu_job_t;
+
+static void *gpu_thread(void *arg)
+{
+	gpu_job_t *j = (gpu_job_t*)arg;
+	j->rc = psmc_b200_decode_run(j->ctx, j->mv, j->what);
+	if (j->rc == 0 && (j->what & PSMC_B200_DEC_RUNS)) {
+		j->rc = psmc_b200_decode_get_runs(j->ctx, 0, 0, 0, 0, 0, 0, &j->nr);
+		if (j->rc == 0) {
+			j->rs = (int32_t*)malloc(sizeof(int32_t) * (j->nr + 1)); j->rst = (int32_t*)malloc(sizeof(int32_t) * (j->nr + 1));
+			j->rl = (int32_t*)malloc(sizeof(int32_t) * (j->nr + 1)); j->rk = (uint8_t*)malloc(j->nr + 1); j->rm = (double*)malloc(sizeof(double) * (j->nr + 1));
+			j->rc = psmc_b200_decode_get_runs(j->ctx, j->nr, j->rs, j->rst, j->rl, j->rk, j->rm, &j->nr);
+		}
+	}
+	if (j->rc != 0) snprintf(j->err, sizeof(j->err), "%s", psmc_b200_last_error()); /* (the message is per thread) */
+	else psmc_b200_get_info(j->ctx, &j->inf);
+	return 0;
+}
+
+/* runs `what` on every context that holds sequences; returns 0 or the first error (message on stderr) */
+static int decode_all_gpus(psmch_em_t *em, const int *cnt, const psmc_b200_model *mv, uint32_t what, gpu_job_t *job, double *gpu_ms, double *dec_ms)
+{
+	pthread_t th[16];
+	int g, rc = 0;
+	const double t0 = now_ms();
+	for (g = 0; g < em->n_gpus; ++g) {
+		memset(&job[g], 0, sizeof(job[g]));
+		job[g].ctx = em->ctx[g]; job[g].mv = mv; job[g].what = what;
+		if (cnt[g] > 0) pthread_create(&th[g], 0, gpu_thread, &job[g]);
+	}
+	for (g = 0; g < em->n_gpus; ++g) {
+		if (cnt[g] == 0) continue;
+		pthread_join(th[g], 0);
+		if (job[g].rc != 0 && rc == 0) { rc = job[g].rc; fprintf(stderr, "psmc: GPU decode failed on device slot %d: %s\n", g, job[g].err); }
+		if (job[g].inf.decode_ms[0] + job[g].inf.decode_ms[1] > *gpu_ms) *gpu_ms = job[g].inf.decode_ms[0] + job[g].inf.decode_ms[1]; /* concurrent: the slowest GPU */
+	}
+	*dec_ms += now_ms() - t0;
+	return rc;
+}
+
 /* ---- DC: one buffer per sequence, formatted in parallel, written in order ---- */
 typedef struct {
 	const psmch_seqs_t *sq;
@@ -165,20 +217,13 @@ int psmch_decode(const psmch_opts_t *o, psmch_em_t *em, const psmch_seqs_t *sq, 
 		char **buf = (char**)calloc(sq->n_seqs > 0 ? sq->n_seqs : 1, sizeof(char*));
 		size_t *blen = (size_t*)calloc(sq->n_seqs > 0 ? sq->n_seqs : 1, sizeof(size_t));
 		pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
-		for (g = 0; g < em->n_gpus && rc == 0; ++g) { /* every GPU decodes its sequences; only the runs come back */
-			psmc_b200_info inf;
-			if (cnt[g] == 0) continue;
-			if ((rc = psmc_b200_decode_run(em->ctx[g], &mv, PSMC_B200_DEC_RUNS)) != 0 ||
-			    (rc = psmc_b200_decode_get_runs(em->ctx[g], 0, 0, 0, 0, 0, 0, &nr[g])) != 0) break;
-			rs[g] = (int32_t*)malloc(sizeof(int32_t) * (nr[g] + 1)); rst[g] = (int32_t*)malloc(sizeof(int32_t) * (nr[g] + 1));
-			rl[g] = (int32_t*)malloc(sizeof(int32_t) * (nr[g] + 1)); rk[g] = (uint8_t*)malloc(nr[g] + 1); rm[g] = (double*)malloc(sizeof(double) * (nr[g] + 1));
-			if ((rc = psmc_b200_decode_get_runs(em->ctx[g], nr[g], rs[g], rst[g], rl[g], rk[g], rm[g], &nr[g])) != 0) break;
-			psmc_b200_get_info(em->ctx[g], &inf);
-			gpu_ms += inf.decode_ms[0] + inf.decode_ms[1]; dec_ms += inf.decode_ms[2];
+		gpu_job_t job[16];
+		rc = decode_all_gpus(em, cnt, &mv, PSMC_B200_DEC_RUNS, job, &gpu_ms, &dec_ms); /* every GPU decodes its sequences; only the runs come back */
+		for (g = 0; g < em->n_gpus; ++g) {
+			rs[g] = job[g].rs; rst[g] = job[g].rst; rl[g] = job[g].rl; rk[g] = job[g].rk; rm[g] = job[g].rm; nr[g] = job[g].nr;
 			tot += nr[g];
 		}
-		if (rc != 0) fprintf(stderr, "psmc: GPU decode failed: %s\n", psmc_b200_last_error());
-		else {
+		if (rc == 0) {
 			/* runs of all contexts in global sequence order (a context returns its sequences in its own order) */
 			st = (int32_t*)malloc(sizeof(int32_t) * (tot + 1)); ln = (int32_t*)malloc(sizeof(int32_t) * (tot + 1));
 			ks = (uint8_t*)malloc(tot + 1); mp = (double*)malloc(sizeof(double) * (tot + 1));
@@ -212,14 +257,8 @@ int psmch_decode(const psmch_opts_t *o, psmch_em_t *em, const psmch_seqs_t *sq, 
 		for (g = 0; g < 16; ++g) { free(rs[g]); free(rst[g]); free(rl[g]); free(rk[g]); free(rm[g]); }
 		free(first); free(st); free(ln); free(ks); free(mp); free(buf); free(blen);
 	} else { /* -D */
-		for (g = 0; g < em->n_gpus && rc == 0; ++g) {
-			psmc_b200_info inf;
-			if (cnt[g] == 0) continue;
-			if ((rc = psmc_b200_decode_run(em->ctx[g], &mv, PSMC_B200_DEC_POST)) != 0) break;
-			psmc_b200_get_info(em->ctx[g], &inf);
-			gpu_ms += inf.decode_ms[0] + inf.decode_ms[1]; dec_ms += inf.decode_ms[2];
-		}
-		if (rc != 0) fprintf(stderr, "psmc: GPU decode failed: %s\n", psmc_b200_last_error());
+		gpu_job_t job[16];
+		rc = decode_all_gpus(em, cnt, &mv, PSMC_B200_DEC_POST, job, &gpu_ms, &dec_ms);
 		for (i = 0; i < sq->n_seqs && rc == 0; ++i) {
 			const psmch_seq_t *s = sq->seqs + i;
 			const int L = s->L, line = 32 + 7 * N, blk = 16384;

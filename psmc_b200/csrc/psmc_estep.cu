@@ -1980,6 +1980,7 @@ extern "C" int psmc_b200_set_warm(psmc_b200_ctx *c, int32_t warm_len, double eps
 	if (warm_len >= 0) {
 		c->warm_len = warm_len;
 		c->warm_len_bwd = warm_len + warm_len / 3;
+		if (c->have_probe || c->planned) c->plan_dirty = true; // the planned overlaps are capped relative to the fixed one: re-plan
 	}
 	if (eps > 0) c->cert_eps = eps;
 	return 0;

@@ -516,9 +516,17 @@ __device__ __forceinline__ double chain_fwd_step(const double *__restrict__ Tc, 
 	__syncthreads();
 	vec[i] = (v > 0.0) ? scalbn(v, ex - emax) : 0.0;
 	__syncthreads();
-	double acc = 0.0;
-#pragma unroll 8
-	for (int j = 0; j < NP; ++j) acc = fma(__ldg(Tc + (size_t)j * NP + i), vec[j], acc);
+	// four independent accumulators: the chain kernels are pure latency (one block walks a run of operators), and a single
+	// accumulator serialises NP dependent FMAs behind NP loads
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+	for (int j = 0; j < NP; j += 4) {
+		a0 = fma(__ldg(Tc + (size_t)j * NP + i), vec[j], a0);
+		a1 = fma(__ldg(Tc + (size_t)(j + 1) * NP + i), vec[j + 1], a1);
+		a2 = fma(__ldg(Tc + (size_t)(j + 2) * NP + i), vec[j + 2], a2);
+		a3 = fma(__ldg(Tc + (size_t)(j + 3) * NP + i), vec[j + 3], a3);
+	}
+	const double acc = (a0 + a1) + (a2 + a3);
 	const double tot = block_sum<NP>(acc, red);
 	return acc / tot;
 }
@@ -532,9 +540,15 @@ __device__ __forceinline__ double chain_bwd_step(const double *__restrict__ Tc, 
 	__syncthreads();
 	vec[i] = b;
 	__syncthreads();
-	double d = 0.0;
-#pragma unroll 8
-	for (int j = 0; j < NP; ++j) d = fma(__ldg(col + j), vec[j], d);
+	double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll 4
+	for (int j = 0; j < NP; j += 4) {
+		d0 = fma(__ldg(col + j), vec[j], d0);
+		d1 = fma(__ldg(col + j + 1), vec[j + 1], d1);
+		d2 = fma(__ldg(col + j + 2), vec[j + 2], d2);
+		d3 = fma(__ldg(col + j + 3), vec[j + 3], d3);
+	}
+	const double d = (d0 + d1) + (d2 + d3);
 	const int ex = Texc[i];
 	int e = (d > 0.0) ? ex + ilogb(d) : INT_MIN;
 	const int emax = block_max_i<NP>(e, redi);
