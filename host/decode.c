@@ -72,11 +72,14 @@ static int decode_all_gpus(psmch_em_t *em, const int *cnt, const psmc_b200_model
 	for (g = 0; g < em->n_gpus; ++g) {
 		memset(&job[g], 0, sizeof(job[g]));
 		job[g].ctx = em->ctx[g]; job[g].mv = mv; job[g].what = what;
-		if (cnt[g] > 0) pthread_create(&th[g], 0, gpu_thread, &job[g]);
+		if (cnt[g] > 0) {
+			if (em->n_gpus > 1) pthread_create(&th[g], 0, gpu_thread, &job[g]);
+			else gpu_thread(&job[g]); /* (one GPU: stay on the thread that owns the CUDA state) */
+		}
 	}
 	for (g = 0; g < em->n_gpus; ++g) {
 		if (cnt[g] == 0) continue;
-		pthread_join(th[g], 0);
+		if (em->n_gpus > 1) pthread_join(th[g], 0);
 		if (job[g].rc != 0 && rc == 0) { rc = job[g].rc; fprintf(stderr, "psmc: GPU decode failed on device slot %d: %s\n", g, job[g].err); }
 		if (job[g].inf.decode_ms[0] + job[g].inf.decode_ms[1] > *gpu_ms) *gpu_ms = job[g].inf.decode_ms[0] + job[g].inf.decode_ms[1]; /* concurrent: the slowest GPU */
 	}
