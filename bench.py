@@ -330,9 +330,14 @@ def run_own(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: NCCL prints its version banner to file descriptor 1 on some hosts
+    # whatever NCCL_DEBUG_FILE says, so descriptor 1 points at stderr until the line is ready
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line and nothing else
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
@@ -501,6 +506,8 @@ def run_own(args):
                 out["decode"] = run_decode(args, fa, total_bins, world)
             except Exception as e:
                 out["decode"] = {"error": str(e)[:300]}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)
         if store is not None:
             store.set("bench_extras_done", "1")
