@@ -1537,6 +1537,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// orders the generic-proxy reads of a stage (already consumed, warp-synchronised) before the async-proxy write that refills it
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
@@ -1555,6 +1557,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 struct EmuBar { int32_t tx; int16_t arrivals, phases; };
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { EmuBar *b = (EmuBar *)bar; b->tx = 0; b->arrivals = (int16_t)count; b->phases = 0; }
 __device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void proxy_fence_async() {}
 __device__ __forceinline__ void emu_bar_check(EmuBar *b, int count) { if (b->arrivals <= 0 && b->tx == 0) { b->arrivals = (int16_t)count; ++b->phases; } }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { EmuBar *b = (EmuBar *)bar; b->tx += (int32_t)bytes; --b->arrivals; }
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
@@ -1720,7 +1723,10 @@ struct BackwardStaged {
 				step(u, ulast - u, b, fm, sm);
 			}
 			__syncwarp(); // every lane of the group has consumed this stage: its first lane may refill it
-			if (gl == 0 && k + STAGES < my_tiles) issue(tile_top - (k + STAGES), stage);
+			if (gl == 0 && k + STAGES < my_tiles) {
+				proxy_fence_async();
+				issue(tile_top - (k + STAGES), stage);
+			}
 		}
 		if (valid) {
 			double *po = part_c + s0;
