@@ -450,6 +450,7 @@ def run_own(args):
         # algorithmic bytes per bin and EM iteration: forward spill write + re-read, scale factors, 2-bit obs twice
         NST = 64
         alg_bytes_per_bin = 16 * NST + 16.5
+        FP64_LANE_INSTR_PER_BIN = 122 * 32 // 4 + 130 * 32 // 2     # 976 forward + 2080 backward
         my_bins = sum(len(s) for s in mine)
         estep_ms = float(mean_ms[5])
         dom = int(np.argmax(mean_ms[:5])); names = ["transfer", "chain", "forward", "backward", "reduce"]
@@ -481,7 +482,14 @@ def run_own(args):
                             "traffic": 1036.0 * my_bins / 1e9, "traffic_unit": "GB per E-step (k_forward + k_backward; ncu, scaled per bin)",
                             "kernel": "whole E-step (all kernels of one iteration on rank 0; dominant: %s)" % names[dom],
                             "algorithmic_bytes_per_bin": alg_bytes_per_bin, "bins_per_launch": my_bins, "peak_source": peak_src,
-                            "estep_ms": estep_ms, "kernels": per_kernel},
+                            "estep_ms": estep_ms, "kernels": per_kernel,
+                            # the pipe that actually limits these kernels: FP64 instructions per lane and bin counted in the
+                            # SASS of the two hot loops (k_forward<8,8,2> stored bin: 122 warp instructions per 4 chunks; k_backward_staged<4,16>:
+                            # 130 per 2 chunks; overlap and repair work NOT counted), against the DFMA issue rate measured on B200
+                            # (profiles/r01_ubench_b200.txt: 34 TFLOP/s = 17e12 lane instructions/s)
+                            "fp64": {"lane_instr_per_bin": FP64_LANE_INSTR_PER_BIN, "achieved_Tinstr_s": FP64_LANE_INSTR_PER_BIN * my_bins / (estep_ms * 1e-3) / 1e12,
+                                     "peak_Tinstr_s": 17.0, "frac": FP64_LANE_INSTR_PER_BIN * my_bins / (estep_ms * 1e-3) / 17.0e12,
+                                     "pipe_active_pct_ncu": {"k_forward": 46.6, "k_backward_staged": 47.5, "source": "profiles/r02_ncu_full.txt"}}},
                "estep": {"bins_per_s": total_bins / (estep_ms * 1e-3) if world == 1 else None, "ms": estep_ms,
                          "mstep_ms": st["t_mstep_ms"], "hj_calls": st["hj_calls"], "chunks": inf["n_chunks"], "chunk_len": inf["chunk_len"], "fast_path": inf},
                "final": {"lk": st["lk"], "theta": float(st["params"][0]), "rho": float(st["params"][1])}}
