@@ -168,6 +168,10 @@ struct psmc_b200_ctx {
 	bool redoing = false;
 	int slots_fwd = 0, slots_bwd = 0; // resident chunks per SM of the chosen forward / backward kernels
 	int g_bww = 8;              // lanes per chunk in the backward warm-up kernel (PSMC_B200_G_BWW)
+	bool g2_fwd_auto = true;    // small shards (multi-GPU runs, single short contigs): fewer than g2_fwd_auto_max chunks per SM leave schedulers
+	int g2_fwd_auto_max = 8;    // idle with 8-lane groups; 16-lane groups then give every chunk twice the lanes (measured on B200: -9 % forward at 3.6 M bins, +15 % at 7 M)
+	// (never with a fixed chunk length, multiplicities or a batch: there a replicate's result does not depend on how it was scheduled, bit for bit)
+	bool wide_fwd(int NP_) const { return gen == 2 && (g2_fwd == 16 || NP_ > 64 || (g2_fwd_auto && chunk_len_req <= 0 && !batch && !weighted && n_chunks <= g2_fwd_auto_max * sm_count)); }
 	int g2_fwd = 8, g2_bww = 8; // generation 2: lanes per chunk of the forward / backward warm-up kernels at NP <= 64 (PSMC_B200_G2_FWD / _BWW: 8 or 16)
 	bool dense = false;         // psmc_b200_set_dense: the backward pass also stores the rows g_u for psmc_b200_dense_counts
 	bool dense_valid = false;   // ghat holds the rows of the last E-step
@@ -874,6 +878,9 @@ extern "C" int psmc_b200_create(psmc_b200_ctx **out, int32_t n_seqs, const int32
 		if (env && atoi(env) > 0) c->probe_hmax = atoi(env);
 		env = getenv("PSMC_B200_G2_FWD");
 		if (env && atoi(env) == 16) c->g2_fwd = 16;
+		if (env && atoi(env) == 8) c->g2_fwd_auto = false;
+		env = getenv("PSMC_B200_G2_FWD_AUTO"); // chunks per SM up to which the forward kernel switches to 16-lane groups (0 = never)
+		if (env && atoi(env) >= 0) c->g2_fwd_auto_max = atoi(env);
 		env = getenv("PSMC_B200_G2_BWW");
 		if (env && atoi(env) == 16) c->g2_bww = 16;
 		env = getenv("PSMC_B200_G_FWD");
@@ -1144,7 +1151,7 @@ static void run_forward(psmc_b200_ctx *c, int warm, int use_prev)
 {
 	cudaStream_t st = c->stream;
 #define FWD(G_, V_) LAUNCH((k_forward<NP / G_, G_, V_>), blocks_for(c->n_chunks, G_), 128, st, c->d_chunks, c->n_chunks, c->d_obs, c->d_model, c->d_vstart, warm, use_prev, c->d_fhat, c->d_sc, c->d_llpart, c->d_fwarm, (c->planned && warm > 0 && !use_prev) ? c->d_warm_f : nullptr)
-	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWD(16, 2);
+	if (c->wide_fwd(NP)) FWD(16, 2);
 	else if (c->gen == 2) FWD(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWD(8, 1);
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWD(16, 1);
@@ -1156,7 +1163,7 @@ static void run_forward_repair(psmc_b200_ctx *c, const unsigned long long *rcnt)
 {
 	cudaStream_t st = c->stream;
 #define FWR(G_, V_) LAUNCH((k_forward_repair<NP / G_, G_, V_>), blocks_for(c->n_sub, G_), 128, st, c->d_sub, c->n_sub, c->d_sub_parent, c->d_chunk_sub0, c->d_obs, c->d_model, c->d_flag + 1, c->d_vsub, c->d_fhat, c->d_sc, c->d_llsub, c->d_fwarm, c->d_cert + 4, rcnt)
-	if (c->gen == 2 && (c->g2_fwd == 16 || NP > 64)) FWR(16, 2);
+	if (c->wide_fwd(NP)) FWR(16, 2);
 	else if (c->gen == 2) FWR(8, 2);
 	else if (c->g_fwd == 8 && NP / 8 <= 8) FWR(8, 1);
 	else if (c->g_fwd <= 16 && NP / 16 <= 8) FWR(16, 1);

@@ -88,6 +88,27 @@ def test_emulated_warmup_certificate_and_repair(oracle, emu, N, warm):
         assert info["repaired_fwd"] == 0 and info["repaired_bwd"] == 0
 
 
+@pytest.mark.parametrize("N", [23, 64])
+@pytest.mark.parametrize("warm", [0, 60])
+def test_emulated_sixteen_lane_groups_for_forward_and_overlap_kernels(oracle, emu_plain, monkeypatch, N, warm):
+    """PSMC_B200_G2_FWD / PSMC_B200_G2_BWW = 16: the forward, forward-repair and backward-overlap kernels with 16-lane groups
+    (2 or 4 states per lane instead of 4 or 8) -- a tuning knob for small shards, same results"""
+    from psmc_b200 import EStep
+    monkeypatch.setenv("PSMC_B200_G2_FWD", "16")
+    monkeypatch.setenv("PSMC_B200_G2_BWW", "16")
+    m = make_model(oracle, N, seed=41)
+    seqs = _seqs(m, [2000, 700, 33, 1], seed=42)
+    want = oracle_stats(oracle, m, seqs)
+    with EStep(seqs, N, chunk_len=300) as es:
+        es.set_warm(warm)
+        got = es.run(_model(m))
+        info = es.info()
+    compare_stats(got, want, TOL, N)
+    assert info["fallbacks"] == 0
+    if warm:
+        assert info["repaired_fwd"] > 0
+
+
 def test_emulated_chunking_is_exact(oracle, emu_plain):
     from psmc_b200 import EStep
     N = 64
