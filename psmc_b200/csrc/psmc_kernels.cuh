@@ -1674,6 +1674,41 @@ struct BackwardStaged {
 		}
 	}
 
+	// the same transition for a bin strictly inside its chunk (every lane group of the warp: u0 < u < ulast, u > 0, no save
+	// point): no activity predicates, no branches around the accumulation
+	__device__ __forceinline__ void step_interior(int u, int t_of_chunk, double (&b)[SPL], const double (&fm)[SPL], double sm)
+	{
+		const int v = u - 1;
+		if ((v & 15) == 15) {
+			word = wprev;
+			wprev = __ldg(obs + ch.ow0 + max((v >> 4) - 1, 0));
+		}
+		const int xm = (word >> ((v & 15) * 2)) & 3;
+		double g[SPL], Pg[SPL], Sg[SPL], Pf[SPL], Sf[SPL], c0, c1;
+		emis_coef(xu, c0, c1);
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) g[i] = fma(c1, M.e0[i], c0) * b[i];
+		prefsuf2<SPL, G>(g, M.V, M.Z, ds, Pg, Sg);
+		prefsuf2<SPL, G>(fm, M.W, M.U, ds, Pf, Sf);
+		if (grow) store_vec<SPL>(grow - (size_t)t_of_chunk * NP, g);
+		const double inv = fast_rcp(sm);
+		const double w0 = (xm == 0) ? 1.0 : 0.0, w1 = (xm == 1) ? 1.0 : 0.0;
+#pragma unroll
+		for (int i = 0; i < SPL; ++i) {
+			aRL[i] = fma(fm[i], Pg[i], aRL[i]);
+			aRU[i] = fma(fm[i], Sg[i], aRU[i]);
+			aAD[i] = fma(fm[i], g[i], aAD[i]);
+			aCL[i] = fma(g[i], Sf[i], aCL[i]);
+			aCU[i] = fma(g[i], Pf[i], aCU[i]);
+			const double bb = fma(M.U[i], Pg[i], fma(M.W[i], Sg[i], M.D[i] * g[i]));
+			const double gam = fm[i] * bb;
+			aE0[i] = fma(gam, w0, aE0[i]);
+			aE1[i] = fma(gam, w1, aE1[i]);
+			b[i] = bb * inv;
+		}
+		xu = xm;
+	}
+
 	__device__ __forceinline__ void run(double (&b)[SPL], double *__restrict__ part_c)
 	{
 #pragma unroll
@@ -1703,6 +1738,29 @@ struct BackwardStaged {
 			if (k < my_tiles) mbar_wait(&bars[stage], parity, err_flag);
 			const double *rows = (const double *)(tiles + (size_t)stage * TILE_BYTES);
 			const double *scs = rows + ROWS * NP;
+			{ // bulk of the chunk: all ROWS bins of this tile strictly inside the chunk, for every lane group of the warp
+				const int u_hi = (int)(rtop - (int64_t)k * ROWS - ch.gb0) + ch.u0 + 1, u_lo = u_hi - (ROWS - 1);
+				const bool inner = valid && k < my_tiles && u_hi < ulast && u_lo > max(ch.u0, 0) && !(bsave_c && usave >= u_lo && usave <= u_hi);
+				if (!__any_sync(FULLMASK, !inner)) {
+#pragma unroll
+					for (int i = 0; i < ROWS; ++i) {
+						double fm[SPL];
+						const double *rp = rows + (size_t)(ROWS - 1 - i) * NP + s0;
+#pragma unroll
+						for (int q = 0; q < SPL; q += 2) {
+							const double2 t2 = *reinterpret_cast<const double2 *>(rp + q);
+							fm[q] = t2.x; fm[q + 1] = t2.y;
+						}
+						step_interior(u_hi - i, ulast - (u_hi - i), b, fm, scs[ROWS - 1 - i]);
+					}
+					__syncwarp();
+					if (gl == 0 && k + STAGES < my_tiles) {
+						proxy_fence_async();
+						issue(tile_top - (k + STAGES), stage);
+					}
+					continue;
+				}
+			}
 #pragma unroll
 			for (int i = 0; i < ROWS; ++i) {
 				const int64_t row = rtop - ((int64_t)k * ROWS + i);   // f row of this step
