@@ -506,11 +506,11 @@ def run_own(args):
                             "estep_ms": estep_ms, "kernels": per_kernel,
                             # the pipe that actually limits these kernels: FP64 instructions per lane and bin counted in the
                             # SASS of the two hot loops (k_forward<8,8,2> stored bin: 122 warp instructions per 4 chunks; k_backward_staged<4,16>:
-                            # 130 per 2 chunks; overlap and repair work NOT counted), against the DFMA issue rate measured on B200
+                            # 130 of the 216 per 2 chunks; overlap and repair work NOT counted), against the DFMA issue rate measured on B200
                             # (profiles/r01_ubench_b200.txt: 34 TFLOP/s = 17e12 lane instructions/s)
                             "fp64": {"lane_instr_per_bin": FP64_LANE_INSTR_PER_BIN, "achieved_Tinstr_s": FP64_LANE_INSTR_PER_BIN * my_bins / (estep_ms * 1e-3) / 1e12,
                                      "peak_Tinstr_s": 17.0, "frac": FP64_LANE_INSTR_PER_BIN * my_bins / (estep_ms * 1e-3) / 17.0e12,
-                                     "pipe_active_pct_ncu": {"k_forward": 46.6, "k_backward_staged": 47.5, "source": "profiles/r02_ncu_full.txt"}}},
+                                     "pipe_active_pct_ncu": {"k_forward": 51.0, "k_backward_staged": 56.5, "source": "profiles/r02_ncu_full.txt"}}},
                "estep": {"bins_per_s": total_bins / (estep_ms * 1e-3) if world == 1 else None, "ms": estep_ms,
                          "mstep_ms": st["t_mstep_ms"], "hj_calls": st["hj_calls"], "chunks": inf["n_chunks"], "chunk_len": inf["chunk_len"], "fast_path": inf},
                "final": {"lk": st["lk"], "theta": float(st["params"][0]), "rho": float(st["params"][1])}}
