@@ -1,4 +1,4 @@
-"""host/fq2psmcfa (consensus FASTQ -> .psmcfa) against the UNMODIFIED reference utility.
+"""host/fq2psmcfa (consensus FASTQ -> .psmcfa) and host/splitfa against the UNMODIFIED reference utilities.
 
 Golden outputs under tests/golden/fq/ were printed by oracle/_ref/fq2psmcfa (utils/fq2psmcfa.c compiled as it lies in the
 reference tree; tools/make_golden_fq.py) for every option the utility has; the bar is byte identity.  Where the reference
@@ -15,7 +15,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "tests", "golden", "fq")
 MINE = os.path.join(ROOT, "host", "fq2psmcfa")
 REF = os.path.join(ROOT, "oracle", "_ref", "fq2psmcfa")
-INDEX = json.load(open(os.path.join(G, "index.json")))
+ALL = json.load(open(os.path.join(G, "index.json")))
+INDEX = {k: v for k, v in ALL.items() if v.get("tool") != "splitfa"}
+SPLIT = {k: v for k, v in ALL.items() if v.get("tool") == "splitfa"}
+MINE_SPLIT = os.path.join(ROOT, "host", "splitfa")
+REF_SPLIT = os.path.join(ROOT, "oracle", "_ref", "splitfa")
 
 
 def run(binary, args, inp=None, stdin=None):
@@ -104,3 +108,45 @@ def test_random_inputs_against_the_reference_binary(tmp_path):
         rc_m, out_m, _ = run(MINE, args, str(p))
         assert rc_r == rc_m == 0
         assert out_m == out_r, (trial, args)
+
+
+@pytest.mark.parametrize("golden", sorted(SPLIT))
+def test_splitfa_matches_reference_output_byte_for_byte(golden):
+    meta = SPLIT[golden]
+    want = gzip.open(os.path.join(G, golden), "rb").read()
+    rc, got, err = run(MINE_SPLIT, [os.path.join(G, meta["input"])] + meta["args"])
+    assert rc == 0, err
+    assert got == want and got.count(b">") == meta["records"]
+
+
+def test_splitfa_pieces_are_what_psmc_split_uses(tmp_path):
+    """the standalone tool and `psmc --split` (in memory, host/bootstrap.c) cut at the same places"""
+    from psmc_b200 import psmcfa
+    src = os.path.join(G, "cons_fq.s1.psmcfa.gz")
+    rc, got, _ = run(MINE_SPLIT, [src, "2000"])
+    p = tmp_path / "s.psmcfa"
+    p.write_bytes(got)
+    _, pieces = psmcfa.read_psmcfa(str(p))
+    _, whole = psmcfa.read_psmcfa(src)
+    want = []
+    for s in whole:          # splitfa.c:24-29 restated
+        i = 0
+        while i < len(s):
+            if len(s) - i < 2000 * 3 // 2:
+                want.append(len(s) - i); break
+            want.append(min(2000, len(s) - i)); i += 2000
+    assert [len(x) for x in pieces] == want
+    assert np.array_equal(np.concatenate(pieces), np.concatenate(whole))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SPLIT), reason="reference utility not built here (oracle/_ref/splitfa)")
+def test_splitfa_random_inputs_against_the_reference_binary(tmp_path):
+    rng = np.random.default_rng(11)
+    for trial in range(30):
+        kind = "fq" if trial % 3 == 0 else "fa"
+        p = tmp_path / ("t%d.%s" % (trial, kind))
+        p.write_bytes(_random_input(rng, kind))
+        t = str(int(rng.integers(1, 3000)))
+        rc_r, out_r, _ = run(REF_SPLIT, [str(p), t])
+        rc_m, out_m, _ = run(MINE_SPLIT, [str(p), t])
+        assert rc_r == rc_m == 0 and out_m == out_r, (trial, t)

@@ -15,6 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tests", "golden", "fq")
 REF = os.path.join(ROOT, "oracle", "_ref", "fq2psmcfa")
+REF_SPLIT = os.path.join(ROOT, "oracle", "_ref", "splitfa")
 
 # option sets: every mask rule, quality / block / good-base thresholds, the pseudo-autosomal mask
 G = ["-g", "300"]   # (the default, 10000 good bases, drops most of these small records: kept in "default" only)
@@ -87,6 +88,15 @@ def main():
             with gzip.open(os.path.join(OUT, name + ".gz"), "wb", compresslevel=9) as f:
                 f.write(r.stdout)
             index[name + ".gz"] = {"input": inp, "args": args, "records": r.stdout.count(b">"), "bytes": len(r.stdout)}
+    # utils/splitfa.c on two of the files just written (trunk sizes around the 1.5-trunk remainder rule) and on a FASTQ
+    for inp, trunks in (("cons_fq.s1.psmcfa.gz", ["2000", "601", "30050", "20034"]), ("cons_fq.g300.psmcfa.gz", ["50", "1"]), ("cons.fq.gz", ["4000"]), ("cons.fa", [])):
+        for t in trunks or [None]:
+            r = subprocess.run([REF_SPLIT, os.path.join(OUT, inp)] + ([t] if t else []), capture_output=True)
+            assert r.returncode == 0, r.stderr
+            name = "split.%s.%s.psmcfa.gz" % (inp.replace(".gz", "").replace(".", "_"), t or "default")
+            with gzip.open(os.path.join(OUT, name), "wb", compresslevel=9) as f:
+                f.write(r.stdout)
+            index[name] = {"tool": "splitfa", "input": inp, "args": [t] if t else [], "records": r.stdout.count(b">"), "bytes": len(r.stdout)}
     json.dump(index, open(os.path.join(OUT, "index.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(index, indent=1))
 
