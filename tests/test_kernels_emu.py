@@ -389,8 +389,9 @@ def test_emulated_mixing_probe_plans_the_overlaps(oracle, emu_plain, monkeypatch
             i["failed_fwd"], i["failed_bwd"], i["repair_rounds"]) for i in infos])
 
 
+@pytest.mark.parametrize("chunk_len", [17, 61, 200])   # 2, 7 and 25 tiles of 8 rows per chunk: all-edge, mixed, mostly the branch-free interior body
 @pytest.mark.parametrize("N", [23, 64])
-def test_emulated_staged_backward_equals_register_ring(oracle, emu_plain, monkeypatch, N):
+def test_emulated_staged_backward_equals_register_ring(oracle, emu_plain, monkeypatch, N, chunk_len):
     """the backward pass with the forward spill staged through shared memory (bulk-asynchronous copies + mbarrier, the
     default) performs the same arithmetic as the register-prefetch variant: same bits, ragged records, dense option included"""
     from psmc_b200 import EStep
@@ -399,7 +400,7 @@ def test_emulated_staged_backward_equals_register_ring(oracle, emu_plain, monkey
     res = {}
     for tma in ("0", "1"):
         monkeypatch.setenv("PSMC_B200_TMA", tma)
-        with EStep(seqs, N, chunk_len=61) as es:
+        with EStep(seqs, N, chunk_len=chunk_len) as es:
             es.set_warm(150)
             es.set_dense(True)
             res[tma] = (es.run(_model(m)), es.dense_counts())
